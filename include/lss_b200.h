@@ -1,0 +1,213 @@
+/*
+ * lss_b200.h  --  C ABI of the B200-native lift-splat library (liblss_b200.so, sm_100a only).
+ *
+ * Drop-in boundary for ONE path of shdragron/LSS-Carla: frustum geometry + lift + splat, forward and
+ * backward (BASELINE.json north_star).  The reference has no FFI of its own -- the
+ * path is Python calling stock ATen ops -- so every entry point below names the reference function
+ * (file:line under the reference root) whose work it replaces; `INTEGRATION.md` shows the ctypes stub
+ * and the `src/models.py` patch a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats, one POD struct; no torch / C++ types cross this boundary.
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; the caller owns all memory,
+ *     including workspaces (sizes from lss_plan_layout); nothing is allocated or freed inside.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it; no call synchronises
+ *     the device or the stream, so every call is CUDA-graph capturable.
+ *   - return value: LSS_OK (0) or a negative lss_status; no exceptions, no global state, re-entrant
+ *     (distinct plans may be used from distinct streams concurrently).
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points return LSS_ERR_CUDA.
+ *   - float tensors are IEEE binary32, C-contiguous in the stated shape unless strides are passed.
+ *
+ * Point / voxel numbering
+ *   point  p = (((b*N + n)*D + d)*fH + h)*fW + w          "flat (b,n,d,h,w) index", models.py:205-213
+ *   voxel  v = ((b*nz + iz)*nx + ix)*ny + iy               dense id used by the library (-1 = dropped)
+ *   rank     = ix*(ny*nz*B) + iy*(nz*B) + iz*B + b         the reference's sort key, models.py:226-229
+ *   BEV element (b, iz*C + c, ix, iy), shape [B, nz*C, nx, ny]                      models.py:240-244
+ */
+#ifndef LSS_B200_H
+#define LSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSS_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum lss_status {
+    LSS_OK = 0,
+    LSS_ERR_BAD_ARG = -1,     /* null pointer, non-positive dimension, inconsistent sizes            */
+    LSS_ERR_ALIGN = -2,       /* a pointer is not aligned as documented (16 B for float rows)        */
+    LSS_ERR_UNSUPPORTED = -3, /* dimensions outside the compiled limits (see lss_limits)             */
+    LSS_ERR_CUDA = -4,        /* a CUDA runtime call failed (launch error, no device, ...)           */
+    LSS_ERR_WORKSPACE = -5    /* workspace pointer null / too small for this problem                 */
+} lss_status;
+
+/* Problem description.  Mirrors what LiftSplatShoot.__init__ derives from grid_conf / data_aug_conf
+ * (models.py:134-150) plus the batch shape.  `lo[k] = bx[k] - dx[k]/2` must be computed in float32 by
+ * the host exactly as the reference's tensor expression does (models.py:212). */
+typedef struct lss_problem {
+    int32_t B, N, D, fH, fW, C; /* batch, cameras, depth bins, feature map, context channels        */
+    int32_t nx, ny, nz;         /* voxel counts (gen_dx_bx, tools.py:174-179)                        */
+    float dx[3];                /* voxel size  x, y, z                                               */
+    float lo[3];                /* lower corner of voxel 0 = bx - dx/2                               */
+} lss_problem;
+
+/* BEV memory layouts.  Both describe the same logical tensor [B, nz*C, nx, ny]. */
+enum { LSS_LAYOUT_NCHW = 0,          /* contiguous, y fastest (what the reference returns)           */
+       LSS_LAYOUT_CHANNELS_LAST = 1  /* torch.channels_last strides: physical [B, nx, ny, nz*C]      */ };
+
+/* Splat accumulation modes (north_star: "atomic" and "deterministic sort-by-rank segmented sum"). */
+enum { LSS_SPLAT_SORTED = 0,      /* per voxel, ascending flat point index, sequential fp32 adds      */
+       LSS_SPLAT_SMEM_ATOMIC = 1, /* tile-owner CTAs, shared-memory atomics, order not fixed          */
+       LSS_SPLAT_RED_GLOBAL = 2   /* memset + red.global.add.f32 straight into the BEV tensor         */ };
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Introspection                                                                                   */
+/* ---------------------------------------------------------------------------------------------- */
+
+int lss_version(void);
+const char *lss_status_string(int status);
+
+/* Compiled limits: max per-sample points (N*D*fH*fW), max tile width, max D for the fused backward. */
+typedef struct lss_limits { int32_t max_points_per_sample, max_tile_cols, max_depth_bins, max_channels; } lss_limits;
+void lss_get_limits(lss_limits *out);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Plan: device-side index structures shared by forward and backward of one batch                  */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Byte offsets of the arrays inside the caller-allocated plan workspace (all 256-B aligned). */
+typedef struct lss_plan_layout {
+    int32_t tile_cols;      /* TY: BEV columns (iy) owned by one CTA tile, multiple of 8             */
+    int32_t tiles_per_row;  /* ceil(ny / TY)                                                         */
+    int32_t n_tiles;        /* B * nz * nx * tiles_per_row                                           */
+    int64_t n_points;       /* B*N*D*fH*fW                                                           */
+    size_t off_vox;         /* int32 [n_points]   dense voxel id or -1                               */
+    size_t off_entries;     /* uint32[n_points]   bucketed (col << 20 | point-in-sample), per tile   */
+    size_t off_tile_start;  /* int32 [n_tiles+1]  exclusive prefix of per-tile kept-point counts     */
+    size_t off_tile_count;  /* int32 [n_tiles]    scratch, all-zero between calls                    */
+    size_t off_cursor;      /* int32 [n_tiles]    scratch                                            */
+    size_t off_sync;        /* int32 [64]         scratch counters, all-zero between calls           */
+    size_t bytes;           /* total workspace size                                                  */
+} lss_plan_layout;
+
+/* Fill `out` for problem `p`.  tile_cols <= 0 selects the default. Host-only, no CUDA calls. */
+int lss_plan_layout_init(const lss_problem *p, int tile_cols, lss_plan_layout *out);
+
+/* Zero the scratch counters of a freshly allocated (or possibly dirty) workspace. */
+int lss_plan_reset(const lss_plan_layout *L, void *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Geometry and voxel indices                                                                      */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Device-side replacement of the two host round trips in get_geometry (models.py:180,186):
+ *   M1 = inverse(post_rots), M2 = rots @ inverse(intrins), closed-form adjugate inverse, fp32.
+ * NOT bit-identical to the LAPACK inverse the reference calls on the CPU; the bit-exact contract of
+ * this library starts at (M1, M2), which the Python layer by default prepares with the reference's
+ * own torch calls.  rots/intrins/post_rots/M1/M2: f32[B*N,3,3]. */
+int lss_calib_matrices(int32_t n_cams, const float *rots, const float *intrins, const float *post_rots,
+                       float *M1, float *M2, void *stream);
+
+/* LiftSplatShoot.get_geometry (models.py:170-190) given the prepared matrices.
+ *   frustum f32[D,fH,fW,3] (the model's `frustum` parameter, models.py:157-168)
+ *   post_trans, trans f32[B*N,3]; M1, M2 f32[B*N,3,3]
+ *   geom_out f32[B,N,D,fH,fW,3]
+ * Bit-exact w.r.t. the reference on CPU: un-fused fp32, rows as (a0*v0 + a1*v1) + a2*v2. */
+int lss_geometry(const lss_problem *p, const float *frustum, const float *post_trans, const float *M1,
+                 const float *M2, const float *trans, float *geom_out, void *stream);
+
+/* Quantise + mask + (optionally) dump what voxel_pooling derives per point (models.py:212-229).
+ * Either `geom` (f32[n_points,3], the `geom_feats` argument of voxel_pooling) is given, or it is null
+ * and the calibration set (frustum, post_trans, M1, M2, trans) is used to evaluate the geometry in
+ * registers (fused path; the geometry tensor is never written).
+ * Outputs (each may be null): vox int32[n_points]; idx int64[n_points,3] (ix,iy,iz, truncation toward
+ * zero, INT64_MIN for non-finite); kept uint8[n_points]; rank int64[n_points] (-1 where dropped). */
+int lss_voxel_index(const lss_problem *p, const float *geom, const float *frustum,
+                    const float *post_trans, const float *M1, const float *M2, const float *trans,
+                    int32_t *vox, int64_t *idx, uint8_t *kept, int64_t *rank, void *stream);
+
+/* Build the plan for one batch: voxel ids (as lss_voxel_index, from `geom` or from calibration),
+ * per-tile buckets of kept points, each bucket sorted by (column, flat point index) -- i.e. the
+ * reference's stable `ranks.argsort()` order inside every voxel (models.py:230).
+ * Replaces models.py:212-231.  `sorted` = 0 skips the in-bucket sort (enough for the atomic modes and
+ * for the backward pass). */
+int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *geom,
+                   const float *frustum, const float *post_trans, const float *M1, const float *M2,
+                   const float *trans, int sorted, void *stream);
+
+/* Parity dump: the reference's sort permutation.  order_out int64[n_points] receives, for
+ * i < n_kept, the flat point index of the i-th element of `x[kept][sorts]` (models.py:222-231), and -1
+ * for i >= n_kept; n_kept_out int32[1].  Needs a plan built with sorted=1.  scratch int32[n_ranks+1]
+ * with n_ranks = B*nx*ny*nz. */
+int lss_plan_reference_order(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
+                             int32_t *scratch, int64_t *order_out, int32_t *n_kept_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Lift + splat, fused level (depthnet output in, BEV out; the B*N*D*fH*fW*C tensor never exists)  */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* CamEncode.get_depth_dist + the operand layout of get_depth_feat (models.py:49-61):
+ *   depthnet_out f32[B*N, D+C, fH, fW]  ->  prob f32[B*N, D, fH, fW] = softmax over D,
+ *                                            ctx_t f32[B*N, fH*fW, C] = context, pixel-major. */
+int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
+                     void *stream);
+
+/* voxel_pooling of the lifted features (models.py:59 outer product + :204-246), without materialising
+ * them:  bev[b, iz*C+c, ix, iy] = sum_{p in voxel} prob[p] * ctx_t[pixel(p), c].
+ * Every element of `bev` is written exactly once (zeros included): no memset, no global atomics
+ * (modes SORTED / SMEM_ATOMIC).  bev f32[B, nz*C, nx, ny] in `layout`. */
+int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
+                  const float *prob, const float *ctx_t, float *bev, int mode, int layout, void *stream);
+
+/* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
+ * autograd backward of models.py:58-59,:199-200,:240-244):
+ *   grad_depthnet f32[B*N, D+C, fH, fW]  (first D channels: logits through the softmax; last C: context)
+ * `grad_rows` is a caller workspace f32[B*nz*nx*ny, C] used only for LSS_LAYOUT_NCHW (rows of hit
+ * voxels are transposed into it); may be null for channels_last. */
+int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
+                  const float *grad_bev, int layout, const float *prob, const float *ctx_t,
+                  float *grad_rows, float *grad_depthnet, void *stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Operator level: LiftSplatShoot.voxel_pooling(geom_feats, x) with a materialised x                */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* x f32 with logical shape [B,N,D,fH,fW,C] and element strides xs[6] (it usually arrives as a permuted
+ * view, models.py:199-200).  bev as above.  Replaces models.py:204-246 given a plan built from `geom`. */
+int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
+                          const float *x, const int64_t *xs_host, float *bev, int mode, int layout,
+                          void *stream);
+
+/* grad_x f32[n_points, C] contiguous: row p = grad_bev[b, iz*C:(iz+1)*C, ix, iy] of p's voxel, or 0. */
+int lss_voxel_pooling_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
+                          const float *grad_bev, int layout, float *grad_rows, float *grad_x,
+                          void *stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Operator level: tools.QuickCumsum / tools.cumsum_trick (tools.py:182-219)                        */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Pass 1: run structure of an already sorted rank vector.  run_id int32[n] = index of the run each
+ * element belongs to; n_runs int32[1] (device).  scratch int32[lss_quickcumsum_scratch_elems(n)]. */
+size_t lss_quickcumsum_scratch_elems(int64_t n);
+int lss_quickcumsum_runs(int64_t n, const int64_t *ranks, int32_t *run_id, int32_t *n_runs,
+                         int32_t *scratch, void *stream);
+/* Pass 2 (after the caller read n_runs to size the outputs, as the reference's boolean indexing does,
+ * tools.py:200):  sums f32[n_runs, C] = per-run sequential sum of x rows (x f32[n, C], row stride
+ * `x_row_stride` elements); geom_out int64[n_runs, 4] = geom_feats row of each run's LAST element.
+ * `scratch` is the buffer lss_quickcumsum_runs filled (it holds the run offsets). */
+int lss_quickcumsum_fwd(int64_t n, int32_t C, const float *x, int64_t x_row_stride,
+                        const int64_t *geom_feats, const int32_t *scratch, int32_t n_runs, float *sums,
+                        int64_t *geom_out, void *stream);
+/* Backward = gather (tools.py:212-219): grad_x[i, :] = grad_sums[run_id[i], :]. */
+int lss_quickcumsum_bwd(int64_t n, int32_t C, const float *grad_sums, const int32_t *run_id,
+                        float *grad_x, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSS_B200_H */

@@ -1,0 +1,126 @@
+"""ctypes binding of liblss_b200.so (the C ABI declared in include/lss_b200.h).
+
+The library is built in-tree by ``build_library()`` (``nvcc -gencode arch=compute_100a,code=sm_100a``).
+There is no CPU fallback: ``lib()`` raises if the shared object is missing, and every compute call
+raises ``RuntimeError`` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+SO_PATH = os.path.join(_PKG, "liblss_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+SOURCES = ["plan.cu", "lift.cu", "splat.cu", "ops.cu"]
+HEADER = os.path.join(_ROOT, "include", "lss_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class LssProblem(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("fH", C.c_int32), ("fW", C.c_int32),
+                ("C", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("dx", C.c_float * 3), ("lo", C.c_float * 3)]
+
+
+class LssPlanLayout(C.Structure):
+    _fields_ = [("tile_cols", C.c_int32), ("tiles_per_row", C.c_int32), ("n_tiles", C.c_int32),
+                ("n_points", C.c_int64), ("off_vox", C.c_size_t), ("off_entries", C.c_size_t),
+                ("off_tile_start", C.c_size_t), ("off_tile_count", C.c_size_t), ("off_cursor", C.c_size_t),
+                ("off_sync", C.c_size_t), ("bytes", C.c_size_t)]
+
+
+class LssLimits(C.Structure):
+    _fields_ = [("max_points_per_sample", C.c_int32), ("max_tile_cols", C.c_int32),
+                ("max_depth_bins", C.c_int32), ("max_channels", C.c_int32)]
+
+
+LAYOUT_NCHW, LAYOUT_CHANNELS_LAST = 0, 1
+SPLAT_SORTED, SPLAT_SMEM_ATOMIC, SPLAT_RED_GLOBAL = 0, 1, 2
+SPLAT_MODES = {"sorted": SPLAT_SORTED, "atomic": SPLAT_SMEM_ATOMIC, "red": SPLAT_RED_GLOBAL}
+
+_P = C.c_void_p
+_PP = C.POINTER(LssProblem)
+_PL = C.POINTER(LssPlanLayout)
+
+# name -> (restype, argtypes); must list every symbol include/lss_b200.h declares
+SIGNATURES = {
+    "lss_version": (C.c_int, []),
+    "lss_status_string": (C.c_char_p, [C.c_int]),
+    "lss_get_limits": (None, [C.POINTER(LssLimits)]),
+    "lss_plan_layout_init": (C.c_int, [_PP, C.c_int, _PL]),
+    "lss_plan_reset": (C.c_int, [_PL, _P, _P]),
+    "lss_calib_matrices": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "lss_geometry": (C.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P]),
+    "lss_voxel_index": (C.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lss_plan_build": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
+    "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P]),
+    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, _P]),
+    "lss_voxel_pooling_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P]),
+    "lss_quickcumsum_scratch_elems": (C.c_size_t, [C.c_int64]),
+    "lss_quickcumsum_runs": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P]),
+    "lss_quickcumsum_fwd": (C.c_int, [C.c_int64, C.c_int32, _P, C.c_int64, _P, _P, C.c_int32, _P, _P, _P]),
+    "lss_quickcumsum_bwd": (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into lss_carla_b200/liblss_b200.so for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), HEADER]
+    if not force and os.path.isfile(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
+        return SO_PATH
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", SO_PATH]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    global _lib
+    _lib = None
+    return SO_PATH
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  lss_carla_b200 has no CPU or PyTorch fallback for the lift-splat path.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib().lss_status_string(status).decode()
+        raise RuntimeError(f"liblss_b200: {what} failed with status {status}: {msg}")
+
+
+def header_symbols():
+    """Names of the functions declared in include/lss_b200.h (used by the export test)."""
+    import re
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lss_[a-z0-9_]+)\s*\(", txt)))

@@ -1,0 +1,120 @@
+// Shared device/host helpers for liblss_b200 (sm_100a).  See include/lss_b200.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lss_b200.h"
+
+#define LSS_FULL_MASK 0xffffffffu
+#define LSS_PIDX_BITS 20                     // point-in-sample bits of a bucket entry
+#define LSS_PIDX_MASK ((1u << LSS_PIDX_BITS) - 1u)
+#define LSS_MAX_TILE_COLS 4096               // 12 bits of column per entry
+#define LSS_MAX_DEPTH 256                    // fused backward keeps per-depth state in registers
+#define LSS_MAX_CHANNELS 256
+
+#define LSS_CHECK_LAUNCH()                                                \
+    do {                                                                  \
+        cudaError_t e__ = cudaGetLastError();                             \
+        if (e__ != cudaSuccess) return LSS_ERR_CUDA;                      \
+    } while (0)
+
+#define LSS_REQUIRE(cond, code) \
+    do {                        \
+        if (!(cond)) return (code); \
+    } while (0)
+
+static inline bool lss_aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static inline int lss_check_problem(const lss_problem *p) {
+    if (!p) return LSS_ERR_BAD_ARG;
+    if (p->B <= 0 || p->N <= 0 || p->D <= 0 || p->fH <= 0 || p->fW <= 0 || p->C <= 0) return LSS_ERR_BAD_ARG;
+    if (p->nx <= 0 || p->ny <= 0 || p->nz <= 0) return LSS_ERR_BAD_ARG;
+    for (int k = 0; k < 3; ++k)
+        if (!(p->dx[k] > 0.f)) return LSS_ERR_BAD_ARG;
+    const int64_t P = (int64_t)p->N * p->D * p->fH * p->fW;
+    if (P > (int64_t)LSS_PIDX_MASK + 1) return LSS_ERR_UNSUPPORTED;
+    if ((int64_t)p->B * P >= (int64_t)1 << 31) return LSS_ERR_UNSUPPORTED;
+    if ((int64_t)p->B * p->nx * p->ny * p->nz >= (int64_t)1 << 31) return LSS_ERR_UNSUPPORTED;
+    if (p->C > LSS_MAX_CHANNELS) return LSS_ERR_UNSUPPORTED;
+    return LSS_OK;
+}
+
+// Device copy of the problem with the derived sizes every kernel needs.
+struct Dims {
+    int B, N, D, fH, fW, C;
+    int nx, ny, nz;
+    int HW;        // fH*fW
+    int DHW;       // D*fH*fW
+    int P;         // points per sample N*D*fH*fW
+    int n_points;  // B*P
+    float dx[3], lo[3];
+};
+
+static inline Dims make_dims(const lss_problem *p) {
+    Dims d;
+    d.B = p->B; d.N = p->N; d.D = p->D; d.fH = p->fH; d.fW = p->fW; d.C = p->C;
+    d.nx = p->nx; d.ny = p->ny; d.nz = p->nz;
+    d.HW = p->fH * p->fW;
+    d.DHW = p->D * d.HW;
+    d.P = p->N * d.DHW;
+    d.n_points = p->B * d.P;
+    for (int k = 0; k < 3; ++k) { d.dx[k] = p->dx[k]; d.lo[k] = p->lo[k]; }
+    return d;
+}
+
+// Tiling of the BEV grid: one CTA tile = (b, iz, ix, TY consecutive iy).
+struct Tiling {
+    int TY;       // columns per tile
+    int nty;      // tiles per (b,iz,ix) row
+    int n_tiles;
+};
+
+__host__ __device__ __forceinline__ int lss_kc_for(int C) { return (C + 31) / 32; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LSS_FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(LSS_FULL_MASK, v, o));
+    return v;
+}
+
+// dense voxel id -> element offset of its C-channel row in a BEV-shaped tensor
+//   rows workspace / NCHW-transposed rows:   v * C
+//   channels_last BEV [B, nx, ny, nz*C]:      ((b*nx+ix)*ny+iy)*(nz*C) + iz*C
+__device__ __forceinline__ size_t voxel_row_offset_cl(int v, const Dims &d) {
+    int iy = v % d.ny; int t = v / d.ny;
+    int ix = t % d.nx; t /= d.nx;
+    int iz = t % d.nz; int b = t / d.nz;
+    return ((size_t)((b * d.nx + ix) * (size_t)d.ny + iy)) * (size_t)(d.nz * d.C) + (size_t)iz * d.C;
+}
+
+// Single-CTA exclusive scan of a[0..n) in place, a[n] = total (cold paths only: parity dump, run offsets).
+static __global__ void __launch_bounds__(1024) k_scan_single(int32_t *a, int n, int32_t *total) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int x = i < n ? a[i] : 0;
+        int inc = x;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(LSS_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp[w];
+        const int excl = s_carry + woff + inc - x;
+        if (i < n) a[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { a[n] = s_carry; if (total) *total = s_carry; }
+}
+

@@ -1,0 +1,453 @@
+// Geometry, voxel indices and the per-batch plan (tile buckets sorted in the reference's rank order).
+//
+// Replaces, for the lift-splat path of shdragron/LSS-Carla:
+//   LiftSplatShoot.get_geometry          src/models.py:170-190
+//   the index half of voxel_pooling      src/models.py:212-231  (quantise, mask, rank, argsort)
+//
+// All per-point arithmetic uses the round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fsub_rn/
+// __fdiv_rn), which nvcc never contracts into FMAs, so results are bit-identical to the reference's
+// CPU evaluation (oracle/lss_oracle.py documents the measured association of the 3x3 products).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// per-point arithmetic
+// ------------------------------------------------------------------------------------------------
+
+struct CalibPtrs {
+    const float *frustum;     // [D,fH,fW,3]
+    const float *post_trans;  // [B*N,3]
+    const float *M1;          // [B*N,3,3] inverse(post_rots)
+    const float *M2;          // [B*N,3,3] rots @ inverse(intrins)
+    const float *trans;       // [B*N,3]
+};
+
+__device__ __forceinline__ float row_dot_unfused(const float *__restrict__ m, float v0, float v1, float v2) {
+    // (a0*v0 + a1*v1) + a2*v2, one rounding per operation  (models.py:180,187 as ATen's CPU bmm evaluates it)
+    return __fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + 0), v0), __fmul_rn(__ldg(m + 1), v1)), __fmul_rn(__ldg(m + 2), v2));
+}
+
+__device__ __forceinline__ void ego_point(const CalibPtrs &c, int cam, int in_cam, float out[3]) {
+    const float *fr = c.frustum + (size_t)in_cam * 3;
+    const float *pt = c.post_trans + cam * 3;
+    const float p0 = __fsub_rn(__ldg(fr + 0), __ldg(pt + 0));   // models.py:179
+    const float p1 = __fsub_rn(__ldg(fr + 1), __ldg(pt + 1));
+    const float p2 = __fsub_rn(__ldg(fr + 2), __ldg(pt + 2));
+    const float *m1 = c.M1 + cam * 9;
+    const float q0 = row_dot_unfused(m1 + 0, p0, p1, p2);       // models.py:180
+    const float q1 = row_dot_unfused(m1 + 3, p0, p1, p2);
+    const float q2 = row_dot_unfused(m1 + 6, p0, p1, p2);
+    const float r0 = __fmul_rn(q0, q2);                         // models.py:183-185
+    const float r1 = __fmul_rn(q1, q2);
+    const float *m2 = c.M2 + cam * 9;
+    const float *tr = c.trans + cam * 3;
+    out[0] = __fadd_rn(row_dot_unfused(m2 + 0, r0, r1, q2), __ldg(tr + 0));   // models.py:187-188
+    out[1] = __fadd_rn(row_dot_unfused(m2 + 3, r0, r1, q2), __ldg(tr + 1));
+    out[2] = __fadd_rn(row_dot_unfused(m2 + 6, r0, r1, q2), __ldg(tr + 2));
+}
+
+// ((g - lo) / dx).long()  with x86 semantics for values a 64-bit integer cannot hold (models.py:212)
+__device__ __forceinline__ long long quantise(float g, float lo, float dx) {
+    const float u = __fdiv_rn(__fsub_rn(g, lo), dx);
+    if (!(fabsf(u) < 9223372036854775808.0f)) return (long long)0x8000000000000000ULL;  // NaN, inf, overflow
+    return __float2ll_rz(u);
+}
+
+__device__ __forceinline__ int voxel_of_point(const Dims &d, int b, const float g[3], long long ii[3]) {
+    ii[0] = quantise(g[0], d.lo[0], d.dx[0]);
+    ii[1] = quantise(g[1], d.lo[1], d.dx[1]);
+    ii[2] = quantise(g[2], d.lo[2], d.dx[2]);
+    const bool kept = ii[0] >= 0 && ii[0] < d.nx && ii[1] >= 0 && ii[1] < d.ny && ii[2] >= 0 && ii[2] < d.nz;  // :219-221
+    if (!kept) return -1;
+    return ((b * d.nz + (int)ii[2]) * d.nx + (int)ii[0]) * d.ny + (int)ii[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: calibration matrices, geometry, voxel index (+ tile histogram)
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void inv3x3(const float *a, float *o) {
+    const float c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+    const float det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    const float r = 1.0f / det;
+    o[0] = c00 * r; o[1] = (a[2] * a[7] - a[1] * a[8]) * r; o[2] = (a[1] * a[5] - a[2] * a[4]) * r;
+    o[3] = c01 * r; o[4] = (a[0] * a[8] - a[2] * a[6]) * r; o[5] = (a[2] * a[3] - a[0] * a[5]) * r;
+    o[6] = c02 * r; o[7] = (a[1] * a[6] - a[0] * a[7]) * r; o[8] = (a[0] * a[4] - a[1] * a[3]) * r;
+}
+
+__global__ void k_calib_matrices(int n_cams, const float *__restrict__ rots, const float *__restrict__ intrins,
+                                 const float *__restrict__ post_rots, float *__restrict__ M1, float *__restrict__ M2) {
+    const int cam = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cam >= n_cams) return;
+    float a[9], inv[9];
+    for (int i = 0; i < 9; ++i) a[i] = post_rots[cam * 9 + i];
+    inv3x3(a, inv);
+    for (int i = 0; i < 9; ++i) M1[cam * 9 + i] = inv[i];
+    for (int i = 0; i < 9; ++i) a[i] = intrins[cam * 9 + i];
+    inv3x3(a, inv);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            const float *R = rots + cam * 9 + r * 3;
+            M2[cam * 9 + r * 3 + c] = __fadd_rn(__fadd_rn(__fmul_rn(R[0], inv[c]), __fmul_rn(R[1], inv[3 + c])),
+                                                __fmul_rn(R[2], inv[6 + c]));
+        }
+}
+
+__global__ void k_geometry(Dims d, CalibPtrs c, float *__restrict__ geom) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.n_points) return;
+    const int cam = p / d.DHW, in_cam = p - cam * d.DHW;
+    float g[3];
+    ego_point(c, cam, in_cam, g);
+    geom[(size_t)p * 3 + 0] = g[0];
+    geom[(size_t)p * 3 + 1] = g[1];
+    geom[(size_t)p * 3 + 2] = g[2];
+}
+
+// One thread per frustum point.  COUNT adds the per-tile histogram of kept points and, in the last CTA
+// to finish, the exclusive scan tile_count -> tile_start (and leaves tile_count / cursor zeroed).
+template <bool FROM_GEOM, bool COUNT>
+__global__ void __launch_bounds__(256)
+k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, int32_t *__restrict__ vox,
+              long long *__restrict__ idx, uint8_t *__restrict__ kept, long long *__restrict__ rank,
+              int32_t *__restrict__ tile_count, int32_t *__restrict__ tile_start, int32_t *__restrict__ cursor,
+              int32_t *__restrict__ sync) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < d.n_points;
+    int v = -1;
+    if (live) {
+        const int b = p / d.P;
+        float g[3];
+        if (FROM_GEOM) {
+            g[0] = __ldg(geom + (size_t)p * 3 + 0);
+            g[1] = __ldg(geom + (size_t)p * 3 + 1);
+            g[2] = __ldg(geom + (size_t)p * 3 + 2);
+        } else {
+            const int cam = p / d.DHW;
+            ego_point(c, cam, p - cam * d.DHW, g);
+        }
+        long long ii[3];
+        v = voxel_of_point(d, b, g, ii);
+        if (vox) vox[p] = v;
+        if (idx) { idx[(size_t)p * 3 + 0] = ii[0]; idx[(size_t)p * 3 + 1] = ii[1]; idx[(size_t)p * 3 + 2] = ii[2]; }
+        if (kept) kept[p] = v >= 0;
+        if (rank)   // models.py:226-229, int64
+            rank[p] = v >= 0 ? ii[0] * ((long long)d.ny * d.nz * d.B) + ii[1] * ((long long)d.nz * d.B) + ii[2] * d.B + b : -1;
+    }
+    if (!COUNT) return;
+
+    // ---- per-tile histogram, warp-aggregated
+    const int lane = threadIdx.x & 31;
+    int tile = -1 - lane;   // unique negative key for dropped points: singleton groups
+    if (v >= 0) {
+        const int iy = v % d.ny;
+        tile = (v / d.ny) * tl.nty + iy / tl.TY;
+    }
+    const unsigned peers = __match_any_sync(LSS_FULL_MASK, tile);
+    if (v >= 0 && lane == __ffs(peers) - 1) atomicAdd(tile_count + tile, __popc(peers));
+
+    // ---- last CTA scans the histogram
+    __shared__ int s_last;
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(sync, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    for (int base = 0; base < tl.n_tiles; base += 1024) {
+        const int i0 = base + threadIdx.x * 4;
+        int a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = (i0 + k < tl.n_tiles) ? __ldcg(tile_count + i0 + k) : 0;
+            if (i0 + k < tl.n_tiles) { tile_count[i0 + k] = 0; cursor[i0 + k] = 0; }
+        }
+        const int tsum = a[0] + a[1] + a[2] + a[3];
+        int inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(LSS_FULL_MASK, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp[w];
+        int run = s_carry + woff + inc - tsum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < tl.n_tiles) tile_start[i0 + k] = run;
+            run += a[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = run;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { tile_start[tl.n_tiles] = s_carry; *sync = 0; }
+}
+
+// Scatter kept points into their tile buckets: entries[tile_start[t] + k] = col << 20 | point-in-sample.
+__global__ void __launch_bounds__(256)
+k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, const int32_t *__restrict__ tile_start,
+               int32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int v = -1;
+    if (p < d.n_points) v = __ldg(vox + p);
+    int tile = -1 - lane, col = 0;
+    if (v >= 0) {
+        const int iy = v % d.ny;
+        const int ty = iy / tl.TY;
+        tile = (v / d.ny) * tl.nty + ty;
+        col = iy - ty * tl.TY;
+    }
+    const unsigned peers = __match_any_sync(LSS_FULL_MASK, tile);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (v >= 0 && lane == leader) base = atomicAdd(cursor + tile, __popc(peers));
+    base = __shfl_sync(LSS_FULL_MASK, base, leader);
+    if (v >= 0) {
+        const int slot = __ldg(tile_start + tile) + base + __popc(peers & ((1u << lane) - 1u));
+        entries[slot] = ((uint32_t)col << LSS_PIDX_BITS) | (uint32_t)(p % d.P);
+    }
+}
+
+// Sort every bucket by (column, point index): all comparators point the same way ("flip" bitonic
+// network), so the virtual +inf padding beyond n never moves and n need not be a power of two.
+template <typename Keys>
+__device__ __forceinline__ void bitonic_sort_block(Keys a, int n) {
+    int m = 1;
+    while (m < n) m <<= 1;
+    const int half = m >> 1;
+    for (int k = 2; k <= m; k <<= 1) {
+        const int hk = k >> 1;
+        for (int q = threadIdx.x; q < half; q += blockDim.x) {   // flip stage: i <-> i ^ (k-1)
+            const int i = (q / hk) * k + (q % hk);
+            const int l = i ^ (k - 1);
+            if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int q = threadIdx.x; q < half; q += blockDim.x) {
+                const int i = (q / j) * 2 * j + (q % j);
+                const int l = i + j;
+                if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+#define LSS_SORT_SMEM_CAP 8192   // entries sorted in shared memory (32 KB); larger buckets sort in global memory
+
+__global__ void __launch_bounds__(256)
+k_plan_sort(Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries) {
+    __shared__ uint32_t s_keys[LSS_SORT_SMEM_CAP];
+    const int t = blockIdx.x;
+    const int s = tile_start[t], n = tile_start[t + 1] - s;
+    if (n <= 1) return;
+    uint32_t *g = entries + s;
+    if (n <= LSS_SORT_SMEM_CAP) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = g[i];
+        __syncthreads();
+        bitonic_sort_block(s_keys, n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = s_keys[i];
+    } else {
+        __syncthreads();
+        bitonic_sort_block((volatile uint32_t *)g, n);   // rare: correctness fallback, L2-resident
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity dump: the reference's sort permutation (models.py:226-231)
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ int rank_of_voxel(const Dims &d, int v) {
+    const int iy = v % d.ny; int t = v / d.ny;
+    const int ix = t % d.nx; t /= d.nx;
+    const int iz = t % d.nz; const int b = t / d.nz;
+    return ((ix * d.ny + iy) * d.nz + iz) * d.B + b;
+}
+
+__device__ __forceinline__ int voxel_of_entry(const Dims &d, const Tiling &tl, int tile, uint32_t e) {
+    const int ty = tile % tl.nty;
+    return (tile / tl.nty) * d.ny + ty * tl.TY + (int)(e >> LSS_PIDX_BITS);
+}
+
+__global__ void k_fill_i32(int32_t *a, int64_t n, int32_t val) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = val;
+}
+__global__ void k_fill_i64(long long *a, int64_t n, long long val) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = val;
+}
+
+// one CTA per tile: count points per reference rank
+__global__ void k_ref_count(Dims d, Tiling tl, const int32_t *__restrict__ tile_start,
+                            const uint32_t *__restrict__ entries, int32_t *__restrict__ rank_count) {
+    const int t = blockIdx.x;
+    const int s = tile_start[t], e = tile_start[t + 1];
+    for (int i = s + threadIdx.x; i < e; i += blockDim.x)
+        atomicAdd(rank_count + rank_of_voxel(d, voxel_of_entry(d, tl, t, entries[i])), 1);
+}
+
+__global__ void k_ref_place(Dims d, Tiling tl, const int32_t *__restrict__ tile_start,
+                            const uint32_t *__restrict__ entries, const int32_t *__restrict__ rank_start,
+                            long long *__restrict__ order) {
+    const int t = blockIdx.x;
+    const int s = tile_start[t], e = tile_start[t + 1];
+    const int b = (t / tl.nty) / (d.nz * d.nx);
+    for (int i = s + threadIdx.x; i < e; i += blockDim.x) {
+        const uint32_t en = entries[i];
+        int first = i;                                   // walk back to the first entry of this voxel
+        while (first > s && (entries[first - 1] >> LSS_PIDX_BITS) == (en >> LSS_PIDX_BITS)) --first;
+        const int r = rank_of_voxel(d, voxel_of_entry(d, tl, t, en));
+        order[rank_start[r] + (i - first)] = (long long)b * d.P + (long long)(en & LSS_PIDX_MASK);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------------
+
+static inline Tiling make_tiling(const lss_plan_layout *L) {
+    Tiling t; t.TY = L->tile_cols; t.nty = L->tiles_per_row; t.n_tiles = L->n_tiles; return t;
+}
+
+extern "C" int lss_plan_layout_init(const lss_problem *p, int tile_cols, lss_plan_layout *out) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(out != nullptr, LSS_ERR_BAD_ARG);
+    if (tile_cols <= 0) tile_cols = p->ny <= 256 ? ((p->ny + 7) / 8) * 8 : 256;
+    LSS_REQUIRE(tile_cols % 8 == 0 && tile_cols <= LSS_MAX_TILE_COLS, LSS_ERR_UNSUPPORTED);
+    const Dims d = make_dims(p);
+    out->tile_cols = tile_cols;
+    out->tiles_per_row = (p->ny + tile_cols - 1) / tile_cols;
+    const int64_t nt = (int64_t)p->B * p->nz * p->nx * out->tiles_per_row;
+    LSS_REQUIRE(nt < ((int64_t)1 << 30), LSS_ERR_UNSUPPORTED);
+    out->n_tiles = (int32_t)nt;
+    out->n_points = d.n_points;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t off = 0;
+    out->off_vox = off;        off += up((size_t)d.n_points * 4);
+    out->off_entries = off;    off += up((size_t)d.n_points * 4);
+    out->off_tile_start = off; off += up(((size_t)nt + 1) * 4);
+    out->off_tile_count = off; off += up((size_t)nt * 4);
+    out->off_cursor = off;     off += up((size_t)nt * 4);
+    out->off_sync = off;       off += up(64 * 4);
+    out->bytes = off;
+    return LSS_OK;
+}
+
+extern "C" int lss_plan_reset(const lss_plan_layout *L, void *ws, void *stream) {
+    LSS_REQUIRE(L && ws, LSS_ERR_WORKSPACE);
+    cudaStream_t s = (cudaStream_t)stream;
+    char *w = (char *)ws;
+    // tile_count, cursor and sync are contiguous
+    if (cudaMemsetAsync(w + L->off_tile_count, 0, L->bytes - L->off_tile_count, s) != cudaSuccess) return LSS_ERR_CUDA;
+    return LSS_OK;
+}
+
+extern "C" int lss_calib_matrices(int32_t n_cams, const float *rots, const float *intrins, const float *post_rots,
+                                  float *M1, float *M2, void *stream) {
+    LSS_REQUIRE(n_cams > 0 && rots && intrins && post_rots && M1 && M2, LSS_ERR_BAD_ARG);
+    k_calib_matrices<<<(n_cams + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n_cams, rots, intrins, post_rots, M1, M2);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+extern "C" int lss_geometry(const lss_problem *p, const float *frustum, const float *post_trans, const float *M1,
+                            const float *M2, const float *trans, float *geom_out, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(frustum && post_trans && M1 && M2 && trans && geom_out, LSS_ERR_BAD_ARG);
+    const Dims d = make_dims(p);
+    CalibPtrs c{frustum, post_trans, M1, M2, trans};
+    k_geometry<<<(d.n_points + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d, c, geom_out);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+extern "C" int lss_voxel_index(const lss_problem *p, const float *geom, const float *frustum, const float *post_trans,
+                               const float *M1, const float *M2, const float *trans, int32_t *vox, int64_t *idx,
+                               uint8_t *kept, int64_t *rank, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    const bool from_geom = geom != nullptr;
+    LSS_REQUIRE(from_geom || (frustum && post_trans && M1 && M2 && trans), LSS_ERR_BAD_ARG);
+    const Dims d = make_dims(p);
+    CalibPtrs c{frustum, post_trans, M1, M2, trans};
+    Tiling tl{8, 1, 1};
+    const int grid = (d.n_points + 255) / 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (from_geom)
+        k_voxel_index<true, false><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, (long long *)idx, kept, (long long *)rank,
+                                                        nullptr, nullptr, nullptr, nullptr);
+    else
+        k_voxel_index<false, false><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, (long long *)idx, kept, (long long *)rank,
+                                                         nullptr, nullptr, nullptr, nullptr);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *geom,
+                              const float *frustum, const float *post_trans, const float *M1, const float *M2,
+                              const float *trans, int sorted, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
+    const bool from_geom = geom != nullptr;
+    LSS_REQUIRE(from_geom || (frustum && post_trans && M1 && M2 && trans), LSS_ERR_BAD_ARG);
+    const Dims d = make_dims(p);
+    LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
+    const Tiling tl = make_tiling(L);
+    char *w = (char *)workspace;
+    int32_t *vox = (int32_t *)(w + L->off_vox);
+    uint32_t *entries = (uint32_t *)(w + L->off_entries);
+    int32_t *tile_start = (int32_t *)(w + L->off_tile_start);
+    int32_t *tile_count = (int32_t *)(w + L->off_tile_count);
+    int32_t *cursor = (int32_t *)(w + L->off_cursor);
+    int32_t *sync = (int32_t *)(w + L->off_sync);
+    CalibPtrs c{frustum, post_trans, M1, M2, trans};
+    const int grid = (d.n_points + 255) / 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (from_geom)
+        k_voxel_index<true, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
+                                                       tile_start, cursor, sync);
+    else
+        k_voxel_index<false, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
+                                                        tile_start, cursor, sync);
+    LSS_CHECK_LAUNCH();
+    k_plan_scatter<<<grid, 256, 0, s>>>(d, tl, vox, tile_start, cursor, entries);
+    LSS_CHECK_LAUNCH();
+    if (sorted) {
+        k_plan_sort<<<tl.n_tiles, 256, 0, s>>>(tl, tile_start, entries);
+        LSS_CHECK_LAUNCH();
+    }
+    return LSS_OK;
+}
+
+extern "C" int lss_plan_reference_order(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
+                                        int32_t *scratch, int64_t *order_out, int32_t *n_kept_out, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
+    LSS_REQUIRE(scratch && order_out, LSS_ERR_BAD_ARG);
+    const Dims d = make_dims(p);
+    const Tiling tl = make_tiling(L);
+    const char *w = (const char *)workspace;
+    const uint32_t *entries = (const uint32_t *)(w + L->off_entries);
+    const int32_t *tile_start = (const int32_t *)(w + L->off_tile_start);
+    const int n_ranks = d.B * d.nx * d.ny * d.nz;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_fill_i32<<<592, 256, 0, s>>>(scratch, (int64_t)n_ranks + 1, 0);
+    k_fill_i64<<<592, 256, 0, s>>>((long long *)order_out, d.n_points, -1);
+    k_ref_count<<<tl.n_tiles, 128, 0, s>>>(d, tl, tile_start, entries, scratch);
+    k_scan_single<<<1, 1024, 0, s>>>(scratch, n_ranks, n_kept_out);
+    k_ref_place<<<tl.n_tiles, 128, 0, s>>>(d, tl, tile_start, entries, scratch, (long long *)order_out);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}

@@ -1,0 +1,376 @@
+"""Torch-facing operators of the B200 lift-splat library.
+
+PyTorch is plumbing here: it owns device memory, streams and autograd bookkeeping; all arithmetic of the
+path runs in liblss_b200.so (hand-written CUDA for sm_100a) through the C ABI of include/lss_b200.h.
+Nothing in this module falls back to ATen: CPU tensors or a missing library raise.
+
+Reference functions replaced (paths under the reference root):
+    LiftSplatShoot.get_geometry     src/models.py:170-190   -> geometry()
+    CamEncode.get_depth_feat (lift) src/models.py:49-61     -> lift_prepare() (operands only)
+    LiftSplatShoot.voxel_pooling    src/models.py:204-246   -> voxel_pooling() / lift_splat()
+    QuickCumsum / cumsum_trick      src/tools.py:182-219    -> QuickCumsum / cumsum_trick
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, LssPlanLayout, LssProblem, check, lib)
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the lift-splat path has no CPU implementation")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+@dataclass
+class Problem:
+    """Static description of one lift-splat problem (mirrors lss_problem)."""
+    B: int
+    N: int
+    D: int
+    fH: int
+    fW: int
+    C: int
+    nx: tuple
+    dx: tuple   # float32 values as python floats
+    lo: tuple   # bx - dx/2 evaluated in float32 (models.py:212)
+
+    def __post_init__(self):
+        p = LssProblem()
+        p.B, p.N, p.D, p.fH, p.fW, p.C = self.B, self.N, self.D, self.fH, self.fW, self.C
+        p.nx, p.ny, p.nz = (int(v) for v in self.nx)
+        for k in range(3):
+            p.dx[k] = self.dx[k]
+            p.lo[k] = self.lo[k]
+        self.c = p
+
+    @property
+    def n_points(self):
+        return self.B * self.N * self.D * self.fH * self.fW
+
+    @property
+    def n_voxels(self):
+        return self.B * int(self.nx[0]) * int(self.nx[1]) * int(self.nx[2])
+
+    @property
+    def bev_shape(self):
+        return (self.B, int(self.nx[2]) * self.C, int(self.nx[0]), int(self.nx[1]))
+
+    @staticmethod
+    def from_grid(B, N, D, fH, fW, C, dx, bx, nx):
+        """dx, bx: float32 tensors (any device), nx: integer tensor -- the model's parameters
+        (models.py:143-145).  `lo` is evaluated with float32 tensor ops exactly like models.py:212."""
+        dxc, bxc = dx.detach().float().cpu(), bx.detach().float().cpu()
+        lo = bxc - dxc / 2.
+        return Problem(B, N, D, fH, fW, C, tuple(int(v) for v in nx.detach().cpu().tolist()),
+                       tuple(float(v) for v in dxc.tolist()), tuple(float(v) for v in lo.tolist()))
+
+
+class Plan:
+    """Per-batch index structures (voxel ids, tile buckets) living in one workspace tensor."""
+
+    def __init__(self, prob: Problem, device, tile_cols: int = 0):
+        self.prob = prob
+        self.layout = LssPlanLayout()
+        check(lib().lss_plan_layout_init(C.byref(prob.c), tile_cols, C.byref(self.layout)), "lss_plan_layout_init")
+        self.ws = torch.zeros(self.layout.bytes, dtype=torch.uint8, device=device)   # scratch counters start at 0
+        self.sorted = False
+        self.built = False
+        self.busy = False     # True between a differentiable forward and its backward
+
+    def _view(self, off, n, dtype):
+        item = torch.empty(0, dtype=dtype).element_size()
+        return self.ws[off:off + n * item].view(dtype)
+
+    @property
+    def vox(self):
+        return self._view(self.layout.off_vox, self.prob.n_points, torch.int32)
+
+    @property
+    def entries(self):
+        return self._view(self.layout.off_entries, self.prob.n_points, torch.int32)
+
+    @property
+    def tile_start(self):
+        return self._view(self.layout.off_tile_start, self.layout.n_tiles + 1, torch.int32)
+
+    def reset(self):
+        check(lib().lss_plan_reset(C.byref(self.layout), _ptr(self.ws), _stream()), "lss_plan_reset")
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry / plan
+# ------------------------------------------------------------------------------------------------
+
+def calib_matrices_reference(rots, intrins, post_rots):
+    """M1 = inverse(post_rots), M2 = rots @ inverse(intrins) with the reference's own calls
+    (models.py:180,186): LAPACK inverse on the host, product on the device.  Bit-identical inputs for
+    the kernels, at the price of the reference's host round trip (one stream synchronisation)."""
+    M1 = torch.inverse(post_rots.cpu()).to(post_rots.device)
+    M2 = rots.matmul(torch.inverse(intrins.cpu()).to(rots.device))
+    return M1.contiguous(), M2.contiguous()
+
+
+def calib_matrices_device(rots, intrins, post_rots):
+    """Same matrices from a closed-form 3x3 inverse on the device: no host round trip, graph-capturable;
+    last-bit differences from LAPACK are possible ('inverse modes')."""
+    rots, intrins, post_rots = (_f32c(t, n) for t, n in ((rots, "rots"), (intrins, "intrins"), (post_rots, "post_rots")))
+    n_cams = rots.numel() // 9
+    M1, M2 = torch.empty_like(rots), torch.empty_like(rots)
+    check(lib().lss_calib_matrices(n_cams, _ptr(rots), _ptr(intrins), _ptr(post_rots), _ptr(M1), _ptr(M2), _stream()),
+          "lss_calib_matrices")
+    return M1, M2
+
+
+def geometry(prob: Problem, frustum, post_trans, M1, M2, trans):
+    """get_geometry (models.py:170-190) given prepared matrices -> f32[B,N,D,fH,fW,3]."""
+    frustum, post_trans, M1, M2, trans = (_f32c(t, n) for t, n in (
+        (frustum, "frustum"), (post_trans, "post_trans"), (M1, "M1"), (M2, "M2"), (trans, "trans")))
+    out = torch.empty((prob.B, prob.N, prob.D, prob.fH, prob.fW, 3), dtype=torch.float32, device=frustum.device)
+    check(lib().lss_geometry(C.byref(prob.c), _ptr(frustum), _ptr(post_trans), _ptr(M1), _ptr(M2), _ptr(trans),
+                             _ptr(out), _stream()), "lss_geometry")
+    return out
+
+
+def voxel_index(prob: Problem, geom=None, calib=None, want=("vox", "idx", "kept", "rank")):
+    """Per-point quantisation dump (models.py:212-229).  `geom` f32[...,3] or `calib` =
+    (frustum, post_trans, M1, M2, trans).  Returns dict of tensors."""
+    dev = geom.device if geom is not None else calib[0].device
+    n = prob.n_points
+    out = {}
+    if "vox" in want:
+        out["vox"] = torch.empty(n, dtype=torch.int32, device=dev)
+    if "idx" in want:
+        out["idx"] = torch.empty((n, 3), dtype=torch.int64, device=dev)
+    if "kept" in want:
+        out["kept"] = torch.empty(n, dtype=torch.uint8, device=dev)
+    if "rank" in want:
+        out["rank"] = torch.empty(n, dtype=torch.int64, device=dev)
+    g = _f32c(geom, "geom") if geom is not None else None
+    cal = [_f32c(t, "calib") for t in calib] if calib is not None else [None] * 5
+    check(lib().lss_voxel_index(C.byref(prob.c), _ptr(g), *[_ptr(t) for t in cal], _ptr(out.get("vox")),
+                                _ptr(out.get("idx")), _ptr(out.get("kept")), _ptr(out.get("rank")), _stream()),
+          "lss_voxel_index")
+    return out
+
+
+def build_plan(prob: Problem, geom=None, calib=None, sorted: bool = True, plan: Plan | None = None,
+               tile_cols: int = 0) -> Plan:
+    """Voxel ids + tile buckets (+ in-bucket sort) for one batch; replaces models.py:212-231."""
+    dev = geom.device if geom is not None else calib[0].device
+    if plan is None:
+        plan = Plan(prob, dev, tile_cols)
+    g = _f32c(geom, "geom") if geom is not None else None
+    cal = [_f32c(t, "calib") for t in calib] if calib is not None else [None] * 5
+    check(lib().lss_plan_build(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g),
+                               *[_ptr(t) for t in cal], 1 if sorted else 0, _stream()), "lss_plan_build")
+    plan.sorted = bool(sorted)
+    plan.built = True
+    plan._keepalive = (g, cal)
+    return plan
+
+
+def reference_order(plan: Plan):
+    """The reference's `sorts` (models.py:230) as flat point indices, int64[n_kept]."""
+    prob = plan.prob
+    if not plan.sorted:
+        raise RuntimeError("reference_order needs a plan built with sorted=True")
+    scratch = torch.empty(prob.n_voxels + 1, dtype=torch.int32, device=plan.ws.device)
+    order = torch.empty(prob.n_points, dtype=torch.int64, device=plan.ws.device)
+    nk = torch.empty(1, dtype=torch.int32, device=plan.ws.device)
+    check(lib().lss_plan_reference_order(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(scratch),
+                                         _ptr(order), _ptr(nk), _stream()), "lss_plan_reference_order")
+    return order[: int(nk.item())]
+
+
+# ------------------------------------------------------------------------------------------------
+# lift + splat
+# ------------------------------------------------------------------------------------------------
+
+def lift_prepare(prob: Problem, depthnet_out):
+    """softmax over depth + pixel-major context (models.py:49-61) -> (prob [BN,D,fH,fW], ctx_t [BN,HW,C])."""
+    x = _f32c(depthnet_out, "depthnet_out")
+    BN, HW = prob.B * prob.N, prob.fH * prob.fW
+    if tuple(x.shape) != (BN, prob.D + prob.C, prob.fH, prob.fW):
+        raise ValueError(f"depthnet_out has shape {tuple(x.shape)}, expected {(BN, prob.D + prob.C, prob.fH, prob.fW)}")
+    pr = torch.empty((BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device)
+    ct = torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device)
+    check(lib().lss_lift_prepare(C.byref(prob.c), _ptr(x), _ptr(pr), _ptr(ct), _stream()), "lss_lift_prepare")
+    return pr, ct
+
+
+def _empty_bev(prob: Problem, device, channels_last: bool):
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    return torch.empty(prob.bev_shape, dtype=torch.float32, device=device, memory_format=fmt)
+
+
+def _bev_layout(t):
+    """Layout code of a BEV-shaped tensor, making it dense in one of the two supported formats."""
+    if t.is_contiguous():
+        return t, LAYOUT_NCHW
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return t, LAYOUT_CHANNELS_LAST
+    return t.contiguous(), LAYOUT_NCHW
+
+
+def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False):
+    if mode == "sorted" and not plan.sorted:
+        raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
+    bev = _empty_bev(prob, pr.device, channels_last)
+    check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct), _ptr(bev),
+                              SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW, _stream()),
+          "lss_splat_fwd")
+    return bev
+
+
+def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None):
+    g, layout = _bev_layout(_f32c_keep(grad_bev))
+    if layout == LAYOUT_NCHW and grad_rows is None:
+        grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
+    out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
+    check(lib().lss_splat_bwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), layout, _ptr(pr), _ptr(ct),
+                              _ptr(grad_rows), _ptr(out), _stream()), "lss_splat_bwd")
+    return out
+
+
+def _f32c_keep(t):
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError("expected a float32 CUDA tensor")
+    return t
+
+
+class _LiftSplatFn(torch.autograd.Function):
+    """depthnet output [B*N, D+C, fH, fW] -> BEV [B, nz*C, nx, ny]; backward = fused gather."""
+
+    @staticmethod
+    def forward(ctx, depthnet_out, prob, plan, mode, channels_last):
+        pr, ct = lift_prepare(prob, depthnet_out)
+        bev = splat_fwd(prob, plan, pr, ct, mode, channels_last)
+        ctx.prob, ctx.plan = prob, plan
+        ctx.save_for_backward(pr, ct)
+        plan.busy = bool(ctx.needs_input_grad[0])
+        return bev
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        pr, ct = ctx.saved_tensors
+        out = splat_bwd(ctx.prob, ctx.plan, grad_bev, pr, ct)
+        ctx.plan.busy = False
+        return out, None, None, None, None
+
+
+def lift_splat(depthnet_out, prob: Problem, plan: Plan, mode="sorted", channels_last=False):
+    """Fused lift + splat of the depthnet output through an existing plan (differentiable w.r.t.
+    `depthnet_out`; geometry carries no gradient, tools.py:207)."""
+    return _LiftSplatFn.apply(depthnet_out, prob, plan, mode, channels_last)
+
+
+class _VoxelPoolingFn(torch.autograd.Function):
+    """Operator-level voxel_pooling(geom_feats, x) with a materialised x (models.py:204-246)."""
+
+    @staticmethod
+    def forward(ctx, x, prob, plan, mode, channels_last):
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("x must be a float32 CUDA tensor")
+        strides = (C.c_int64 * 6)(*x.stride())
+        bev = _empty_bev(prob, x.device, channels_last)
+        check(lib().lss_voxel_pooling_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(x), strides,
+                                          _ptr(bev), SPLAT_MODES[mode],
+                                          LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW, _stream()),
+              "lss_voxel_pooling_fwd")
+        ctx.prob, ctx.plan, ctx.xshape = prob, plan, tuple(x.shape)
+        return bev
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        prob, plan = ctx.prob, ctx.plan
+        g, layout = _bev_layout(_f32c_keep(grad_bev))
+        rows = None
+        if layout == LAYOUT_NCHW:
+            rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
+        gx = torch.empty(ctx.xshape, dtype=torch.float32, device=g.device)
+        check(lib().lss_voxel_pooling_bwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), layout,
+                                          _ptr(rows), _ptr(gx), _stream()), "lss_voxel_pooling_bwd")
+        return gx, None, None, None, None
+
+
+def voxel_pooling(geom_feats, x, dx, bx, nx, mode="sorted", channels_last=False, plan=None):
+    """Drop-in for LiftSplatShoot.voxel_pooling(geom_feats, x) (models.py:204-246).
+
+    geom_feats f32[B,N,D,H,W,3], x f32[B,N,D,H,W,C] (any strides) -> f32[B, nz*C, nx, ny]."""
+    B, N, D, H, W, Cc = x.shape
+    prob = Problem.from_grid(B, N, D, H, W, Cc, dx, bx, nx)
+    plan = build_plan(prob, geom=geom_feats, sorted=(mode == "sorted"), plan=plan)
+    return _VoxelPoolingFn.apply(x, prob, plan, mode, channels_last)
+
+
+# ------------------------------------------------------------------------------------------------
+# QuickCumsum / cumsum_trick (tools.py:182-219)
+# ------------------------------------------------------------------------------------------------
+
+class QuickCumsum(torch.autograd.Function):
+    """Same signature and return values as the reference's `QuickCumsum.apply(x, geom_feats, ranks)`:
+    x f32[n, C] and geom_feats i64[n, 4] sorted by `ranks` i64[n] -> (sums f32[V, C], geom i64[V, 4]),
+    V = number of distinct ranks; each run keeps the coordinates of its LAST point (tools.py:198-200)."""
+
+    @staticmethod
+    def forward(ctx, x, geom_feats, ranks):
+        if not x.is_cuda:
+            raise RuntimeError("QuickCumsum: CUDA tensors required (no CPU implementation)")
+        n, Cc = x.shape
+        x = x.float()
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        geom_feats = geom_feats.contiguous().long()
+        ranks = ranks.contiguous().long()
+        L = lib()
+        run_id = torch.empty(max(n, 1), dtype=torch.int32, device=x.device)
+        n_runs = torch.zeros(1, dtype=torch.int32, device=x.device)
+        scratch = torch.empty(L.lss_quickcumsum_scratch_elems(n), dtype=torch.int32, device=x.device)
+        check(L.lss_quickcumsum_runs(n, _ptr(ranks), _ptr(run_id), _ptr(n_runs), _ptr(scratch), _stream()),
+              "lss_quickcumsum_runs")
+        V = int(n_runs.item())      # data-dependent output size: same sync as the reference's x[kept]
+        sums = torch.empty((V, Cc), dtype=torch.float32, device=x.device)
+        gout = torch.empty((V, geom_feats.shape[1]), dtype=torch.int64, device=x.device)
+        if geom_feats.shape[1] != 4:
+            raise ValueError("geom_feats must have 4 columns (ix, iy, iz, b)")
+        check(L.lss_quickcumsum_fwd(n, Cc, _ptr(x), x.stride(0), _ptr(geom_feats), _ptr(scratch), V, _ptr(sums),
+                                    _ptr(gout), _stream()), "lss_quickcumsum_fwd")
+        ctx.save_for_backward(run_id)
+        ctx.n, ctx.Cc = n, Cc
+        ctx.mark_non_differentiable(gout)
+        return sums, gout
+
+    @staticmethod
+    def backward(ctx, gradx, gradgeom):
+        run_id, = ctx.saved_tensors
+        g = gradx.contiguous().float()
+        out = torch.empty((ctx.n, ctx.Cc), dtype=torch.float32, device=g.device)
+        check(lib().lss_quickcumsum_bwd(ctx.n, ctx.Cc, _ptr(g), _ptr(run_id), _ptr(out), _stream()),
+              "lss_quickcumsum_bwd")
+        return out, None, None
+
+
+def cumsum_trick(x, geom_feats, ranks):
+    """tools.py:182-190.  Same kernels as QuickCumsum (the reference's two variants differ only in how
+    autograd derives the backward; the gather backward is exact for both)."""
+    return QuickCumsum.apply(x, geom_feats, ranks)

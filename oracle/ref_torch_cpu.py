@@ -48,13 +48,19 @@ def run_sum_autograd(feats, coords, ranks):
     return torch.cat((pref[:1], pref[1:] - pref[:-1])), coords
 
 
+def _host_inverse(m):
+    """`torch.inverse(m.cpu()).cuda()` of models.py:180,186: LAPACK on the host, result back on m's device."""
+    return torch.inverse(m.cpu()).to(m.device)
+
+
 def geometry(frustum, rots, trans, intrins, post_rots, post_trans):
-    """models.py:170-190 (the `.cpu()/.cuda()` hops are identity on the host)."""
+    """models.py:170-190.  The two 3x3 inverses run on the host as in the reference (identity hop for
+    CPU tensors), so the same function also times the stock-ATen path on a GPU."""
     B, N, _ = trans.shape
     pts = frustum - post_trans.view(B, N, 1, 1, 1, 3)
-    pts = torch.inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(pts.unsqueeze(-1))
+    pts = _host_inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(pts.unsqueeze(-1))
     pts = torch.cat((pts[..., :2, :] * pts[..., 2:3, :], pts[..., 2:3, :]), 5)
-    combine = rots.matmul(torch.inverse(intrins))
+    combine = rots.matmul(_host_inverse(intrins))
     pts = combine.view(B, N, 1, 1, 1, 3, 3).matmul(pts).squeeze(-1)
     pts += trans.view(B, N, 1, 1, 1, 3)
     return pts

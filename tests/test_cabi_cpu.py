@@ -1,0 +1,104 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/lss_b200.h
+declares, host-only entry points work, and the Python layer refuses to run without CUDA (no fallback)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lss_carla_b200 import _lib, ops
+from lss_carla_b200.synthetic import CONFIGS
+from lss_carla_b200.tools import gen_dx_bx
+from oracle import lss_oracle as O
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not os.path.isfile(_lib.SO_PATH):
+        _lib.build_library()
+    return _lib.lib()
+
+
+def test_every_header_symbol_is_exported_and_bound(L):
+    names = _lib.header_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/lss_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert L.lss_version() == 100
+    assert b"workspace" in L.lss_status_string(-5)
+
+
+def test_struct_sizes_match_header():
+    # lss_problem: 9 int32 + 6 float = 60 bytes; lss_plan_layout: 3 int32 (+pad) + int64 + 7 size_t
+    assert C.sizeof(_lib.LssProblem) == 60
+    assert C.sizeof(_lib.LssPlanLayout) == 16 + 8 + 7 * 8
+
+
+def _problem(cfg):
+    dx, bx, nx = gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    fH, fW = cfg.fHW
+    return ops.Problem.from_grid(cfg.B, cfg.N, cfg.D, fH, fW, cfg.C, dx, bx, nx)
+
+
+def test_problem_lo_matches_oracle():
+    for name in ("cfg1", "cfg4", "tiny"):
+        cfg = CONFIGS[name]
+        p = _problem(cfg)
+        dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+        lo = bx - dx / np.float32(2)
+        assert np.array_equal(np.array(p.lo, np.float32), lo)
+        assert np.array_equal(np.array(p.dx, np.float32), dx)
+        assert tuple(p.nx) == tuple(int(v) for v in nx)
+        tdx, tbx, tnx = gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+        assert tnx.dtype == torch.int64 and tdx.dtype == torch.float32
+        assert np.array_equal(tbx.numpy(), bx)
+
+
+def test_plan_layout_host_only(L):
+    cfg = CONFIGS["cfg2"]
+    p = _problem(cfg)
+    lay = _lib.LssPlanLayout()
+    assert L.lss_plan_layout_init(C.byref(p.c), 0, C.byref(lay)) == 0
+    assert lay.tile_cols == 200 and lay.tiles_per_row == 1 and lay.n_tiles == 8 * 200
+    assert lay.n_points == cfg.points == 346368
+    assert lay.bytes >= 2 * 4 * cfg.points
+    assert L.lss_plan_layout_init(C.byref(p.c), 56, C.byref(lay)) == 0
+    assert lay.tiles_per_row == 4 and lay.n_tiles == 8 * 200 * 4
+    assert L.lss_plan_layout_init(C.byref(p.c), 13, C.byref(lay)) == -3      # not a multiple of 8
+    lim = _lib.LssLimits()
+    L.lss_get_limits(C.byref(lim))
+    assert lim.max_points_per_sample == 1 << 20 and lim.max_depth_bins == 256
+
+
+def test_bad_arguments_return_status_codes(L):
+    cfg = CONFIGS["tiny"]
+    p = _problem(cfg)
+    null = C.c_void_p(0)
+    assert L.lss_geometry(C.byref(p.c), null, null, null, null, null, null, null) == -1
+    assert L.lss_lift_prepare(C.byref(p.c), null, null, null, null) == -1
+    bad = _lib.LssProblem()
+    lay = _lib.LssPlanLayout()
+    assert L.lss_plan_layout_init(C.byref(bad), 0, C.byref(lay)) == -1       # zero dims
+    big = _problem(cfg)
+    big.c.D = 1 << 20
+    assert L.lss_plan_layout_init(C.byref(big.c), 0, C.byref(lay)) == -3     # > 2^20 points per sample
+    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, 0, 0, null) == -5
+    assert L.lss_quickcumsum_scratch_elems(5000) >= 5000 + 5
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of computing with ATen."""
+    cfg = CONFIGS["tiny"]
+    p = _problem(cfg)
+    fH, fW = cfg.fHW
+    x = torch.zeros(cfg.B * cfg.N, cfg.D + cfg.C, fH, fW)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.lift_prepare(p, x)
+    with pytest.raises(RuntimeError):
+        ops.QuickCumsum.apply(torch.zeros(4, 8), torch.zeros(4, 4, dtype=torch.long), torch.zeros(4, dtype=torch.long))
+    import lss_carla_b200.ops as ops_src
+    src = open(ops_src.__file__).read()
+    assert "oracle" not in src.replace("# oracle", ""), "product code must not import the oracle"
