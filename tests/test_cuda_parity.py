@@ -95,7 +95,7 @@ def test_plan_and_reference_sort_order(case, tile_cols):
     assert ts[0] == 0 and ts[-1] == int(g["n_kept"]) and np.all(np.diff(ts) >= 0)
     # scratch counters are left zeroed for the next build
     L = plan.layout
-    assert not plan.ws[L.off_tile_count:].any()
+    assert not plan.ws[L.off_tile_count:L.off_cursor].any() and not plan.ws[L.off_sync:].any()
     # reference order: flat index of x[kept][sorts]
     order = ops.reference_order(plan).cpu().numpy()
     rs = O.ranks_and_sort(idx, kept, cfg.B, g["nx"])
