@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the lift-splat hot path (BASELINE.json: BEV-pool Mpoints/s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+                    [--mode sorted|atomic|red] [--layout nchw|channels_last] [--inverse device|reference]
+
+One "step" = one pass of the path over one synthetic SimBEV-shaped batch:
+    calibration matrices -> geometry/voxel ids/plan (sorted buckets) -> lift operands (softmax, ctx^T)
+    -> splat forward (BEV written once) -> backward (gradient rows + gather to the depthnet-output gradient).
+points/step = B*N*D*fH*fW (every frustum point, kept or not).
+
+Numbers in the JSON line
+    value     Mpoints/s, whole job (all ranks), inputs resident in HBM, steps replayed as CUDA graphs,
+              4 rotating buffer sets (> 126 MB L2) so no step finds its tensors in L2.
+    e2e       same metric through the public API (`lss_carla_b200.api.LiftSplat` + autograd) with HOST
+              (pinned) depthnet output + calibration copied in and the input gradient copied out per step.
+    roofline  dominant kernel (splat forward) alone: algorithmic bytes per launch / mean launch time,
+              against MEASURED_PEAKS.json hbm_gbs.
+    cpu_baseline  oracle/ref_torch_cpu.py (the reference's ATen op chain) on the host cores, bounded sample.
+
+`--impl reference` times that CPU port as the reference arm (the reference is pure Python/PyTorch and
+`/root/reference` does not exist on the GPU box).  Under torchrun only rank 0 runs it.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from lss_carla_b200.synthetic import CONFIGS, make_batch, make_bev_grad  # noqa: E402
+
+METRIC = "bev_pool_mpoints_per_s_fwd_bwd"
+UNIT = "Mpoints/s"
+L2_BYTES = 126e6
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# clock / throttle sampling during the timed region (NVML)
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown",
+                 "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown",
+                 "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, attr in names.items():
+                    if r & getattr(nv, attr, 0):
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's ATen op chain on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_run(cfg, steps, warmup, seed=0):
+    from oracle import lss_oracle as O
+    from oracle import ref_torch_cpu as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = make_batch(cfg, seed, "train")
+    dx, bx, nx = (torch.from_numpy(a) for a in O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound))
+    frustum = torch.from_numpy(O.create_frustum(cfg.final_dim, list(cfg.dbound)))
+    calib = {k: b[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans")}
+    gb = make_bev_grad(cfg, seed)
+    for _ in range(warmup):
+        T.liftsplat_step(b["depthnet_out"], frustum, calib, dx, bx, nx, cfg.C, gb)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        T.liftsplat_step(b["depthnet_out"], frustum, calib, dx, bx, nx, cfg.C, gb)
+    dt = time.perf_counter() - t0
+    return cfg.points * steps / dt / 1e6, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference_arm(args, cfg, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))          # bounded: ~0.5-1 s of CPU work per step at cfg2
+    warm = max(1, min(args.warmup, 2))
+    val, ms, cores = cpu_reference_run(cfg, steps, warm)
+    sample = f"{steps} full {cfg.name} fwd+bwd steps (B={cfg.B}) of the reference ATen op chain, torch CPU, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "where": "host CPU (oracle/ref_torch_cpu.py port of the reference path)"},
+            "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    fH, fW = cfg.fHW
+    X, Y, Z = cfg.nx
+    return (f"{cfg.name}: LSS lift-splat fwd+bwd, bsz={cfg.B}/GPU, {cfg.N} cams {cfg.final_dim[0]}x{cfg.final_dim[1]} "
+            f"(feat {fH}x{fW}), D={cfg.D}, C={cfg.C}, grid {X}x{Y}x{Z}")
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+class BufferSet:
+    """One complete set of device tensors for a step (inputs, plan workspace, outputs)."""
+
+    def __init__(self, cfg, prob, seed, dev, channels_last, tile_cols):
+        from lss_carla_b200 import ops
+        b = make_batch(cfg, seed, "train")
+        self.host = b
+        self.rots, self.intrins, self.post_rots = (b[k].to(dev) for k in ("rots", "intrins", "post_rots"))
+        self.post_trans, self.trans = b["post_trans"].to(dev).reshape(-1, 3), b["trans"].to(dev).reshape(-1, 3)
+        self.dn = b["depthnet_out"].to(dev)
+        fmt = torch.channels_last if channels_last else torch.contiguous_format
+        self.grad_bev = make_bev_grad(cfg, seed).to(dev).contiguous(memory_format=fmt)
+        self.plan = ops.Plan(prob, dev, tile_cols)
+        self.rows = None if channels_last else torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=dev)
+        self.out = {}
+
+
+def one_step(ops, prob, frustum, bs, mode, channels_last, inverse):
+    """The whole path for one batch; every launch goes through the C ABI on the current stream."""
+    if inverse == "device":
+        M1, M2 = ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots)
+    else:
+        M1, M2 = ops.calib_matrices_reference(bs.rots, bs.intrins, bs.post_rots)
+    calib = (frustum, bs.post_trans, M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), bs.trans)
+    ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=bs.plan)
+    pr, ct = ops.lift_prepare(prob, bs.dn)
+    bev = ops.splat_fwd(prob, bs.plan, pr, ct, mode, channels_last)
+    grad = ops.splat_bwd(prob, bs.plan, bs.grad_bev, pr, ct, bs.rows)
+    bs.out = {"bev": bev, "grad": grad, "pr": pr, "ct": ct, "M1": M1, "M2": M2}
+    return bev, grad
+
+
+LAUNCHES_PER_STEP = {"sorted": 8, "atomic": 7, "red": 8}   # calib, voxel+count, scatter, [sort], lift, fwd(+memset), rows, gather
+
+
+def time_kernel(fn, sets, iters, stream):
+    """Mean duration of one launch of `fn(bs)`, back to back over the rotating buffer sets."""
+    for bs in sets:
+        fn(bs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(iters):
+        fn(sets[i % len(sets)])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default="sorted", choices=["sorted", "atomic", "red"])
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"])
+    ap.add_argument("--inverse", default="device", choices=["device", "reference"])
+    ap.add_argument("--tile-cols", type=int, default=0)
+    ap.add_argument("--sets", type=int, default=4)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = CONFIGS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from lss_carla_b200 import api, ops
+    from lss_carla_b200.tools import gen_dx_bx
+
+    args.warmup = max(args.warmup, 3)
+    channels_last = args.layout == "channels_last"
+    dx, bx, nx = gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    fH, fW = cfg.fHW
+    prob = ops.Problem.from_grid(cfg.B, cfg.N, cfg.D, fH, fW, cfg.C, dx, bx, nx)
+    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, splat_mode=args.mode, inverse_mode="reference",
+                       bev_channels_last=channels_last, device=dev, tile_cols=args.tile_cols)
+    frustum = ls.frustum
+    sets = [BufferSet(cfg, prob, 100 * rank + i, dev, channels_last, args.tile_cols) for i in range(args.sets)]
+    stream = torch.cuda.current_stream()
+
+    # ---- CUDA graphs of one step per buffer set (launch-bound sequence of 8 small kernels)
+    use_graph = not args.no_graph and args.inverse == "device"
+    graphs = []
+    for bs in sets:
+        one_step(ops, prob, frustum, bs, args.mode, channels_last, args.inverse)
+    torch.cuda.synchronize()
+    if use_graph:
+        side = torch.cuda.Stream()
+        for bs in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                one_step(ops, prob, frustum, bs, args.mode, channels_last, args.inverse)
+            graphs.append(g)
+        torch.cuda.synchronize()
+
+    def step(i):
+        if use_graph:
+            graphs[i % len(graphs)].replay()
+        else:
+            one_step(ops, prob, frustum, sets[i % len(sets)], args.mode, channels_last, args.inverse)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = world * cfg.points * args.steps / elapsed / 1e6
+
+    # ---- e2e through the public API: host buffers in, input gradient out, every step
+    e2e_steps = max(10, min(args.e2e_steps, args.steps))
+    pinned = []
+    for bs in sets:
+        h = {k: bs.host[k].pin_memory() for k in ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans")}
+        h["grad_out"] = torch.empty_like(h["depthnet_out"]).pin_memory()
+        h["probe"] = torch.empty(1024, dtype=torch.float32).pin_memory()
+        pinned.append(h)
+    h2d = sum(pinned[0][k].numel() * 4 for k in ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans"))
+    d2h = pinned[0]["grad_out"].numel() * 4 + pinned[0]["probe"].numel() * 4
+
+    def e2e_step(i):
+        h, bs = pinned[i % len(pinned)], sets[i % len(sets)]
+        x = h["depthnet_out"].to(dev, non_blocking=True).requires_grad_(True)
+        bev = ls(x, h["rots"], h["trans"], h["intrins"], h["post_rots"], h["post_trans"])
+        bev.backward(bs.grad_bev)
+        h["grad_out"].copy_(x.grad, non_blocking=True)
+        h["probe"].copy_(bev.detach().reshape(-1)[:1024], non_blocking=True)
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_elapsed = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_elapsed = float(t.item())
+    e2e_value = world * cfg.points * e2e_steps / e2e_elapsed / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timings (rank 0): each stage alone, back to back over the rotating sets
+    kiters = 200
+    for bs in sets:
+        one_step(ops, prob, frustum, bs, args.mode, channels_last, args.inverse)
+    torch.cuda.synchronize()
+    layout_code = 1 if channels_last else 0
+    stages = {}
+    stages["calib"] = time_kernel(lambda bs: ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots), sets, kiters, stream)
+    stages["plan_build"] = time_kernel(
+        lambda bs: ops.build_plan(prob, calib=(frustum, bs.post_trans, bs.out["M1"].reshape(-1, 3, 3),
+                                               bs.out["M2"].reshape(-1, 3, 3), bs.trans),
+                                  sorted=(args.mode == "sorted"), plan=bs.plan), sets, kiters, stream)
+    stages["lift_prepare"] = time_kernel(lambda bs: ops.lift_prepare(prob, bs.dn), sets, kiters, stream)
+    stages["splat_fwd"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last),
+                                      sets, kiters, stream)
+    stages["splat_bwd"] = time_kernel(lambda bs: ops.splat_bwd(prob, bs.plan, bs.grad_bev, bs.out["pr"], bs.out["ct"], bs.rows),
+                                      sets, kiters, stream)
+
+    X, Y, Z = cfg.nx
+    IN = 4 * cfg.B * cfg.N * (cfg.D + cfg.C) * fH * fW
+    G = 4 * cfg.B * cfg.C * Z * X * Y
+    v_hit = int((sets[0].out["bev"].reshape(cfg.B, Z, cfg.C, X, Y).abs().sum(2) > 0).sum()) if not channels_last else \
+        int((sets[0].out["bev"].abs().sum(1) > 0).sum())
+    fwd_bytes = IN + G                                    # forward (fused)
+    bwd_bytes = 4 * cfg.C * v_hit + 2 * IN                # backward (fused)
+    peak, peak_src = load_peaks()
+    achieved = fwd_bytes / stages["splat_fwd"] / 1e9
+    step_s = elapsed / args.steps
+    roof = {"bound": "hbm", "kernel": "k_splat_fwd_tile", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+            "algorithmic_bytes_per_launch": fwd_bytes, "kernel_us": round(stages["splat_fwd"] * 1e6, 2),
+            "step_algorithmic_bytes": fwd_bytes + bwd_bytes,
+            "step_frac": round((fwd_bytes + bwd_bytes) / step_s / 1e9 / peak, 4),
+            "stage_us": {k: round(v * 1e6, 2) for k, v in stages.items()}}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        n = 3
+        v, ms, cores = cpu_reference_run(cfg, n, 1)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} full {cfg.name} fwd+bwd steps of oracle/ref_torch_cpu.py (reference ATen op chain), {ms:.0f} ms/step"}
+
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 5), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "splat_mode": args.mode, "bev_layout": args.layout,
+                       "inverse": args.inverse, "cuda_graph": use_graph,
+                       "l2": f"{args.sets} rotating buffer sets (~{(2 * G + IN) * (1 if channels_last else 1.5) / 1e6:.0f} MB each) > 126 MB L2",
+                       "points_per_step_per_gpu": cfg.points, "voxels_hit": v_hit},
+            "clocks": clk.summary(),
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": round(e2e_elapsed / e2e_steps * 1e3, 4),
+                    "api": "lss_carla_b200.api.LiftSplat.__call__ + autograd backward; host LAPACK inverses (reference mode)"},
+            "gpu_launches": LAUNCHES_PER_STEP[args.mode] * args.steps,
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""Public entry point of the path for callers that do not hold a `LiftSplatShoot` module.
+
+    ls = LiftSplat(grid_conf, data_aug_conf, device="cuda:0")
+    bev = ls(depthnet_out, rots, trans, intrins, post_rots, post_trans)     # [B, nz*C, nx, ny], autograd-aware
+
+`depthnet_out` is what `CamEncode.depthnet` produces (reference src/models.py:56); the remaining
+arguments are the calibration tensors of `LiftSplatShoot.forward` (models.py:256).  Inputs may live on
+the host (pinned or not): they are copied to the device on the current stream.  With
+`inverse_mode="reference"` and HOST calibration the two 3x3 inverses run on the host exactly as the
+reference does (models.py:180,186) without any device->host round trip.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import models, ops
+from .tools import gen_dx_bx
+
+
+class LiftSplat:
+    def __init__(self, grid_conf, data_aug_conf, C=64, downsample=16, splat_mode="sorted",
+                 inverse_mode="reference", bev_channels_last=False, device="cuda:0", tile_cols=0):
+        self.device = torch.device(device)
+        dx, bx, nx = gen_dx_bx(grid_conf["xbound"], grid_conf["ybound"], grid_conf["zbound"])
+        self.dx, self.bx, self.nx = dx, bx, nx
+        ogfH, ogfW = data_aug_conf["final_dim"]
+        fH, fW = ogfH // downsample, ogfW // downsample
+        ds = torch.arange(*grid_conf["dbound"], dtype=torch.float)
+        xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float)
+        ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float)
+        fr = torch.empty(ds.shape[0], fH, fW, 3)
+        fr[..., 0], fr[..., 1], fr[..., 2] = xs.view(1, 1, fW), ys.view(1, fH, 1), ds.view(-1, 1, 1)
+        self.frustum = fr.to(self.device)
+        self.D, self.camC = ds.shape[0], C
+        self.splat_mode, self.inverse_mode, self.bev_channels_last = splat_mode, inverse_mode, bev_channels_last
+        self.tile_cols = tile_cols
+
+    def _dev(self, t):
+        return t if t.is_cuda else t.to(self.device, non_blocking=True)
+
+    def __call__(self, depthnet_out, rots, trans, intrins, post_rots, post_trans, plan=None):
+        B, N = trans.shape[:2]
+        fH, fW = depthnet_out.shape[-2:]
+        prob = models._problem_for(self, B, N, fH, fW, depthnet_out.shape[1] - self.D)
+        if plan is None:
+            if self.inverse_mode == "reference":
+                # host tensors: LAPACK inverse where the data already is; device tensors: the reference's round trip
+                M1 = torch.inverse(post_rots.cpu() if post_rots.is_cuda else post_rots)
+                M2h = torch.inverse(intrins.cpu() if intrins.is_cuda else intrins)
+                M1, M2 = self._dev(M1), self._dev(rots).matmul(self._dev(M2h))
+            else:
+                M1, M2 = ops.calib_matrices_device(self._dev(rots), self._dev(intrins), self._dev(post_rots))
+            calib = (self.frustum, self._dev(post_trans).reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3),
+                     self._dev(trans).reshape(-1, 3))
+            plan = ops.build_plan(prob, calib=calib, sorted=(self.splat_mode == "sorted"),
+                                  plan=models._cached_plan(self, prob, self.device))
+        return ops.lift_splat(self._dev(depthnet_out), prob, plan, self.splat_mode, self.bev_channels_last)
