@@ -185,14 +185,26 @@ LAUNCHES_PER_STEP = {"sorted": 8, "atomic": 7, "red": 8}   # calib, voxel+count,
 
 
 def time_kernel(fn, sets, iters, stream):
-    """Mean duration of one launch of `fn(bs)`, back to back over the rotating buffer sets."""
+    """Mean duration of one launch of `fn(bs)`: one CUDA graph per buffer set (no host overhead in the
+    timed region), replayed back to back over the rotating sets, bracketed by two events."""
     for bs in sets:
         fn(bs)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graphs, keep = [], []
+    for bs in sets:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            keep.append(fn(bs))
+        graphs.append(g)
+    torch.cuda.synchronize()
+    for g in graphs:
+        g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(iters):
-        fn(sets[i % len(sets)])
+        graphs[i % len(graphs)].replay()
     e1.record(stream)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e-3

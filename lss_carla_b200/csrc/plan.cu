@@ -218,22 +218,24 @@ k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, const int32_t
 
 // Sort every bucket by (column, point index): all comparators point the same way ("flip" bitonic
 // network), so the virtual +inf padding beyond n never moves and n need not be a power of two.
+// Index arithmetic uses shifts only (k, j are powers of two).
 template <typename Keys>
 __device__ __forceinline__ void bitonic_sort_block(Keys a, int n) {
-    int m = 1;
-    while (m < n) m <<= 1;
+    int m = 1, lm = 0;
+    while (m < n) { m <<= 1; ++lm; }
     const int half = m >> 1;
-    for (int k = 2; k <= m; k <<= 1) {
-        const int hk = k >> 1;
+    for (int lk = 1; lk <= lm; ++lk) {
+        const int k = 1 << lk, hk = k >> 1;
         for (int q = threadIdx.x; q < half; q += blockDim.x) {   // flip stage: i <-> i ^ (k-1)
-            const int i = (q / hk) * k + (q % hk);
+            const int i = ((q >> (lk - 1)) << lk) | (q & (hk - 1));
             const int l = i ^ (k - 1);
             if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
         }
         __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
             for (int q = threadIdx.x; q < half; q += blockDim.x) {
-                const int i = (q / j) * 2 * j + (q % j);
+                const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
                 const int l = i + j;
                 if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
             }
@@ -242,9 +244,10 @@ __device__ __forceinline__ void bitonic_sort_block(Keys a, int n) {
     }
 }
 
-#define LSS_SORT_SMEM_CAP 8192   // entries sorted in shared memory (32 KB); larger buckets sort in global memory
+#define LSS_SORT_SMEM_CAP 4096   // entries sorted in shared memory (16 KB); larger buckets sort in global memory
+#define LSS_SORT_THREADS 128
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LSS_SORT_THREADS)
 k_plan_sort(Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries) {
     __shared__ uint32_t s_keys[LSS_SORT_SMEM_CAP];
     const int t = blockIdx.x;
@@ -424,7 +427,7 @@ extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, vo
     k_plan_scatter<<<grid, 256, 0, s>>>(d, tl, vox, tile_start, cursor, entries);
     LSS_CHECK_LAUNCH();
     if (sorted) {
-        k_plan_sort<<<tl.n_tiles, 256, 0, s>>>(tl, tile_start, entries);
+        k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, 0, s>>>(tl, tile_start, entries);
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;

@@ -7,14 +7,17 @@
 //
 // Forward is a TILE-OWNER kernel: one CTA owns the BEV tile (b, iz, ix, TY consecutive iy) and reads the
 // bucket of points the plan assigned to it (plan.cu).  Every BEV element is written exactly once, zeros
-// included, so there is no memset and no global atomic.  In SORTED mode a warp walks one voxel's points in
-// ascending flat index and adds float32(prob * ctx) sequentially -- a fixed summation order; in
-// SMEM_ATOMIC mode warps walk the (unsorted) bucket and accumulate with shared-memory atomics.
-// RED_GLOBAL is the classical pixel-owner red.global.add splat, kept for measurement.
+// included, so there is no memset and no global atomic.  The tile is staged in shared memory (zero-filled
+// with 16-byte stores, non-empty voxels overwrite their channels) and streamed out with 16-byte stores.
+//   SORTED       the bucket is sorted by (column, point): warps take 32-entry chunks, find the voxel
+//                segments that START in their chunk by ballot, and add float32(prob*ctx) sequentially in
+//                ascending point order (a fixed summation order; a segment is never split between warps).
+//   SMEM_ATOMIC  warps walk the (unsorted) bucket and accumulate with shared-memory atomics.
+//   RED_GLOBAL   classical pixel-owner red.global.add splat into a zeroed BEV, kept for measurement.
 //
-// Backward is a pure gather (tools.py:212-219): for NCHW gradients a tile-owner kernel first transposes the
-// rows of hit voxels into channel-contiguous rows; a pixel-owner kernel then gathers one row per frustum
-// point and fuses the outer-product and softmax backward.
+// Backward is a pure gather (tools.py:212-219): for NCHW gradients a tile-owner kernel first gathers the
+// channels of every hit voxel into a channel-contiguous row; a pixel-owner kernel then reads one row per
+// frustum point and fuses the outer-product and softmax backward.
 #include "common.cuh"
 
 #define SPLAT_THREADS 256
@@ -26,6 +29,26 @@ struct SrcArgs {
     long long s[6];
 };
 
+// Channel ownership of a lane.  VW > 0: C == 32*VW, the lane owns the VW contiguous channels
+// [lane*VW, lane*VW+VW) and moves them with one VW*4-byte access.  VW == 0: generic, the lane owns
+// channels lane + 32*k (k < KC), predicated on c < C, with an arbitrary element stride.
+template <int VW, int KC> struct ChanMap {
+    static constexpr int NA = VW ? VW : KC;
+    __device__ static __forceinline__ int ch(int lane, int i) { return VW ? lane * VW + i : lane + 32 * i; }
+};
+
+template <int VW, int KC>
+__device__ __forceinline__ void load_row(const float *__restrict__ row, long long cs, int lane, int C, float *x) {
+    if (VW == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(row) + lane); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
+    else if (VW == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(row) + lane); x[0] = t.x; x[1] = t.y; }
+    else if (VW == 1) { x[0] = __ldg(row + lane); }
+    else {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { const int c = lane + 32 * k; x[k] = c < C ? __ldg(row + c * cs) : 0.f; }
+    }
+}
+
+// Source of one bucket entry: weight and element offset of its C-channel row.
 template <bool DENSE>
 __device__ __forceinline__ void entry_source(const Dims &d, const SrcArgs &a, int b, uint32_t e, float &w, long long &off) {
     const int pidx = (int)(e & LSS_PIDX_MASK);
@@ -55,119 +78,148 @@ __device__ __forceinline__ TileCoord tile_coord(const Dims &d, const Tiling &tl,
     return t;
 }
 
+// The tile as a 2-D block: NR rows of RL floats; shared-memory row stride SRS, global row stride GRS.
+//   NCHW           rows = channels, row = `cols` consecutive iy      (SRS = TY+4, GRS = nx*ny)
+//   channels_last  rows = columns,  row = C consecutive channels     (SRS = C,    GRS = nz*C)
+struct Tile2D { int NR, RL, SRS; size_t GRS, gbase; };
+
+template <bool CL>
+__device__ __forceinline__ Tile2D tile_2d(const Dims &d, const Tiling &tl, const TileCoord &tc) {
+    Tile2D t;
+    if (CL) {
+        t.NR = tc.cols; t.RL = d.C; t.SRS = d.C; t.GRS = (size_t)d.nz * d.C;
+        t.gbase = ((size_t)(tc.b * d.nx + tc.ix) * d.ny + tc.y0) * t.GRS + (size_t)tc.iz * d.C;
+    } else {
+        t.NR = d.C; t.RL = tc.cols; t.SRS = tl.TY + 4; t.GRS = (size_t)d.nx * d.ny;
+        t.gbase = ((size_t)(tc.b * d.nz + tc.iz) * d.C) * t.GRS + (size_t)tc.ix * d.ny + tc.y0;
+    }
+    return t;
+}
+
+// Stream a tile to global memory (src == nullptr: zeros).  Division-free walk: every thread advances by
+// SPLAT_THREADS vector slots per iteration.
+template <bool VEC4>
+__device__ __forceinline__ void store_tile(const Tile2D &t, const float *__restrict__ src, float *__restrict__ bev) {
+    constexpr int W = VEC4 ? 4 : 1;
+    const int vpr = t.RL / W;                       // vector slots per row
+    const int total = t.NR * vpr;
+    int row = threadIdx.x / vpr, v = threadIdx.x - row * vpr;
+    const int dr = SPLAT_THREADS / vpr, dv = SPLAT_THREADS - dr * vpr;
+    float *g = bev + t.gbase;
+    for (int i = threadIdx.x; i < total; i += SPLAT_THREADS) {
+        if (VEC4) {
+            const float4 val = src ? *reinterpret_cast<const float4 *>(src + row * t.SRS + v * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(g + (size_t)row * t.GRS + v * 4) = val;
+        } else {
+            g[(size_t)row * t.GRS + v] = src ? src[row * t.SRS + v] : 0.f;
+        }
+        v += dv; row += dr;
+        if (v >= vpr) { v -= vpr; ++row; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward, tile-owner
 // ------------------------------------------------------------------------------------------------
-// smem (floats): NCHW            acc[C][TYP]   TYP = TY|1 (odd stride: conflict-free column writes)
-//                CL + ATOMIC     acc[TY][C]
-//                then (SORTED)   colstart[TY+1] as int
-template <int KC, bool ATOMIC, bool CL, bool DENSE>
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE, bool VEC4>
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const uint32_t *__restrict__ entries,
                  SrcArgs src, float *__restrict__ bev) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
+    using CM = ChanMap<VW, KC>;
+    constexpr int NA = CM::NA;
     const int tile = blockIdx.x;
     const TileCoord tc = tile_coord(d, tl, tile);
+    const Tile2D t2 = tile_2d<CL>(d, tl, tc);
     const int s = __ldg(tile_start + tile), n = __ldg(tile_start + tile + 1) - s;
+    if (n == 0) { store_tile<VEC4>(t2, nullptr, bev); return; }   // nothing lands here: stream zeros
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = d.C;
-    const int TYP = tl.TY | 1;
-    const size_t plane = (size_t)d.nx * d.ny;
-    // NCHW: element (c, y) of this tile;  CL: element (y, c)
-    const size_t nchw_base = ((size_t)(tc.b * d.nz + tc.iz) * C) * plane + (size_t)tc.ix * d.ny + tc.y0;
-    const size_t cl_base = ((size_t)(tc.b * d.nx + tc.ix) * d.ny + tc.y0) * (size_t)(d.nz * C) + (size_t)tc.iz * C;
-    const size_t cl_stride = (size_t)d.nz * C;
     const long long cs = DENSE ? src.s[5] : 1;
-
-    if (n == 0) {   // nothing lands here: stream zeros
-        if (CL) {
-            for (int i = threadIdx.x; i < tc.cols * C; i += SPLAT_THREADS) bev[cl_base + (size_t)(i / C) * cl_stride + (i % C)] = 0.f;
-        } else {
-            for (int c = warp; c < C; c += SPLAT_WARPS)
-                for (int y = lane; y < tc.cols; y += 32) bev[nchw_base + (size_t)c * plane + y] = 0.f;
-        }
-        return;
+    const int SRS = t2.SRS;
+    {   // zero the staging tile with 16-byte stores (its size is a multiple of 4 floats)
+        const int n4 = (CL ? tl.TY * C : C * SRS) >> 2;
+        float4 *z = reinterpret_cast<float4 *>(smem);
+        for (int i = threadIdx.x; i < n4; i += SPLAT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-
-    float *acc_tile = smem;
+    __syncthreads();
     const uint32_t *ent = entries + s;
 
-    if (!ATOMIC) {
-        int *colstart = (int *)(smem + (CL ? 0 : (size_t)C * TYP));
-        // first bucket position of every column (bucket is sorted by column)
-        for (int i = threadIdx.x; i <= n; i += SPLAT_THREADS) {
-            const int c_prev = i == 0 ? -1 : (int)(__ldg(ent + i - 1) >> LSS_PIDX_BITS);
-            const int c_cur = i == n ? tl.TY : (int)(__ldg(ent + i) >> LSS_PIDX_BITS);
-            for (int c = c_prev + 1; c <= c_cur; ++c) colstart[c] = i;
-        }
-        __syncthreads();
-        for (int col = warp; col < tc.cols; col += SPLAT_WARPS) {
-            const int cb = colstart[col], ce = colstart[col + 1];
-            float acc[KC];
-#pragma unroll
-            for (int k = 0; k < KC; ++k) acc[k] = 0.f;
-            for (int j0 = cb; j0 < ce; j0 += 32) {
-                float w = 0.f; long long off = 0;
-                if (j0 + lane < ce) entry_source<DENSE>(d, src, tc.b, __ldg(ent + j0 + lane), w, off);
-                const int cnt = min(32, ce - j0);
+    for (int c0 = warp * 32; c0 < n; c0 += SPLAT_THREADS) {
+        const int i = c0 + lane;
+        const bool valid = i < n;
+        const uint32_t e = valid ? __ldg(ent + i) : 0u;
+        float w = 0.f; long long off = 0;
+        if (valid) entry_source<DENSE>(d, src, tc.b, e, w, off);
+        const int lim = min(32, n - c0);
+        if (ATOMIC) {
+            const int col = (int)(e >> LSS_PIDX_BITS);
 #pragma unroll 4
-                for (int jj = 0; jj < cnt; ++jj) {
-                    const float wj = __shfl_sync(LSS_FULL_MASK, w, jj);
-                    const long long oj = __shfl_sync(LSS_FULL_MASK, off, jj);
-                    const float *row = src.base + oj;
-#pragma unroll
-                    for (int k = 0; k < KC; ++k) {
-                        const int c = lane + 32 * k;
-                        if (c < C) acc[k] = __fadd_rn(acc[k], __fmul_rn(wj, __ldg(row + c * cs)));   // ascending point order
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int c = lane + 32 * k;
-                if (c < C) {
-                    if (CL) bev[cl_base + (size_t)col * cl_stride + c] = acc[k];
-                    else acc_tile[c * TYP + col] = acc[k];
-                }
-            }
-        }
-        if (CL) return;
-        __syncthreads();
-    } else {
-        const int tile_elems = CL ? tl.TY * C : C * TYP;
-        for (int i = threadIdx.x; i < tile_elems; i += SPLAT_THREADS) acc_tile[i] = 0.f;
-        __syncthreads();
-        for (int j0 = warp * 32; j0 < n; j0 += SPLAT_THREADS) {
-            float w = 0.f; long long off = 0; int col = 0;
-            if (j0 + lane < n) {
-                const uint32_t e = __ldg(ent + j0 + lane);
-                col = (int)(e >> LSS_PIDX_BITS);
-                entry_source<DENSE>(d, src, tc.b, e, w, off);
-            }
-            const int cnt = min(32, n - j0);
-#pragma unroll 4
-            for (int jj = 0; jj < cnt; ++jj) {
+            for (int jj = 0; jj < lim; ++jj) {
                 const float wj = __shfl_sync(LSS_FULL_MASK, w, jj);
                 const long long oj = __shfl_sync(LSS_FULL_MASK, off, jj);
                 const int cj = __shfl_sync(LSS_FULL_MASK, col, jj);
-                const float *row = src.base + oj;
+                float x[NA];
+                load_row<VW, KC>(src.base + oj, cs, lane, C, x);
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const int c = lane + 32 * k;
-                    if (c < C) atomicAdd(acc_tile + (CL ? cj * C + c : c * TYP + cj), __fmul_rn(wj, __ldg(row + c * cs)));
+                for (int a = 0; a < NA; ++a) {
+                    const int c = CM::ch(lane, a);
+                    if (VW || c < C) atomicAdd(smem + (CL ? cj * C + c : c * SRS + cj), __fmul_rn(wj, x[a]));
+                }
+            }
+        } else {
+            const uint32_t ep = (valid && i > 0) ? __ldg(ent + i - 1) : 0u;
+            const bool head = valid && (i == 0 || (e >> LSS_PIDX_BITS) != (ep >> LSS_PIDX_BITS));
+            unsigned heads = __ballot_sync(LSS_FULL_MASK, head);
+            while (heads) {                          // every voxel segment that starts in this chunk
+                const int sl = __ffs(heads) - 1;
+                heads &= heads - 1;
+                const int el = heads ? __ffs(heads) - 1 : lim;
+                const int col = (int)(__shfl_sync(LSS_FULL_MASK, e, sl) >> LSS_PIDX_BITS);
+                float acc[NA];
+#pragma unroll
+                for (int a = 0; a < NA; ++a) acc[a] = 0.f;
+#pragma unroll 4
+                for (int jj = sl; jj < el; ++jj) {   // ascending point order
+                    const float wj = __shfl_sync(LSS_FULL_MASK, w, jj);
+                    const long long oj = __shfl_sync(LSS_FULL_MASK, off, jj);
+                    float x[NA];
+                    load_row<VW, KC>(src.base + oj, cs, lane, C, x);
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[a]));
+                }
+                if (!heads && lim == 32) {           // last segment of a full chunk may run on
+                    for (int k = c0 + 32; k < n; k += 32) {
+                        const int i2 = k + lane;
+                        const uint32_t e2 = i2 < n ? __ldg(ent + i2) : 0u;
+                        const bool same = i2 < n && (int)(e2 >> LSS_PIDX_BITS) == col;
+                        const unsigned m = __ballot_sync(LSS_FULL_MASK, same);
+                        const int cnt = m == LSS_FULL_MASK ? 32 : __ffs(~m) - 1;
+                        if (cnt == 0) break;
+                        float w2 = 0.f; long long off2 = 0;
+                        if (lane < cnt) entry_source<DENSE>(d, src, tc.b, e2, w2, off2);
+                        for (int jj = 0; jj < cnt; ++jj) {
+                            const float wj = __shfl_sync(LSS_FULL_MASK, w2, jj);
+                            const long long oj = __shfl_sync(LSS_FULL_MASK, off2, jj);
+                            float x[NA];
+                            load_row<VW, KC>(src.base + oj, cs, lane, C, x);
+#pragma unroll
+                            for (int a = 0; a < NA; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[a]));
+                        }
+                        if (cnt < 32) break;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < NA; ++a) {
+                    const int c = CM::ch(lane, a);
+                    if (VW || c < C) smem[CL ? col * C + c : c * SRS + col] = acc[a];
                 }
             }
         }
-        __syncthreads();
     }
-
-    // ---- stream the tile out
-    if (CL) {
-        for (int i = threadIdx.x; i < tc.cols * C; i += SPLAT_THREADS) bev[cl_base + (size_t)(i / C) * cl_stride + (i % C)] = acc_tile[i];
-    } else {
-        for (int c = warp; c < C; c += SPLAT_WARPS)
-            for (int y = lane; y < tc.cols; y += 32) bev[nchw_base + (size_t)c * plane + y] = acc_tile[c * TYP + y];
-    }
+    __syncthreads();
+    store_tile<VEC4>(t2, smem, bev);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -221,32 +273,42 @@ k_vp_fwd_red(Dims d, const int32_t *__restrict__ vox, SrcArgs src, float *__rest
 // ------------------------------------------------------------------------------------------------
 
 // NCHW gradient -> channel-contiguous rows of the voxels that received points: rows[v, 0:C].
-// One CTA per non-empty tile: coalesced row loads into shared memory, transposed 4*C-byte row stores.
+// One CTA per non-empty tile marks its hit columns in shared memory; warps then gather the C strided
+// channels of each hit voxel (4-byte loads C*nx*ny apart; neighbouring columns share 32-byte sectors
+// through L1) and write one contiguous 4*C-byte row.  Only sectors that contain a hit voxel are read.
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_bwd_rows_nchw(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const uint32_t *__restrict__ entries,
                 const float *__restrict__ grad_bev, float *__restrict__ rows) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int tile = blockIdx.x;
     const int s = __ldg(tile_start + tile), n = __ldg(tile_start + tile + 1) - s;
     if (n == 0) return;
     const TileCoord tc = tile_coord(d, tl, tile);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = d.C, TYP = tl.TY | 1;
-    float *g_tile = smem;                       // [C][TYP]
-    int *hit = (int *)(smem + (size_t)C * TYP); // [TY]
+    const int C = d.C;
+    unsigned *hit = reinterpret_cast<unsigned *>(smem);      // bitmap over the tile's columns
+    const int nwords = (tl.TY + 31) >> 5;
+    for (int i = threadIdx.x; i < nwords; i += SPLAT_THREADS) hit[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += SPLAT_THREADS) {
+        const int col = (int)(__ldg(entries + s + i) >> LSS_PIDX_BITS);
+        atomicOr(hit + (col >> 5), 1u << (col & 31));
+    }
+    __syncthreads();
     const size_t plane = (size_t)d.nx * d.ny;
-    const size_t nchw_base = ((size_t)(tc.b * d.nz + tc.iz) * C) * plane + (size_t)tc.ix * d.ny + tc.y0;
-    for (int i = threadIdx.x; i < tl.TY; i += SPLAT_THREADS) hit[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += SPLAT_THREADS) hit[__ldg(entries + s + i) >> LSS_PIDX_BITS] = 1;
-    for (int c = warp; c < C; c += SPLAT_WARPS)
-        for (int y = lane; y < tc.cols; y += 32) g_tile[c * TYP + y] = __ldg(grad_bev + nchw_base + (size_t)c * plane + y);
-    __syncthreads();
+    const float *gsrc = grad_bev + ((size_t)(tc.b * d.nz + tc.iz) * C) * plane + (size_t)tc.ix * d.ny + tc.y0;
     const int v0 = ((tc.b * d.nz + tc.iz) * d.nx + tc.ix) * d.ny + tc.y0;
-    for (int col = warp; col < tc.cols; col += SPLAT_WARPS) {
-        if (!hit[col]) continue;
-        float *dst = rows + (size_t)(v0 + col) * C;
-        for (int c = lane; c < C; c += 32) dst[c] = g_tile[c * TYP + col];
+    // hit columns are dealt round-robin to the warps
+    int k = 0;
+    for (int wd = 0; wd < nwords; ++wd) {
+        unsigned bits = hit[wd];
+        while (bits) {
+            const int col = (wd << 5) + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if ((k++ & (SPLAT_WARPS - 1)) != warp) continue;
+            float *dst = rows + (size_t)(v0 + col) * C;
+            for (int c = lane; c < C; c += 32) dst[c] = __ldg(gsrc + (size_t)c * plane + col);
+        }
     }
 }
 
@@ -254,65 +316,95 @@ k_bwd_rows_nchw(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const
 //   g      = rows[voxel(p)]                               (QuickCumsum.backward + griddify backward)
 //   gp_d   = <g, ctx>            d_ctx += prob_d * g        (outer product backward, models.py:59)
 //   d_logit_d = prob_d * (gp_d - sum_d' prob_d' gp_d')      (softmax backward, models.py:50)
-template <int KC, int NCH, bool CL>
+// Lane `dl` of a 32-depth chunk owns depth dl: it loads voxel id / prob / row offset once; rows are then
+// broadcast by shuffle and loaded by all lanes (dropped points read row 0 with weight 0, so the loop is
+// branch-free and loads of consecutive depths overlap).  The per-depth dot products are reduced through
+// shared memory (one column sum per lane) instead of 5 shuffles per depth.  The 8 warps of a CTA own 8
+// consecutive pixels; outputs are staged in shared memory and written as 32-byte runs.
+template <int VW, int KC, int NCH, bool CL>
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_bwd_gather(Dims d, const int32_t *__restrict__ vox, const float *__restrict__ prob, const float *__restrict__ ctx_t,
              const float *__restrict__ rows, float *__restrict__ grad_dn) {
-    const int pix = blockIdx.x * SPLAT_WARPS + (threadIdx.x >> 5);
-    if (pix >= d.B * d.N * d.HW) return;
-    const int lane = threadIdx.x & 31;
-    const int bn = pix / d.HW, hw = pix - bn * d.HW;
-    float ctx[KC], dctx[KC];
+    extern __shared__ __align__(16) float smem[];
+    using CM = ChanMap<VW, KC>;
+    constexpr int NA = CM::NA;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npix = d.B * d.N * d.HW;
+    const int pix0 = blockIdx.x * SPLAT_WARPS;
+    const int pix = pix0 + warp;
+    const int DC = d.D + d.C;
+    float *part = smem + warp * (32 * 33);                 // [32 depths][33] partial dot products
+    float *stage = smem + SPLAT_WARPS * (32 * 33);         // [D+C][8] outputs of the CTA's 8 pixels
+    if (pix < npix) {
+        const int bn = pix / d.HW, hw = pix - bn * d.HW;
+        float ctx[NA], dctx[NA];
+        load_row<VW, KC>(ctx_t + (size_t)pix * d.C, 1, lane, d.C, ctx);
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        ctx[k] = (lane + 32 * k < d.C) ? __ldg(ctx_t + (size_t)pix * d.C + lane + 32 * k) : 0.f;
-        dctx[k] = 0.f;
-    }
-    int vv[NCH]; float pr[NCH], gp[NCH];
+        for (int a = 0; a < NA; ++a) dctx[a] = 0.f;
+        float pr[NCH], gp[NCH];
+        long long ro[NCH];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        const int dd = ch * 32 + lane;
-        vv[ch] = -1; pr[ch] = 0.f; gp[ch] = 0.f;
-        if (dd < d.D) {
-            const size_t p = ((size_t)bn * d.D + dd) * d.HW + hw;
-            vv[ch] = __ldg(vox + p);
-            pr[ch] = __ldg(prob + p);
-        }
-    }
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        const int cnt = min(32, d.D - ch * 32);
-        for (int dl = 0; dl < cnt; ++dl) {
-            const int v = __shfl_sync(LSS_FULL_MASK, vv[ch], dl);
-            if (v < 0) continue;                                   // warp-uniform
-            const float pj = __shfl_sync(LSS_FULL_MASK, pr[ch], dl);
-            const float *row = rows + (CL ? voxel_row_offset_cl(v, d) : (size_t)v * d.C);
-            float dot = 0.f;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int c = lane + 32 * k;
-                const float g = c < d.C ? __ldg(row + c) : 0.f;
-                dot = fmaf(g, ctx[k], dot);
-                dctx[k] = fmaf(pj, g, dctx[k]);
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int dd = ch * 32 + lane;
+            pr[ch] = 0.f; gp[ch] = 0.f; ro[ch] = 0;
+            if (dd < d.D) {
+                const size_t p = ((size_t)bn * d.D + dd) * d.HW + hw;
+                const int v = __ldg(vox + p);
+                pr[ch] = __ldg(prob + p);      // dropped points still take part in the softmax backward
+                ro[ch] = v < 0 ? -1 : (CL ? (long long)voxel_row_offset_cl(v, d) : (long long)v * d.C);
             }
-            dot = warp_sum(dot);
-            if (lane == dl) gp[ch] = dot;
+        }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int cnt = min(32, d.D - ch * 32);
+            if (cnt <= 0) break;
+#pragma unroll 4
+            for (int dl = 0; dl < cnt; ++dl) {
+                const long long o = __shfl_sync(LSS_FULL_MASK, ro[ch], dl);
+                const float pj = o < 0 ? 0.f : __shfl_sync(LSS_FULL_MASK, pr[ch], dl);   // dropped: weight 0
+                float g[NA];
+                // dropped point: read this pixel's own (finite) context row instead, weight 0
+                load_row<VW, KC>(o < 0 ? ctx_t + (size_t)pix * d.C : rows + o, 1, lane, d.C, g);
+                float dot = 0.f;
+#pragma unroll
+                for (int a = 0; a < NA; ++a) {
+                    dot = fmaf(g[a], ctx[a], dot);
+                    dctx[a] = fmaf(pj, g[a], dctx[a]);
+                }
+                part[dl * 33 + lane] = o < 0 ? 0.f : dot;
+            }
+            __syncwarp();
+            if (lane < cnt) {
+                float sacc = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) sacc += part[lane * 33 + j];
+                gp[ch] = sacc;
+            }
+            __syncwarp();
+        }
+        float sdot = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) sdot = fmaf(pr[ch], gp[ch], sdot);
+        sdot = warp_sum(sdot);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int dd = ch * 32 + lane;
+            if (dd < d.D) stage[dd * SPLAT_WARPS + warp] = pr[ch] * (gp[ch] - sdot);
+        }
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            const int c = CM::ch(lane, a);
+            if (VW || c < d.C) stage[(d.D + c) * SPLAT_WARPS + warp] = dctx[a];
         }
     }
-    float sdot = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) sdot = fmaf(pr[ch], gp[ch], sdot);
-    sdot = warp_sum(sdot);
-    float *out = grad_dn + (size_t)bn * (d.D + d.C) * d.HW + hw;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        const int dd = ch * 32 + lane;
-        if (dd < d.D) out[(size_t)dd * d.HW] = pr[ch] * (gp[ch] - sdot);
-    }
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int c = lane + 32 * k;
-        if (c < d.C) out[(size_t)(d.D + c) * d.HW] = dctx[k];
+    __syncthreads();
+    // write [D+C] x 8 pixels: 8 consecutive threads cover 8 consecutive pixels of one channel row
+    const int pl = threadIdx.x & (SPLAT_WARPS - 1);
+    const int opix = pix0 + pl;
+    if (opix < npix) {
+        const int bn = opix / d.HW, hw = opix - bn * d.HW;
+        float *out = grad_dn + (size_t)bn * DC * d.HW + hw;
+        for (int c = threadIdx.x >> 3; c < DC; c += SPLAT_THREADS / SPLAT_WARPS) out[(size_t)c * d.HW] = stage[c * SPLAT_WARPS + pl];
     }
 }
 
@@ -338,40 +430,56 @@ static inline Tiling make_tiling(const lss_plan_layout *L) {
     Tiling t; t.TY = L->tile_cols; t.nty = L->tiles_per_row; t.n_tiles = L->n_tiles; return t;
 }
 
-template <int KC, bool ATOMIC, bool CL, bool DENSE>
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE, bool VEC4>
 static int launch_fwd_tile(const Dims &d, const Tiling &tl, const int32_t *tile_start, const uint32_t *entries,
                            const SrcArgs &src, float *bev, cudaStream_t s) {
-    const int TYP = tl.TY | 1;
-    size_t smem = 0;
-    if (ATOMIC) smem = (size_t)(CL ? tl.TY * d.C : d.C * TYP) * 4;
-    else smem = (size_t)(CL ? 0 : d.C * TYP) * 4 + (size_t)(tl.TY + 1) * 4;
-    auto kern = k_splat_fwd_tile<KC, ATOMIC, CL, DENSE>;
+    const size_t smem = (size_t)(CL ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
+    auto kern = k_splat_fwd_tile<VW, KC, ATOMIC, CL, DENSE, VEC4>;
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return LSS_ERR_CUDA;
+    if (smem > 48 * 1024) {
+        static bool configured = false;    // per instantiation
+        if (!configured) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return LSS_ERR_CUDA;
+            configured = true;
+        }
+    }
     kern<<<tl.n_tiles, SPLAT_THREADS, smem, s>>>(d, tl, tile_start, entries, src, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
 
-template <int KC, bool DENSE>
-static int dispatch_fwd_tile(bool atomic, bool cl, const Dims &d, const Tiling &tl, const int32_t *ts, const uint32_t *en,
-                             const SrcArgs &src, float *bev, cudaStream_t s) {
-    if (atomic) return cl ? launch_fwd_tile<KC, true, true, DENSE>(d, tl, ts, en, src, bev, s)
-                          : launch_fwd_tile<KC, true, false, DENSE>(d, tl, ts, en, src, bev, s);
-    return cl ? launch_fwd_tile<KC, false, true, DENSE>(d, tl, ts, en, src, bev, s)
-              : launch_fwd_tile<KC, false, false, DENSE>(d, tl, ts, en, src, bev, s);
+template <int VW, int KC, bool DENSE>
+static int dispatch_fwd_flags(bool atomic, bool cl, bool vec4, const Dims &d, const Tiling &tl, const int32_t *ts,
+                              const uint32_t *en, const SrcArgs &src, float *bev, cudaStream_t s) {
+#define FWD_CASE(A, L, V) return launch_fwd_tile<VW, KC, A, L, DENSE, V>(d, tl, ts, en, src, bev, s)
+    if (atomic) { if (cl) { if (vec4) FWD_CASE(true, true, true); else FWD_CASE(true, true, false); }
+                  else    { if (vec4) FWD_CASE(true, false, true); else FWD_CASE(true, false, false); } }
+    else        { if (cl) { if (vec4) FWD_CASE(false, true, true); else FWD_CASE(false, true, false); }
+                  else    { if (vec4) FWD_CASE(false, false, true); else FWD_CASE(false, false, false); } }
+#undef FWD_CASE
+}
+
+// vector stores of the tile need 16-byte aligned rows in global memory
+static bool tile_vec4_ok(const Dims &d, const Tiling &tl, bool cl, const float *bev) {
+    if (!lss_aligned(bev, 16)) return false;
+    if (cl) return d.C % 4 == 0;
+    return d.ny % 4 == 0 && tl.TY % 4 == 0;
 }
 
 template <bool DENSE>
-static int dispatch_fwd_kc(bool atomic, bool cl, const Dims &d, const Tiling &tl, const int32_t *ts, const uint32_t *en,
-                           const SrcArgs &src, float *bev, cudaStream_t s) {
+static int dispatch_fwd(bool atomic, bool cl, const Dims &d, const Tiling &tl, const int32_t *ts, const uint32_t *en,
+                        const SrcArgs &src, float *bev, cudaStream_t s) {
+    const bool vec4 = tile_vec4_ok(d, tl, cl, bev);
+    if (!DENSE && lss_aligned(src.base, 16)) {
+        if (d.C == 32) return dispatch_fwd_flags<1, 1, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+        if (d.C == 64) return dispatch_fwd_flags<2, 1, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+        if (d.C == 128) return dispatch_fwd_flags<4, 1, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+    }
     const int kc = lss_kc_for(d.C);
-    if (kc <= 1) return dispatch_fwd_tile<1, DENSE>(atomic, cl, d, tl, ts, en, src, bev, s);
-    if (kc <= 2) return dispatch_fwd_tile<2, DENSE>(atomic, cl, d, tl, ts, en, src, bev, s);
-    if (kc <= 4) return dispatch_fwd_tile<4, DENSE>(atomic, cl, d, tl, ts, en, src, bev, s);
-    return dispatch_fwd_tile<8, DENSE>(atomic, cl, d, tl, ts, en, src, bev, s);
+    if (kc <= 2) return dispatch_fwd_flags<0, 2, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+    if (kc <= 4) return dispatch_fwd_flags<0, 4, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+    return dispatch_fwd_flags<0, 8, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
 }
 
 static size_t bev_elems(const Dims &d) { return (size_t)d.B * d.nz * d.C * d.nx * d.ny; }
@@ -395,7 +503,7 @@ extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, con
     SrcArgs src{};
     src.base = ctx_t; src.prob = prob;
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
-        return dispatch_fwd_kc<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, d, tl, tile_start, entries, src, bev, s);
+        return dispatch_fwd<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, d, tl, tile_start, entries, src, bev, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {
         if (cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
         const int npix = d.B * d.N * d.HW;
@@ -433,7 +541,7 @@ extern "C" int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout
     src.base = x; src.prob = nullptr;
     for (int i = 0; i < 6; ++i) src.s[i] = xs_host[i];
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
-        return dispatch_fwd_kc<true>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, d, tl, tile_start, entries, src, bev, s);
+        return dispatch_fwd<true>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, d, tl, tile_start, entries, src, bev, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {
         if (cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
         const int grid = (d.n_points + SPLAT_WARPS - 1) / SPLAT_WARPS;
@@ -447,31 +555,55 @@ extern "C" int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout
 
 static int launch_bwd_rows(const Dims &d, const Tiling &tl, const int32_t *tile_start, const uint32_t *entries,
                            const float *grad_bev, float *rows, cudaStream_t s) {
-    const size_t smem = (size_t)d.C * (tl.TY | 1) * 4 + (size_t)tl.TY * 4;
-    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(k_bwd_rows_nchw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return LSS_ERR_CUDA;
+    const size_t smem = (size_t)((tl.TY + 31) / 32) * 4;
     k_bwd_rows_nchw<<<tl.n_tiles, SPLAT_THREADS, smem, s>>>(d, tl, tile_start, entries, grad_bev, rows);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
 
-template <int KC, int NCH>
-static void launch_gather(bool cl, int grid, cudaStream_t s, const Dims &d, const int32_t *vox, const float *prob,
-                          const float *ctx_t, const float *rows, float *grad_dn) {
-    if (cl) k_bwd_gather<KC, NCH, true><<<grid, SPLAT_THREADS, 0, s>>>(d, vox, prob, ctx_t, rows, grad_dn);
-    else k_bwd_gather<KC, NCH, false><<<grid, SPLAT_THREADS, 0, s>>>(d, vox, prob, ctx_t, rows, grad_dn);
+template <int VW, int KC, int NCH, bool CL>
+static int launch_gather_one(int grid, size_t smem, cudaStream_t s, const Dims &d, const int32_t *vox, const float *prob,
+                             const float *ctx_t, const float *rows, float *grad_dn) {
+    auto kern = k_bwd_gather<VW, KC, NCH, CL>;
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return LSS_ERR_CUDA;
+            configured = true;
+        }
+    }
+    kern<<<grid, SPLAT_THREADS, smem, s>>>(d, vox, prob, ctx_t, rows, grad_dn);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
 }
 
-template <int KC>
-static void dispatch_gather_nch(bool cl, int grid, cudaStream_t s, const Dims &d, const int32_t *vox, const float *prob,
-                                const float *ctx_t, const float *rows, float *grad_dn) {
+template <int VW, int KC>
+static int dispatch_gather(bool cl, cudaStream_t s, const Dims &d, const int32_t *vox, const float *prob,
+                           const float *ctx_t, const float *rows, float *grad_dn) {
+    const int npix = d.B * d.N * d.HW;
+    const int grid = (npix + SPLAT_WARPS - 1) / SPLAT_WARPS;
+    const size_t smem = ((size_t)SPLAT_WARPS * 32 * 33 + (size_t)(d.D + d.C) * SPLAT_WARPS) * 4;
     const int nch = (d.D + 31) / 32;
-    if (nch <= 1) launch_gather<KC, 1>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_dn);
-    else if (nch <= 2) launch_gather<KC, 2>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_dn);
-    else if (nch <= 4) launch_gather<KC, 4>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_dn);
-    else launch_gather<KC, 8>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_dn);
+#define G_CASE(N) return cl ? launch_gather_one<VW, KC, N, true>(grid, smem, s, d, vox, prob, ctx_t, rows, grad_dn) \
+                            : launch_gather_one<VW, KC, N, false>(grid, smem, s, d, vox, prob, ctx_t, rows, grad_dn)
+    if (nch <= 2) G_CASE(2);
+    if (nch <= 4) G_CASE(4);
+    G_CASE(8);
+#undef G_CASE
+}
+
+static int run_gather(bool cl, cudaStream_t s, const Dims &d, const int32_t *vox, const float *prob, const float *ctx_t,
+                      const float *rows, float *grad_dn) {
+    const bool vec_ok = lss_aligned(ctx_t, 16) && lss_aligned(rows, 16) && (!cl || (d.C % 4 == 0));
+    if (vec_ok && d.C == 32) return dispatch_gather<1, 1>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
+    if (vec_ok && d.C == 64) return dispatch_gather<2, 1>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
+    if (vec_ok && d.C == 128) return dispatch_gather<4, 1>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
+    const int kc = lss_kc_for(d.C);
+    if (kc <= 2) return dispatch_gather<0, 2>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
+    if (kc <= 4) return dispatch_gather<0, 4>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
+    return dispatch_gather<0, 8>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
 }
 
 extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
@@ -499,15 +631,7 @@ extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, con
         if (st != LSS_OK) return st;
         rows = grad_rows;
     }
-    const int npix = d.B * d.N * d.HW;
-    const int grid = (npix + SPLAT_WARPS - 1) / SPLAT_WARPS;
-    const int kc = lss_kc_for(d.C);
-    if (kc <= 1) dispatch_gather_nch<1>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_depthnet);
-    else if (kc <= 2) dispatch_gather_nch<2>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_depthnet);
-    else if (kc <= 4) dispatch_gather_nch<4>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_depthnet);
-    else dispatch_gather_nch<8>(cl, grid, s, d, vox, prob, ctx_t, rows, grad_depthnet);
-    LSS_CHECK_LAUNCH();
-    return LSS_OK;
+    return run_gather(cl, s, d, vox, prob, ctx_t, rows, grad_depthnet);
 }
 
 extern "C" int lss_voxel_pooling_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
