@@ -166,19 +166,32 @@ class BufferSet:
         self.out = {}
 
 
-def one_step(ops, prob, frustum, bs, mode, channels_last, inverse):
-    """The whole path for one batch; every launch goes through the C ABI on the current stream."""
+STAGES = ("calib", "plan_build", "lift_prepare", "splat_fwd", "splat_bwd")
+
+
+def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAGES)):
+    """The whole path for one batch; every launch goes through the C ABI on the current stream.
+    `upto` < 5 runs only the first stages (used to attribute in-step time to each stage)."""
     if inverse == "device":
         M1, M2 = ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots)
     else:
         M1, M2 = ops.calib_matrices_reference(bs.rots, bs.intrins, bs.post_rots)
+    bs.out.update({"M1": M1, "M2": M2})
+    if upto < 2:
+        return
     calib = (frustum, bs.post_trans, M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), bs.trans)
     ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=bs.plan)
+    if upto < 3:
+        return
     pr, ct = ops.lift_prepare(prob, bs.dn)
+    bs.out.update({"pr": pr, "ct": ct})
+    if upto < 4:
+        return
     bev = ops.splat_fwd(prob, bs.plan, pr, ct, mode, channels_last)
-    grad = ops.splat_bwd(prob, bs.plan, bs.grad_bev, pr, ct, bs.rows)
-    bs.out = {"bev": bev, "grad": grad, "pr": pr, "ct": ct, "M1": M1, "M2": M2}
-    return bev, grad
+    bs.out["bev"] = bev
+    if upto < 5:
+        return
+    bs.out["grad"] = ops.splat_bwd(prob, bs.plan, bs.grad_bev, pr, ct, bs.rows)
 
 
 LAUNCHES_PER_STEP = {"sorted": 8, "atomic": 7, "red": 8}   # calib, voxel+count, scatter, [sort], lift, fwd(+memset), rows, gather
@@ -346,6 +359,14 @@ def main():
         one_step(ops, prob, frustum, bs, args.mode, channels_last, args.inverse)
     torch.cuda.synchronize()
     layout_code = 1 if channels_last else 0
+    # (a) in-step attribution: graphs of the first k stages, T_k - T_(k-1) = cost of stage k inside the step
+    #     (its inputs are L2-hot exactly as in the real step); (b) each stage alone (inputs L2-cold)
+    instep, prev = {}, 0.0
+    for k, name in enumerate(STAGES, start=1):
+        tk = time_kernel(lambda bs, k=k: one_step(ops, prob, frustum, bs, args.mode, channels_last, args.inverse, upto=k),
+                         sets, kiters, stream)
+        instep[name] = tk - prev
+        prev = tk
     stages = {}
     stages["calib"] = time_kernel(lambda bs: ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots), sets, kiters, stream)
     stages["plan_build"] = time_kernel(
@@ -373,7 +394,8 @@ def main():
             "algorithmic_bytes_per_launch": fwd_bytes, "kernel_us": round(stages["splat_fwd"] * 1e6, 2),
             "step_algorithmic_bytes": fwd_bytes + bwd_bytes,
             "step_frac": round((fwd_bytes + bwd_bytes) / step_s / 1e9 / peak, 4),
-            "stage_us": {k: round(v * 1e6, 2) for k, v in stages.items()}}
+            "stage_us_in_step": {k: round(v * 1e6, 2) for k, v in instep.items()},
+            "stage_us_alone_l2_cold": {k: round(v * 1e6, 2) for k, v in stages.items()}}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

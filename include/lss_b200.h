@@ -156,12 +156,24 @@ int lss_plan_reference_order(const lss_problem *p, const lss_plan_layout *L, con
 int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
                      void *stream);
 
+/* Kernel variants of the tile-owner forward (same results; SORTED is bit-identical across variants). */
+enum { LSS_VARIANT_AUTO = 0,
+       LSS_VARIANT_TILE = 1,      /* tile staged in shared memory, every BEV element written once, no memset */
+       LSS_VARIANT_TILE_TMA = 2,  /* same, persistent CTAs, rows streamed with cp.async.bulk (TMA)            */
+       LSS_VARIANT_SCATTER = 3    /* BEV zeroed by cudaMemsetAsync, voxel sums stored straight to global      */ };
+
+/* Zero a BEV tensor (what `torch.zeros` does at models.py:240).  Callers may issue it early / on another
+ * stream and pass precleared=1 to lss_splat_fwd so that it overlaps the plan build. */
+int lss_bev_clear(const lss_problem *p, float *bev, void *stream);
+
 /* voxel_pooling of the lifted features (models.py:59 outer product + :204-246), without materialising
  * them:  bev[b, iz*C+c, ix, iy] = sum_{p in voxel} prob[p] * ctx_t[pixel(p), c].
- * Every element of `bev` is written exactly once (zeros included): no memset, no global atomics
- * (modes SORTED / SMEM_ATOMIC).  bev f32[B, nz*C, nx, ny] in `layout`. */
+ * No global atomics in modes SORTED / SMEM_ATOMIC with the TILE variants.  `precleared` != 0 promises that
+ * `bev` is already all-zero (only read by the SCATTER variant and RED_GLOBAL mode).
+ * bev f32[B, nz*C, nx, ny] in `layout`. */
 int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
-                  const float *prob, const float *ctx_t, float *bev, int mode, int layout, void *stream);
+                  const float *prob, const float *ctx_t, float *bev, int mode, int layout, int variant,
+                  int precleared, void *stream);
 
 /* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
  * autograd backward of models.py:58-59,:199-200,:240-244):
@@ -180,7 +192,7 @@ int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
  * view, models.py:199-200).  bev as above.  Replaces models.py:204-246 given a plan built from `geom`. */
 int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                           const float *x, const int64_t *xs_host, float *bev, int mode, int layout,
-                          void *stream);
+                          int variant, int precleared, void *stream);
 
 /* grad_x f32[n_points, C] contiguous: row p = grad_bev[b, iz*C:(iz+1)*C, ix, iy] of p's voxel, or 0. */
 int lss_voxel_pooling_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,

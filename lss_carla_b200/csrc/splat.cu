@@ -18,10 +18,14 @@
 // Backward is a pure gather (tools.py:212-219): for NCHW gradients a tile-owner kernel first gathers the
 // channels of every hit voxel into a channel-contiguous row; a pixel-owner kernel then reads one row per
 // frustum point and fuses the outer-product and softmax backward.
+#include <cstdlib>
+
 #include "common.cuh"
 
 #define SPLAT_THREADS 256
 #define SPLAT_WARPS (SPLAT_THREADS / 32)
+
+__device__ __forceinline__ unsigned long long lss_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 struct SrcArgs {
     const float *base;   // LIFT: ctx_t [B*N, HW, C]        DENSE: x with strides s[0..5]
@@ -121,105 +125,203 @@ __device__ __forceinline__ void store_tile(const Tile2D &t, const float *__restr
 // ------------------------------------------------------------------------------------------------
 // forward, tile-owner
 // ------------------------------------------------------------------------------------------------
-template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE, bool VEC4>
-__global__ void __launch_bounds__(SPLAT_THREADS)
-k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const uint32_t *__restrict__ entries,
-                 SrcArgs src, float *__restrict__ bev) {
-    extern __shared__ __align__(16) float smem[];
+
+// Walk the bucket `ent[0..n)` of one tile and deliver every voxel sum to out[c*cstr + col*colstr]
+// (shared-memory staging tile or the BEV tensor itself).
+//
+// SORTED: a warp takes the 32-entry chunk c0 and owns every voxel segment that STARTS in it (head bits
+// found by ballot); it requests UB context rows before consuming them, adds float32(prob*ctx) in
+// ascending point order and closes the running sum at every head.  A segment is never split between
+// warps: the last segment of a chunk is followed into the next chunks by the same warp.
+// ATOMIC: no order, every entry is added with an atomic (shared or global).
+template <int VW, int KC, bool ATOMIC, bool DENSE>
+__device__ __forceinline__ void walk_bucket(const Dims &d, const SrcArgs &src, int b, const uint32_t *__restrict__ ent,
+                                            int n, float *__restrict__ out, long long cstr, long long colstr) {
     using CM = ChanMap<VW, KC>;
     constexpr int NA = CM::NA;
-    const int tile = blockIdx.x;
-    const TileCoord tc = tile_coord(d, tl, tile);
-    const Tile2D t2 = tile_2d<CL>(d, tl, tc);
-    const int s = __ldg(tile_start + tile), n = __ldg(tile_start + tile + 1) - s;
-    if (n == 0) { store_tile<VEC4>(t2, nullptr, bev); return; }   // nothing lands here: stream zeros
-
+    constexpr int UB = NA >= 8 ? 2 : (NA >= 4 ? 4 : 8);   // rows in flight per warp (register budget)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = d.C;
     const long long cs = DENSE ? src.s[5] : 1;
-    const int SRS = t2.SRS;
-    {   // zero the staging tile with 16-byte stores (its size is a multiple of 4 floats)
-        const int n4 = (CL ? tl.TY * C : C * SRS) >> 2;
-        float4 *z = reinterpret_cast<float4 *>(smem);
-        for (int i = threadIdx.x; i < n4; i += SPLAT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#define LSS_FLUSH(col)                                                                  \
+    _Pragma("unroll") for (int a = 0; a < NA; ++a) {                                    \
+        const int c = CM::ch(lane, a);                                                  \
+        if (VW || c < C) out[c * cstr + (col) * colstr] = acc[a];                       \
     }
-    __syncthreads();
-    const uint32_t *ent = entries + s;
 
     for (int c0 = warp * 32; c0 < n; c0 += SPLAT_THREADS) {
         const int i = c0 + lane;
         const bool valid = i < n;
         const uint32_t e = valid ? __ldg(ent + i) : 0u;
         float w = 0.f; long long off = 0;
-        if (valid) entry_source<DENSE>(d, src, tc.b, e, w, off);
+        if (valid) entry_source<DENSE>(d, src, b, e, w, off);
         const int lim = min(32, n - c0);
+        const int col = (int)(e >> LSS_PIDX_BITS);
         if (ATOMIC) {
-            const int col = (int)(e >> LSS_PIDX_BITS);
-#pragma unroll 4
-            for (int jj = 0; jj < lim; ++jj) {
-                const float wj = __shfl_sync(LSS_FULL_MASK, w, jj);
-                const long long oj = __shfl_sync(LSS_FULL_MASK, off, jj);
-                const int cj = __shfl_sync(LSS_FULL_MASK, col, jj);
-                float x[NA];
-                load_row<VW, KC>(src.base + oj, cs, lane, C, x);
+            for (int j0 = 0; j0 < lim; j0 += UB) {
+                float x[UB][NA];
 #pragma unroll
-                for (int a = 0; a < NA; ++a) {
-                    const int c = CM::ch(lane, a);
-                    if (VW || c < C) atomicAdd(smem + (CL ? cj * C + c : c * SRS + cj), __fmul_rn(wj, x[a]));
-                }
-            }
-        } else {
-            const uint32_t ep = (valid && i > 0) ? __ldg(ent + i - 1) : 0u;
-            const bool head = valid && (i == 0 || (e >> LSS_PIDX_BITS) != (ep >> LSS_PIDX_BITS));
-            unsigned heads = __ballot_sync(LSS_FULL_MASK, head);
-            while (heads) {                          // every voxel segment that starts in this chunk
-                const int sl = __ffs(heads) - 1;
-                heads &= heads - 1;
-                const int el = heads ? __ffs(heads) - 1 : lim;
-                const int col = (int)(__shfl_sync(LSS_FULL_MASK, e, sl) >> LSS_PIDX_BITS);
-                float acc[NA];
+                for (int u = 0; u < UB; ++u)       // lanes >= lim hold off = 0: a valid (unused) row
+                    load_row<VW, KC>(src.base + __shfl_sync(LSS_FULL_MASK, off, (j0 + u) & 31), cs, lane, C, x[u]);
 #pragma unroll
-                for (int a = 0; a < NA; ++a) acc[a] = 0.f;
-#pragma unroll 4
-                for (int jj = sl; jj < el; ++jj) {   // ascending point order
-                    const float wj = __shfl_sync(LSS_FULL_MASK, w, jj);
-                    const long long oj = __shfl_sync(LSS_FULL_MASK, off, jj);
-                    float x[NA];
-                    load_row<VW, KC>(src.base + oj, cs, lane, C, x);
+                for (int u = 0; u < UB; ++u) {
+                    if (j0 + u >= lim) break;
+                    const float wj = __shfl_sync(LSS_FULL_MASK, w, j0 + u);
+                    const int cj = __shfl_sync(LSS_FULL_MASK, col, j0 + u);
 #pragma unroll
-                    for (int a = 0; a < NA; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[a]));
-                }
-                if (!heads && lim == 32) {           // last segment of a full chunk may run on
-                    for (int k = c0 + 32; k < n; k += 32) {
-                        const int i2 = k + lane;
-                        const uint32_t e2 = i2 < n ? __ldg(ent + i2) : 0u;
-                        const bool same = i2 < n && (int)(e2 >> LSS_PIDX_BITS) == col;
-                        const unsigned m = __ballot_sync(LSS_FULL_MASK, same);
-                        const int cnt = m == LSS_FULL_MASK ? 32 : __ffs(~m) - 1;
-                        if (cnt == 0) break;
-                        float w2 = 0.f; long long off2 = 0;
-                        if (lane < cnt) entry_source<DENSE>(d, src, tc.b, e2, w2, off2);
-                        for (int jj = 0; jj < cnt; ++jj) {
-                            const float wj = __shfl_sync(LSS_FULL_MASK, w2, jj);
-                            const long long oj = __shfl_sync(LSS_FULL_MASK, off2, jj);
-                            float x[NA];
-                            load_row<VW, KC>(src.base + oj, cs, lane, C, x);
-#pragma unroll
-                            for (int a = 0; a < NA; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[a]));
-                        }
-                        if (cnt < 32) break;
+                    for (int a = 0; a < NA; ++a) {
+                        const int c = CM::ch(lane, a);
+                        if (VW || c < C) atomicAdd(out + c * cstr + cj * colstr, __fmul_rn(wj, x[u][a]));
                     }
                 }
+            }
+            continue;
+        }
+        const uint32_t ep = (valid && i > 0) ? __ldg(ent + i - 1) : 0u;
+        const bool head = valid && (i == 0 || (e >> LSS_PIDX_BITS) != (ep >> LSS_PIDX_BITS));
+        const unsigned heads = __ballot_sync(LSS_FULL_MASK, head);
+        if (heads == 0u) continue;               // the whole chunk continues a segment owned by an earlier warp
+        const int first = __ffs(heads) - 1;      // entries before it belong to that earlier segment too
+        float acc[NA];
 #pragma unroll
-                for (int a = 0; a < NA; ++a) {
-                    const int c = CM::ch(lane, a);
-                    if (VW || c < C) smem[CL ? col * C + c : c * SRS + col] = acc[a];
+        for (int a = 0; a < NA; ++a) acc[a] = 0.f;
+        int cur = -1;
+        for (int j0 = first & ~(UB - 1); j0 < lim; j0 += UB) {
+            float x[UB][NA];
+#pragma unroll
+            for (int u = 0; u < UB; ++u)         // row addresses depend on the entry only, not on prob
+                load_row<VW, KC>(src.base + __shfl_sync(LSS_FULL_MASK, off, (j0 + u) & 31), cs, lane, C, x[u]);
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int jj = j0 + u;
+                if (jj >= lim) break;
+                const float wj = __shfl_sync(LSS_FULL_MASK, w, jj);
+                if ((heads >> jj) & 1u) {
+                    if (cur >= 0) { LSS_FLUSH(cur) }
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) acc[a] = 0.f;
+                    cur = __shfl_sync(LSS_FULL_MASK, col, jj);
+                }
+                if (jj >= first) {
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[u][a]));
                 }
             }
         }
+        if (lim == 32) {                         // the last segment of a full chunk may run on
+            for (int k = c0 + 32; k < n; k += 32) {
+                const int i2 = k + lane;
+                const uint32_t e2 = i2 < n ? __ldg(ent + i2) : 0u;
+                const bool same = i2 < n && (int)(e2 >> LSS_PIDX_BITS) == cur;
+                const unsigned m = __ballot_sync(LSS_FULL_MASK, same);
+                const int cnt = m == LSS_FULL_MASK ? 32 : __ffs(~m) - 1;
+                if (cnt == 0) break;
+                float w2 = 0.f; long long off2 = 0;
+                if (lane < cnt) entry_source<DENSE>(d, src, b, e2, w2, off2);
+                for (int jj = 0; jj < cnt; ++jj) {
+                    const float wj = __shfl_sync(LSS_FULL_MASK, w2, jj);
+                    float x[NA];
+                    load_row<VW, KC>(src.base + __shfl_sync(LSS_FULL_MASK, off2, jj), cs, lane, C, x);
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[a]));
+                }
+                if (cnt < 32) break;
+            }
+        }
+        LSS_FLUSH(cur)
     }
+#undef LSS_FLUSH
+}
+
+__device__ __forceinline__ void zero_smem(float *buf, int n_floats) {
+    float4 *z = reinterpret_cast<float4 *>(buf);
+    for (int i = threadIdx.x; i < (n_floats >> 2); i += SPLAT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// One CTA per tile, LSU stores.  Generic path: any shape / alignment.
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE, bool VEC4>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const uint32_t *__restrict__ entries,
+                 SrcArgs src, float *__restrict__ bev) {
+    extern __shared__ __align__(16) float smem[];
+    const int tile = blockIdx.x;
+    const TileCoord tc = tile_coord(d, tl, tile);
+    const Tile2D t2 = tile_2d<CL>(d, tl, tc);
+    const int s = __ldg(tile_start + tile), n = __ldg(tile_start + tile + 1) - s;
+    if (n == 0) { store_tile<VEC4>(t2, nullptr, bev); return; }   // nothing lands here: stream zeros
+    zero_smem(smem, CL ? tl.TY * d.C : d.C * t2.SRS);
+    __syncthreads();
+    walk_bucket<VW, KC, ATOMIC, DENSE>(d, src, tc.b, entries + s, n, smem, CL ? 1 : t2.SRS, CL ? d.C : 1);
     __syncthreads();
     store_tile<VEC4>(t2, smem, bev);
+}
+
+// ---- bulk-copy (TMA) helpers: shared -> global, tracked by per-thread bulk async-groups
+__device__ __forceinline__ void bulk_store(float *gdst, const float *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Persistent CTAs, two staging tiles in shared memory, rows streamed out by the TMA unit
+// (cp.async.bulk shared -> global): while tile k drains asynchronously the CTA gathers tile k+1, so the
+// LSU only carries the gather and the few STS of non-empty voxels.  Empty tiles are streamed from a
+// constant zero row.  Requires 16-byte aligned rows (host checks); NR rows of RL floats per tile.
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_splat_fwd_tma(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const uint32_t *__restrict__ entries,
+                SrcArgs src, float *__restrict__ bev, int tile_floats) {
+    extern __shared__ __align__(128) float smem[];
+    float *zrow = smem + 2 * tile_floats;             // max row length zeros
+    const int zlen = CL ? d.C : tl.TY;
+    for (int i = threadIdx.x; i < zlen; i += SPLAT_THREADS) zrow[i] = 0.f;
+    fence_async_smem();
+    __syncthreads();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tl.n_tiles; tile += gridDim.x, ++it) {
+        float *buf = smem + (it & 1) * tile_floats;
+        const TileCoord tc = tile_coord(d, tl, tile);
+        const Tile2D t2 = tile_2d<CL>(d, tl, tc);
+        const int s = __ldg(tile_start + tile), n = __ldg(tile_start + tile + 1) - s;
+        float *g = bev + t2.gbase;
+        const unsigned row_bytes = (unsigned)t2.RL * 4u;
+        if (n == 0) {
+            for (int r = threadIdx.x; r < t2.NR; r += SPLAT_THREADS) bulk_store(g + (size_t)r * t2.GRS, zrow, row_bytes);
+            bulk_commit();                            // every thread commits one group per tile (possibly empty)
+            continue;
+        }
+        bulk_wait_read<1>();                          // this buffer was last streamed two tiles ago
+        __syncthreads();
+        zero_smem(buf, tile_floats);
+        __syncthreads();
+        walk_bucket<VW, KC, ATOMIC, DENSE>(d, src, tc.b, entries + s, n, buf, CL ? 1 : t2.SRS, CL ? d.C : 1);
+        fence_async_smem();                           // generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        for (int r = threadIdx.x; r < t2.NR; r += SPLAT_THREADS) bulk_store(g + (size_t)r * t2.GRS, buf + r * t2.SRS, row_bytes);
+        bulk_commit();
+    }
+    bulk_wait_all();
+}
+
+// Scatter variant: the BEV tensor has been zeroed beforehand (cudaMemsetAsync, possibly on another
+// stream, overlapping the plan build); one light CTA per non-empty tile walks its bucket and stores
+// every voxel sum straight to global memory.  No shared memory, no barriers: many CTAs stay resident
+// and their dependent load chains overlap.  Each voxel is written by exactly one warp, once.
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_splat_fwd_scatter(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const uint32_t *__restrict__ entries,
+                    SrcArgs src, float *__restrict__ bev) {
+    const int tile = blockIdx.x;
+    const int s = __ldg(tile_start + tile), n = __ldg(tile_start + tile + 1) - s;
+    if (n == 0) return;
+    const TileCoord tc = tile_coord(d, tl, tile);
+    const Tile2D t2 = tile_2d<CL>(d, tl, tc);
+    walk_bucket<VW, KC, ATOMIC, DENSE>(d, src, tc.b, entries + s, n, bev + t2.gbase,
+                                       CL ? 1ll : (long long)t2.GRS, CL ? (long long)t2.GRS : 1ll);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,28 +532,87 @@ static inline Tiling make_tiling(const lss_plan_layout *L) {
     Tiling t; t.TY = L->tile_cols; t.nty = L->tiles_per_row; t.n_tiles = L->n_tiles; return t;
 }
 
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_num_sms = n;
+    }
+    return g_num_sms;
+}
+
+template <typename K>
+static int opt_in_smem(K kern, size_t smem, bool &configured) {
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024 && !configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
+        configured = true;
+    }
+    return LSS_OK;
+}
+
 template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE, bool VEC4>
 static int launch_fwd_tile(const Dims &d, const Tiling &tl, const int32_t *tile_start, const uint32_t *entries,
                            const SrcArgs &src, float *bev, cudaStream_t s) {
     const size_t smem = (size_t)(CL ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
     auto kern = k_splat_fwd_tile<VW, KC, ATOMIC, CL, DENSE, VEC4>;
-    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) {
-        static bool configured = false;    // per instantiation
-        if (!configured) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-                return LSS_ERR_CUDA;
-            configured = true;
-        }
-    }
+    static bool configured = false;    // per instantiation
+    int st = opt_in_smem(kern, smem, configured);
+    if (st != LSS_OK) return st;
     kern<<<tl.n_tiles, SPLAT_THREADS, smem, s>>>(d, tl, tile_start, entries, src, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
 
+// persistent TMA variant: 2 staging tiles + one zero row per CTA, as many CTAs per SM as shared memory allows
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE>
+static int launch_fwd_tma(const Dims &d, const Tiling &tl, const int32_t *tile_start, const uint32_t *entries,
+                          const SrcArgs &src, float *bev, cudaStream_t s) {
+    const int tile_floats = CL ? tl.TY * d.C : d.C * (tl.TY + 4);
+    const size_t smem = ((size_t)2 * tile_floats + (size_t)(CL ? d.C : tl.TY) + 32) * 4;
+    auto kern = k_splat_fwd_tma<VW, KC, ATOMIC, CL, DENSE>;
+    static bool configured = false;
+    int st = opt_in_smem(kern, smem, configured);
+    if (st != LSS_OK) return st;
+    static int ctas_per_sm = 0;
+    static size_t ctas_smem = 0;
+    if (ctas_per_sm == 0 || ctas_smem != smem) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SPLAT_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        ctas_per_sm = nb; ctas_smem = smem;
+    }
+    const int grid = min(tl.n_tiles, num_sms() * ctas_per_sm);
+    kern<<<grid, SPLAT_THREADS, smem, s>>>(d, tl, tile_start, entries, src, bev, tile_floats);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+template <int VW, int KC, bool ATOMIC, bool CL, bool DENSE>
+static int launch_fwd_scatter(const Dims &d, const Tiling &tl, const int32_t *tile_start, const uint32_t *entries,
+                              const SrcArgs &src, float *bev, cudaStream_t s) {
+    k_splat_fwd_scatter<VW, KC, ATOMIC, CL, DENSE><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, tile_start, entries, src, bev);
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+enum { VAR_TILE = 1, VAR_TILE_TMA = 2, VAR_SCATTER = 3 };
+
 template <int VW, int KC, bool DENSE>
-static int dispatch_fwd_flags(bool atomic, bool cl, bool vec4, const Dims &d, const Tiling &tl, const int32_t *ts,
+static int dispatch_fwd_flags(bool atomic, bool cl, bool vec4, int variant, const Dims &d, const Tiling &tl, const int32_t *ts,
                               const uint32_t *en, const SrcArgs &src, float *bev, cudaStream_t s) {
+    if (variant == VAR_SCATTER) {
+#define SC_CASE(A, L) return launch_fwd_scatter<VW, KC, A, L, DENSE>(d, tl, ts, en, src, bev, s)
+        if (atomic) { if (cl) SC_CASE(true, true); else SC_CASE(true, false); }
+        else        { if (cl) SC_CASE(false, true); else SC_CASE(false, false); }
+#undef SC_CASE
+    }
+    if (variant == VAR_TILE_TMA) {
+#define TMA_CASE(A, L) return launch_fwd_tma<VW, KC, A, L, DENSE>(d, tl, ts, en, src, bev, s)
+        if (atomic) { if (cl) TMA_CASE(true, true); else TMA_CASE(true, false); }
+        else        { if (cl) TMA_CASE(false, true); else TMA_CASE(false, false); }
+#undef TMA_CASE
+    }
 #define FWD_CASE(A, L, V) return launch_fwd_tile<VW, KC, A, L, DENSE, V>(d, tl, ts, en, src, bev, s)
     if (atomic) { if (cl) { if (vec4) FWD_CASE(true, true, true); else FWD_CASE(true, true, false); }
                   else    { if (vec4) FWD_CASE(true, false, true); else FWD_CASE(true, false, false); } }
@@ -460,32 +621,48 @@ static int dispatch_fwd_flags(bool atomic, bool cl, bool vec4, const Dims &d, co
 #undef FWD_CASE
 }
 
-// vector stores of the tile need 16-byte aligned rows in global memory
+// vector / bulk stores of the tile need 16-byte aligned rows in global memory
 static bool tile_vec4_ok(const Dims &d, const Tiling &tl, bool cl, const float *bev) {
     if (!lss_aligned(bev, 16)) return false;
     if (cl) return d.C % 4 == 0;
     return d.ny % 4 == 0 && tl.TY % 4 == 0;
 }
 
+static size_t bev_elems(const Dims &d);
+
 template <bool DENSE>
-static int dispatch_fwd(bool atomic, bool cl, const Dims &d, const Tiling &tl, const int32_t *ts, const uint32_t *en,
-                        const SrcArgs &src, float *bev, cudaStream_t s) {
+static int dispatch_fwd(bool atomic, bool cl, int variant, int precleared, const Dims &d, const Tiling &tl, const int32_t *ts,
+                        const uint32_t *en, const SrcArgs &src, float *bev, cudaStream_t s) {
     const bool vec4 = tile_vec4_ok(d, tl, cl, bev);
+    const size_t tma_smem = ((size_t)2 * (cl ? tl.TY * d.C : d.C * (tl.TY + 4)) + (size_t)(cl ? d.C : tl.TY) + 32) * 4;
+    if (variant <= 0 || variant > VAR_SCATTER) variant = VAR_SCATTER;                    // AUTO
+    if (variant == VAR_TILE_TMA && !(vec4 && tma_smem <= 227 * 1024)) variant = VAR_TILE;  // bulk copies need aligned rows
+    if (variant == VAR_SCATTER && !precleared &&
+        cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
     if (!DENSE && lss_aligned(src.base, 16)) {
-        if (d.C == 32) return dispatch_fwd_flags<1, 1, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
-        if (d.C == 64) return dispatch_fwd_flags<2, 1, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
-        if (d.C == 128) return dispatch_fwd_flags<4, 1, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+        if (d.C == 32) return dispatch_fwd_flags<1, 1, DENSE>(atomic, cl, vec4, variant, d, tl, ts, en, src, bev, s);
+        if (d.C == 64) return dispatch_fwd_flags<2, 1, DENSE>(atomic, cl, vec4, variant, d, tl, ts, en, src, bev, s);
+        if (d.C == 128) return dispatch_fwd_flags<4, 1, DENSE>(atomic, cl, vec4, variant, d, tl, ts, en, src, bev, s);
     }
     const int kc = lss_kc_for(d.C);
-    if (kc <= 2) return dispatch_fwd_flags<0, 2, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
-    if (kc <= 4) return dispatch_fwd_flags<0, 4, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
-    return dispatch_fwd_flags<0, 8, DENSE>(atomic, cl, vec4, d, tl, ts, en, src, bev, s);
+    if (kc <= 2) return dispatch_fwd_flags<0, 2, DENSE>(atomic, cl, vec4, variant, d, tl, ts, en, src, bev, s);
+    if (kc <= 4) return dispatch_fwd_flags<0, 4, DENSE>(atomic, cl, vec4, variant, d, tl, ts, en, src, bev, s);
+    return dispatch_fwd_flags<0, 8, DENSE>(atomic, cl, vec4, variant, d, tl, ts, en, src, bev, s);
 }
 
 static size_t bev_elems(const Dims &d) { return (size_t)d.B * d.nz * d.C * d.nx * d.ny; }
 
+extern "C" int lss_bev_clear(const lss_problem *p, float *bev, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(bev != nullptr, LSS_ERR_BAD_ARG);
+    const Dims d = make_dims(p);
+    return cudaMemsetAsync(bev, 0, bev_elems(d) * 4, (cudaStream_t)stream) == cudaSuccess ? LSS_OK : LSS_ERR_CUDA;
+}
+
 extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace, const float *prob,
-                             const float *ctx_t, float *bev, int mode, int layout, void *stream) {
+                             const float *ctx_t, float *bev, int mode, int layout, int variant, int precleared,
+                             void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
@@ -503,9 +680,9 @@ extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, con
     SrcArgs src{};
     src.base = ctx_t; src.prob = prob;
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
-        return dispatch_fwd<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, d, tl, tile_start, entries, src, bev, s);
+        return dispatch_fwd<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, precleared, d, tl, tile_start, entries, src, bev, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {
-        if (cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
+        if (!precleared && cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
         const int npix = d.B * d.N * d.HW;
         const int grid = (npix + SPLAT_WARPS - 1) / SPLAT_WARPS;
         const int kc = lss_kc_for(d.C);
@@ -522,7 +699,7 @@ extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, con
 
 extern "C" int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                                      const float *x, const int64_t *xs_host, float *bev, int mode, int layout,
-                                     void *stream) {
+                                     int variant, int precleared, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
@@ -541,9 +718,9 @@ extern "C" int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout
     src.base = x; src.prob = nullptr;
     for (int i = 0; i < 6; ++i) src.s[i] = xs_host[i];
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
-        return dispatch_fwd<true>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, d, tl, tile_start, entries, src, bev, s);
+        return dispatch_fwd<true>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, precleared, d, tl, tile_start, entries, src, bev, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {
-        if (cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
+        if (!precleared && cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
         const int grid = (d.n_points + SPLAT_WARPS - 1) / SPLAT_WARPS;
         if (cl) k_vp_fwd_red<true><<<grid, SPLAT_THREADS, 0, s>>>(d, vox, src, bev);
         else k_vp_fwd_red<false><<<grid, SPLAT_THREADS, 0, s>>>(d, vox, src, bev);

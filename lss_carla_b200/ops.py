@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, LssPlanLayout, LssProblem, check, lib)
+from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, VARIANTS, LssPlanLayout, LssProblem, check, lib)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,13 +232,21 @@ def _bev_layout(t):
     return t.contiguous(), LAYOUT_NCHW
 
 
-def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False):
+def bev_clear(prob: Problem, device, channels_last=False):
+    """A zeroed BEV tensor (models.py:240), e.g. issued early on a side stream for the `scatter` variant."""
+    bev = _empty_bev(prob, device, channels_last)
+    check(lib().lss_bev_clear(C.byref(prob.c), _ptr(bev), _stream()), "lss_bev_clear")
+    return bev
+
+
+def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False, variant="auto", out=None):
+    """`out`: optional pre-zeroed BEV tensor (from bev_clear) -> skips the memset of the scatter variant."""
     if mode == "sorted" and not plan.sorted:
         raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
-    bev = _empty_bev(prob, pr.device, channels_last)
+    bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
     check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct), _ptr(bev),
-                              SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW, _stream()),
-          "lss_splat_fwd")
+                              SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW,
+                              VARIANTS[variant], 1 if out is not None else 0, _stream()), "lss_splat_fwd")
     return bev
 
 
@@ -295,7 +303,7 @@ class _VoxelPoolingFn(torch.autograd.Function):
         bev = _empty_bev(prob, x.device, channels_last)
         check(lib().lss_voxel_pooling_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(x), strides,
                                           _ptr(bev), SPLAT_MODES[mode],
-                                          LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW, _stream()),
+                                          LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW, 0, 0, _stream()),
               "lss_voxel_pooling_fwd")
         ctx.prob, ctx.plan, ctx.xshape = prob, plan, tuple(x.shape)
         return bev
