@@ -163,6 +163,7 @@ class BufferSet:
         self.grad_bev = make_bev_grad(cfg, seed).to(dev).contiguous(memory_format=fmt)
         self.plan = ops.Plan(prob, dev, tile_cols)
         self.rows = None if channels_last else torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=dev)
+        self.vsum = torch.empty((self.plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=dev)
         self.out = {}
 
 
@@ -187,7 +188,7 @@ def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAG
     bs.out.update({"pr": pr, "ct": ct})
     if upto < 4:
         return
-    bev = ops.splat_fwd(prob, bs.plan, pr, ct, mode, channels_last)
+    bev = ops.splat_fwd(prob, bs.plan, pr, ct, mode, channels_last, voxel_sums=bs.vsum)
     bs.out["bev"] = bev
     if upto < 5:
         return
@@ -374,7 +375,7 @@ def main():
                                                bs.out["M2"].reshape(-1, 3, 3), bs.trans),
                                   sorted=(args.mode == "sorted"), plan=bs.plan), sets, kiters, stream)
     stages["lift_prepare"] = time_kernel(lambda bs: ops.lift_prepare(prob, bs.dn), sets, kiters, stream)
-    stages["splat_fwd"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last),
+    stages["splat_fwd"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last, voxel_sums=bs.vsum),
                                       sets, kiters, stream)
     stages["splat_bwd"] = time_kernel(lambda bs: ops.splat_bwd(prob, bs.plan, bs.grad_bev, bs.out["pr"], bs.out["ct"], bs.rows),
                                       sets, kiters, stream)

@@ -88,6 +88,23 @@ typedef struct lss_plan_layout {
     size_t off_vox;         /* int32 [n_points]   dense voxel id or -1                               */
     size_t off_entries;     /* uint32[n_points]   bucketed (col << 20 | point-in-sample), per tile   */
     size_t off_tile_start;  /* int32 [n_tiles+1]  exclusive prefix of per-tile kept-point counts     */
+    size_t off_segs;        /* uint32[n_points]   sorted plans: per tile, (col << 20 | first entry   */
+                            /*                    within the bucket) of every non-empty voxel        */
+    size_t off_tile_nseg;   /* int32 [n_tiles]    sorted plans: non-empty voxels per tile            */
+    size_t off_tile_row0;   /* int32 [n_tiles]    sorted plans: first compact row of the tile (its   */
+                            /*                    k-th non-empty voxel owns row tile_row0 + k)       */
+    size_t off_seg_recs;    /* int32 [n_points,4] sorted plans: voxel records {first entry (global), */
+                            /*                    length (or -(depth bin+1) if the voxel is exactly  */
+                            /*                    the fH image rows of one column and depth),        */
+                            /*                    batch index, compact row}, bucketed by the         */
+                            /*                    camera column (b, n, w) of the voxel's first point:*/
+                            /*                    bucket k owns slots [k*D*fH, (k+1)*D*fH)           */
+    size_t off_key_count;   /* int32 [B*N*fW]     sorted plans: records in every bucket              */
+    size_t off_mixed_recs;  /* int32 [n_rows_cap,4] sorted plans: records of the voxels that hold    */
+                            /*                    points of several camera columns (not bucketed)    */
+    size_t off_counters;    /* int32 [64]         [0] = non-empty voxels of the batch (rows in use), */
+                            /*                    [1] = records in mixed_recs                        */
+    int64_t n_rows_cap;     /* min(n_points, B*nx*ny*nz): capacity of the voxel_sums workspace       */
     size_t off_tile_count;  /* int32 [n_tiles]    scratch, all-zero between calls                    */
     size_t off_cursor;      /* int32 [n_tiles]    scratch                                            */
     size_t off_sync;        /* int32 [64]         scratch counters, all-zero between calls           */
@@ -156,24 +173,26 @@ int lss_plan_reference_order(const lss_problem *p, const lss_plan_layout *L, con
 int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
                      void *stream);
 
-/* Kernel variants of the tile-owner forward (same results; SORTED is bit-identical across variants). */
-enum { LSS_VARIANT_AUTO = 0,
-       LSS_VARIANT_TILE = 1,      /* tile staged in shared memory, every BEV element written once, no memset */
-       LSS_VARIANT_TILE_TMA = 2,  /* same, persistent CTAs, rows streamed with cp.async.bulk (TMA)            */
-       LSS_VARIANT_SCATTER = 3    /* BEV zeroed by cudaMemsetAsync, voxel sums stored straight to global      */ };
+/* Kernel variants of the tile-owner forward in SORTED mode (bit-identical results). */
+enum { LSS_VARIANT_AUTO = 0,   /* GROUP when the shape and workspace allow it, else WARP                          */
+       LSS_VARIANT_WARP = 1,   /* ONE tile-owner kernel: a warp per 32-entry chunk, lane = channel; any C         */
+       LSS_VARIANT_GROUP = 2   /* TWO kernels: register-only gather by 8-lane groups (lane = C/8 contiguous        */
+                               /* channels) into compact per-voxel rows, then a streaming tile-owner store;       */
+                               /* C in {32,64,128}, fused level only, needs the `voxel_sums` workspace            */ };
 
-/* Zero a BEV tensor (what `torch.zeros` does at models.py:240).  Callers may issue it early / on another
- * stream and pass precleared=1 to lss_splat_fwd so that it overlaps the plan build. */
+/* Zero a BEV tensor (what `torch.zeros` does at models.py:240).  Only the RED_GLOBAL mode needs a zeroed
+ * grid; callers may issue the clear early / on another stream and pass precleared=1 to lss_splat_fwd. */
 int lss_bev_clear(const lss_problem *p, float *bev, void *stream);
 
 /* voxel_pooling of the lifted features (models.py:59 outer product + :204-246), without materialising
  * them:  bev[b, iz*C+c, ix, iy] = sum_{p in voxel} prob[p] * ctx_t[pixel(p), c].
- * No global atomics in modes SORTED / SMEM_ATOMIC with the TILE variants.  `precleared` != 0 promises that
- * `bev` is already all-zero (only read by the SCATTER variant and RED_GLOBAL mode).
- * bev f32[B, nz*C, nx, ny] in `layout`. */
+ * Modes SORTED / SMEM_ATOMIC write every BEV element exactly once (zeros included): no memset, no global
+ * atomics.  `precleared` != 0 promises that `bev` is already all-zero (only RED_GLOBAL looks at it).
+ * `voxel_sums`: caller workspace f32[min(n_points, B*nx*ny*nz), C] for the GROUP variant (may be null:
+ * the WARP variant is used).  bev f32[B, nz*C, nx, ny] in `layout`. */
 int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
-                  const float *prob, const float *ctx_t, float *bev, int mode, int layout, int variant,
-                  int precleared, void *stream);
+                  const float *prob, const float *ctx_t, float *voxel_sums, float *bev, int mode, int layout,
+                  int variant, int precleared, void *stream);
 
 /* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
  * autograd backward of models.py:58-59,:199-200,:240-244):
@@ -183,6 +202,11 @@ int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
 int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                   const float *grad_bev, int layout, const float *prob, const float *ctx_t,
                   float *grad_rows, float *grad_depthnet, void *stream);
+
+/* Debug hook (profiling aid, not part of the reference surface): when non-null, the GROUP kernels stamp
+ * %globaltimer at their phase boundaries into `store_buf` (device, 8 x u64 per tile) and `gather_buf`
+ * (8 x u64 per camera column); null switches the stamps off. */
+int lss_debug_set_timeline(void *store_buf, void *gather_buf);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* Operator level: LiftSplatShoot.voxel_pooling(geom_feats, x) with a materialised x                */

@@ -31,7 +31,9 @@ class LssProblem(C.Structure):
 class LssPlanLayout(C.Structure):
     _fields_ = [("tile_cols", C.c_int32), ("tiles_per_row", C.c_int32), ("n_tiles", C.c_int32),
                 ("n_points", C.c_int64), ("off_vox", C.c_size_t), ("off_entries", C.c_size_t),
-                ("off_tile_start", C.c_size_t), ("off_tile_count", C.c_size_t), ("off_cursor", C.c_size_t),
+                ("off_tile_start", C.c_size_t), ("off_segs", C.c_size_t), ("off_tile_nseg", C.c_size_t), ("off_tile_row0", C.c_size_t), ("off_seg_recs", C.c_size_t), ("off_key_count", C.c_size_t), ("off_mixed_recs", C.c_size_t), ("off_counters", C.c_size_t),
+                ("n_rows_cap", C.c_int64),
+                ("off_tile_count", C.c_size_t), ("off_cursor", C.c_size_t),
                 ("off_sync", C.c_size_t), ("bytes", C.c_size_t)]
 
 
@@ -43,7 +45,7 @@ class LssLimits(C.Structure):
 LAYOUT_NCHW, LAYOUT_CHANNELS_LAST = 0, 1
 SPLAT_SORTED, SPLAT_SMEM_ATOMIC, SPLAT_RED_GLOBAL = 0, 1, 2
 SPLAT_MODES = {"sorted": SPLAT_SORTED, "atomic": SPLAT_SMEM_ATOMIC, "red": SPLAT_RED_GLOBAL}
-VARIANTS = {"auto": 0, "tile": 1, "tile_tma": 2, "scatter": 3}
+VARIANTS = {"auto": 0, "warp": 1, "group": 2}
 
 _P = C.c_void_p
 _PP = C.POINTER(LssProblem)
@@ -62,8 +64,9 @@ SIGNATURES = {
     "lss_plan_build": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
     "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P]),
+    "lss_debug_set_timeline": (C.c_int, [_P, _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
-    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P]),

@@ -48,7 +48,13 @@ struct Dims {
     int P;         // points per sample N*D*fH*fW
     int n_points;  // B*P
     float dx[3], lo[3];
+    unsigned long long mDHW, mHW;   // ceil(2^40 / DHW), ceil(2^40 / HW): exact division of a 20-bit point index
 };
+
+// x / divisor for x < 2^20, divisor < 2^20, with m = ceil(2^40 / divisor)
+__host__ __device__ __forceinline__ unsigned lss_div20(unsigned x, unsigned long long m) {
+    return (unsigned)(((unsigned long long)x * m) >> 40);
+}
 
 static inline Dims make_dims(const lss_problem *p) {
     Dims d;
@@ -59,6 +65,8 @@ static inline Dims make_dims(const lss_problem *p) {
     d.P = p->N * d.DHW;
     d.n_points = p->B * d.P;
     for (int k = 0; k < 3; ++k) { d.dx[k] = p->dx[k]; d.lo[k] = p->lo[k]; }
+    d.mDHW = ((1ull << 40) + (unsigned)d.DHW - 1) / (unsigned)d.DHW;
+    d.mHW = ((1ull << 40) + (unsigned)d.HW - 1) / (unsigned)d.HW;
     return d;
 }
 

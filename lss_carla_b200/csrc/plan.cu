@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256)
 k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, int32_t *__restrict__ vox,
               long long *__restrict__ idx, uint8_t *__restrict__ kept, long long *__restrict__ rank,
               int32_t *__restrict__ tile_count, int32_t *__restrict__ tile_start, int32_t *__restrict__ cursor,
-              int32_t *__restrict__ sync) {
+              int32_t *__restrict__ sync, int32_t *__restrict__ counters, int32_t *__restrict__ key_count) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < d.n_points;
     int v = -1;
@@ -187,7 +187,8 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
         if (threadIdx.x == 255) s_carry = run;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { tile_start[tl.n_tiles] = s_carry; *sync = 0; }
+    for (int i = threadIdx.x; i < d.B * d.N * d.fW; i += blockDim.x) key_count[i] = 0;
+    if (threadIdx.x == 0) { tile_start[tl.n_tiles] = s_carry; *sync = 0; counters[0] = 0; counters[1] = 0; }
 }
 
 // Scatter kept points into their tile buckets: entries[tile_start[t] + k] = col << 20 | point-in-sample.
@@ -244,25 +245,164 @@ __device__ __forceinline__ void bitonic_sort_block(Keys a, int n) {
     }
 }
 
-#define LSS_SORT_SMEM_CAP 4096   // entries sorted in shared memory (16 KB); larger buckets sort in global memory
-#define LSS_SORT_THREADS 128
+#define LSS_SORT_SMEM_CAP 4096   // entries grouped in shared memory (16 KB); larger buckets sort in global memory
+#define LSS_SORT_THREADS 256
+
+// Exclusive scan of a[0..L) in shared memory by the whole CTA (L <= LSS_MAX_TILE_COLS); a[L] = total.
+__device__ __forceinline__ void block_scan_excl(int *a, int L, int *s_warp) {
+    const int per = (L + LSS_SORT_THREADS - 1) / LSS_SORT_THREADS;
+    const int lo = threadIdx.x * per, hi = min(L, lo + per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(LSS_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    for (int i = lo; i < hi; ++i) { const int x = a[i]; a[i] = run; run += x; }
+    if (threadIdx.x == LSS_SORT_THREADS - 1) a[L] = run;
+    __syncthreads();
+}
+
+// Ordered enumeration by the whole CTA: calls emit(k, i) for every i in [0, L) with flag(i), k ascending
+// in i starting at 0.  COUNT_ONLY skips the calls.  Returns the number of flagged items (uniform).
+template <bool COUNT_ONLY, typename Flag, typename Emit>
+__device__ __forceinline__ int block_enumerate(int L, int *s_warp, Flag flag, Emit emit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;
+    for (int i0 = 0; i0 < L; i0 += LSS_SORT_THREADS) {
+        const int i = i0 + threadIdx.x;
+        const bool f = i < L && flag(i);
+        const unsigned hb = __ballot_sync(LSS_FULL_MASK, f);
+        if (lane == 0) s_warp[warp] = __popc(hb);
+        __syncthreads();
+        int off = base, total = 0;
+#pragma unroll
+        for (int w = 0; w < LSS_SORT_THREADS / 32; ++w) { const int c = s_warp[w]; if (w < warp) off += c; total += c; }
+        if (!COUNT_ONLY && f) emit(off + __popc(hb & ((1u << lane) - 1u)), i);
+        base += total;
+        __syncthreads();
+    }
+    return base;
+}
+
+// One CTA per tile.  Counting sort by column (histogram, scan, unordered placement into shared memory),
+// then every entry finds its rank inside its column segment by counting the smaller keys of that
+// segment (segments are short: the points of ONE voxel) and is written to its final slot.  Keys are
+// unique (col << 20 | point index), so the ranks of a segment are a permutation.
+// Also emits the tables of the tile's ns non-empty voxels: the tile reserves ns consecutive compact rows
+// [row0, row0+ns) with one atomic (the order of tiles in row space is irrelevant), and for its k-th
+// non-empty voxel writes segs[s+k] = col << 20 | first entry within the bucket and appends the record
+// {first entry (global), length, batch index, row0+k} to the bucket of the camera column (b, n, w) of the
+// voxel's first point -- the forward gather walks these buckets, so that the few context rows of one
+// camera column stay in L1 while all their voxels are summed.
+// `kind`: 0 = every point of the voxel is an image row of the first point's (camera column, depth bin);
+// 1 = all points lie in that camera column (several depths); 2 = points of other columns / cameras.
+// Kinds 0 and 1 go to the bucket of the column.  If a kind-0 voxel holds exactly the fH image rows, in order,
+// the record is PURE and its length field carries -(depth bin + 1): the gather needs neither its entries
+// nor any decoding.  Kind 2 goes to the batch-wide queue of mixed voxels (counters[1]).
+__device__ __forceinline__ void emit_voxel_record(const Dims &d, int b, uint32_t first_entry, int kind, int e0,
+                                                  int len, int row, int4 *__restrict__ seg_recs,
+                                                  int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
+                                                  int32_t *__restrict__ counters) {
+    if (kind == 2) {
+        mixed_recs[atomicAdd(counters + 1, 1)] = make_int4(e0, len, b, row);
+        return;
+    }
+    const unsigned pidx = first_entry & LSS_PIDX_MASK;
+    const unsigned cam = lss_div20(pidx, d.mDHW);
+    const unsigned r = pidx - cam * d.DHW;
+    const unsigned dd = lss_div20(r, d.mHW);
+    const unsigned hw = r - dd * d.HW;
+    const unsigned h = hw / (unsigned)d.fW, w = hw - h * d.fW;
+    const int key = (b * d.N + (int)cam) * d.fW + (int)w;
+    const int slot = atomicAdd(key_count + key, 1);
+    const bool pure = kind == 0 && len == d.fH && h == 0;
+    seg_recs[(size_t)key * (d.D * d.fH) + slot] = make_int4(e0, pure ? -(int)(dd + 1) : len, b, row);
+}
 
 __global__ void __launch_bounds__(LSS_SORT_THREADS)
-k_plan_sort(Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries) {
-    __shared__ uint32_t s_keys[LSS_SORT_SMEM_CAP];
+k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries,
+            uint32_t *__restrict__ segs, int32_t *__restrict__ tile_nseg, int32_t *__restrict__ tile_row0,
+            int4 *__restrict__ seg_recs, int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
+            int32_t *__restrict__ counters) {
+    extern __shared__ int s_int[];                 // start[TY+1], cursor[TY], mixed[TY]
+    __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
+    __shared__ int s_warp[LSS_SORT_THREADS / 32];
+    __shared__ int s_row0;
     const int t = blockIdx.x;
     const int s = tile_start[t], n = tile_start[t + 1] - s;
-    if (n <= 1) return;
+    const int b = t / (tl.nty * d.nx * d.nz);
     uint32_t *g = entries + s;
-    if (n <= LSS_SORT_SMEM_CAP) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = g[i];
+    if (n == 0) { if (threadIdx.x == 0) { tile_nseg[t] = 0; tile_row0[t] = 0; } return; }
+    auto reserve = [&](int ns) {                   // uniform call; returns the tile's first compact row
+        if (threadIdx.x == 0) { s_row0 = atomicAdd(counters, ns); tile_nseg[t] = ns; tile_row0[t] = s_row0; }
         __syncthreads();
-        bitonic_sort_block(s_keys, n);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = s_keys[i];
-    } else {
+        return s_row0;
+    };
+    if (n > LSS_SORT_SMEM_CAP) {                   // rare: correctness fallback, sorts in global memory (L2)
+        bitonic_sort_block((volatile uint32_t *)g, n);
         __syncthreads();
-        bitonic_sort_block((volatile uint32_t *)g, n);   // rare: correctness fallback, L2-resident
+        auto head = [&](int i) { return i == 0 || (g[i] >> LSS_PIDX_BITS) != (g[i - 1] >> LSS_PIDX_BITS); };
+        const int ns = block_enumerate<true>(n, s_warp, head, [](int, int) {});
+        const int row0 = reserve(ns);
+        block_enumerate<false>(n, s_warp, head, [&](int k, int i) {
+            const uint32_t col = g[i] >> LSS_PIDX_BITS;
+            int j = i + 1;                          // segment end: next head (long runs only occur here)
+            while (j < n && (g[j] >> LSS_PIDX_BITS) == col) ++j;
+            segs[s + k] = (col << LSS_PIDX_BITS) | (uint32_t)i;
+            emit_voxel_record(d, b, g[i], 2, s + i, j - i, row0 + k, seg_recs, key_count, mixed_recs, counters);
+        });
+        return;
     }
+    const int TY = tl.TY;
+    int *start = s_int, *cursor = s_int + TY + 1, *mixed = cursor + TY;
+    for (int i = threadIdx.x; i <= TY; i += LSS_SORT_THREADS) start[i] = 0;
+    for (int i = threadIdx.x; i < TY; i += LSS_SORT_THREADS) { cursor[i] = 0; mixed[i] = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) atomicAdd(start + (g[i] >> LSS_PIDX_BITS), 1);
+    __syncthreads();
+    block_scan_excl(start, TY, s_warp);
+    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+        const uint32_t e = g[i];
+        const int col = (int)(e >> LSS_PIDX_BITS);
+        s_grp[start[col] + atomicAdd(cursor + col, 1)] = e;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+        const uint32_t e = s_grp[i];
+        const int col = (int)(e >> LSS_PIDX_BITS);
+        const int a = start[col], bb = start[col + 1];
+        int rank = 0;
+        for (int j = a; j < bb; ++j) rank += s_grp[j] < e;
+        g[a + rank] = e;
+        if (rank == 0) cursor[col] = (int)e;       // the voxel's first point (cursor is free again)
+    }
+    __syncthreads();
+    {   // classify every voxel against its first point: same (camera column, depth) / same column / foreign points
+        const unsigned span = (unsigned)d.fH * d.fW;
+        for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+            const uint32_t e = s_grp[i];
+            const int col = (int)(e >> LSS_PIDX_BITS);
+            const unsigned p = e & LSS_PIDX_MASK, p0 = (uint32_t)cursor[col] & LSS_PIDX_MASK;
+            const unsigned delta = p - p0;
+            if (delta < span && delta % (unsigned)d.fW == 0u) continue;                      // kind 0
+            const bool same_col = lss_div20(p, d.mDHW) == lss_div20(p0, d.mDHW) && delta % (unsigned)d.fW == 0u;
+            atomicMax(mixed + col, same_col ? 1 : 2);
+        }
+    }
+    __syncthreads();
+    auto hit = [&](int c) { return start[c + 1] > start[c]; };
+    const int ns = block_enumerate<true>(TY, s_warp, hit, [](int, int) {});
+    const int row0 = reserve(ns);
+    block_enumerate<false>(TY, s_warp, hit, [&](int k, int c) {
+        segs[s + k] = ((uint32_t)c << LSS_PIDX_BITS) | (uint32_t)start[c];
+        emit_voxel_record(d, b, (uint32_t)cursor[c], mixed[c], s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
+                          mixed_recs, counters);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,6 +478,15 @@ extern "C" int lss_plan_layout_init(const lss_problem *p, int tile_cols, lss_pla
     out->off_vox = off;        off += up((size_t)d.n_points * 4);
     out->off_entries = off;    off += up((size_t)d.n_points * 4);
     out->off_tile_start = off; off += up(((size_t)nt + 1) * 4);
+    out->off_segs = off;       off += up((size_t)d.n_points * 4);
+    out->off_tile_nseg = off;  off += up((size_t)nt * 4);
+    out->off_tile_row0 = off;  off += up((size_t)nt * 4);
+    const int64_t nvox = (int64_t)p->B * p->nx * p->ny * p->nz;
+    out->n_rows_cap = nvox < (int64_t)d.n_points ? nvox : (int64_t)d.n_points;
+    out->off_seg_recs = off;   off += up((size_t)d.n_points * 16);
+    out->off_key_count = off;  off += up((size_t)p->B * p->N * p->fW * 4);
+    out->off_mixed_recs = off; off += up((size_t)out->n_rows_cap * 16);
+    out->off_counters = off;   off += up(64 * 4);
     out->off_tile_count = off; off += up((size_t)nt * 4);
     out->off_cursor = off;     off += up((size_t)nt * 4);
     out->off_sync = off;       off += up(64 * 4);
@@ -388,10 +537,10 @@ extern "C" int lss_voxel_index(const lss_problem *p, const float *geom, const fl
     cudaStream_t s = (cudaStream_t)stream;
     if (from_geom)
         k_voxel_index<true, false><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, (long long *)idx, kept, (long long *)rank,
-                                                        nullptr, nullptr, nullptr, nullptr);
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
         k_voxel_index<false, false><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, (long long *)idx, kept, (long long *)rank,
-                                                         nullptr, nullptr, nullptr, nullptr);
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -414,20 +563,29 @@ extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, vo
     int32_t *tile_count = (int32_t *)(w + L->off_tile_count);
     int32_t *cursor = (int32_t *)(w + L->off_cursor);
     int32_t *sync = (int32_t *)(w + L->off_sync);
+    int32_t *counters = (int32_t *)(w + L->off_counters);
+    int32_t *key_count = (int32_t *)(w + L->off_key_count);
     CalibPtrs c{frustum, post_trans, M1, M2, trans};
     const int grid = (d.n_points + 255) / 256;
     cudaStream_t s = (cudaStream_t)stream;
     if (from_geom)
         k_voxel_index<true, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
-                                                       tile_start, cursor, sync);
+                                                       tile_start, cursor, sync, counters, key_count);
     else
         k_voxel_index<false, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
-                                                        tile_start, cursor, sync);
+                                                        tile_start, cursor, sync, counters, key_count);
     LSS_CHECK_LAUNCH();
     k_plan_scatter<<<grid, 256, 0, s>>>(d, tl, vox, tile_start, cursor, entries);
     LSS_CHECK_LAUNCH();
     if (sorted) {
-        k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, 0, s>>>(tl, tile_start, entries);
+        const size_t sort_smem = (size_t)(3 * tl.TY + 1) * sizeof(int);
+        if (sort_smem > 24 * 1024 &&
+            cudaFuncSetAttribute(k_plan_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess)
+            return LSS_ERR_CUDA;
+        k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, (size_t)(3 * tl.TY + 1) * sizeof(int), s>>>(
+            d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
+            (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
+            (int4 *)(w + L->off_mixed_recs), counters);
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;

@@ -113,6 +113,20 @@ class Plan:
     def tile_start(self):
         return self._view(self.layout.off_tile_start, self.layout.n_tiles + 1, torch.int32)
 
+    @property
+    def tile_nseg(self):
+        return self._view(self.layout.off_tile_nseg, self.layout.n_tiles, torch.int32)
+
+    @property
+    def tile_row0(self):
+        """First compact row of every tile (sorted plans)."""
+        return self._view(self.layout.off_tile_row0, self.layout.n_tiles, torch.int32)
+
+    @property
+    def n_rows(self):
+        """Device scalar: number of non-empty voxels of the batch (sorted plans)."""
+        return self._view(self.layout.off_counters, 1, torch.int32)
+
     def reset(self):
         check(lib().lss_plan_reset(C.byref(self.layout), _ptr(self.ws), _stream()), "lss_plan_reset")
 
@@ -239,12 +253,17 @@ def bev_clear(prob: Problem, device, channels_last=False):
     return bev
 
 
-def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False, variant="auto", out=None):
-    """`out`: optional pre-zeroed BEV tensor (from bev_clear) -> skips the memset of the scatter variant."""
+def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False, variant="auto", out=None,
+              voxel_sums=None):
+    """`out`: optional pre-zeroed BEV tensor (from bev_clear) for mode 'red'.  `voxel_sums`: optional
+    workspace f32[min(n_points, n_voxels), C] of the two-kernel GROUP variant (allocated when omitted)."""
     if mode == "sorted" and not plan.sorted:
         raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
     bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
-    check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct), _ptr(bev),
+    if voxel_sums is None and mode == "sorted" and variant != "warp" and prob.C in (32, 64, 128):
+        voxel_sums = torch.empty((plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=pr.device)
+    check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct),
+                              _ptr(voxel_sums), _ptr(bev),
                               SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW,
                               VARIANTS[variant], 1 if out is not None else 0, _stream()), "lss_splat_fwd")
     return bev

@@ -17,7 +17,7 @@ for case in sys.argv[1:] or ["tiny_train_s0"]:
         pr, ct = ops.lift_prepare(prob, torch.from_numpy(g["depthnet_out"]).to(dev))
         vox = plan.vox.cpu().numpy().astype(np.int64)
         want = O.splat_from_prob(pr.cpu().numpy(), ct.cpu().numpy(), vox, cfg.B, cfg.C, g["nx"])
-        for variant in ("tile", "tile_tma", "scatter"):
+        for variant in ("warp", "group"):
             for cl in (False, True):
                 bev = ops.splat_fwd(prob, plan, pr, ct, "sorted", cl, variant=variant).cpu().numpy()
                 bad = bev != want

@@ -96,6 +96,14 @@ def test_plan_and_reference_sort_order(case, tile_cols):
     # scratch counters are left zeroed for the next build
     L = plan.layout
     assert not plan.ws[L.off_tile_count:L.off_cursor].any() and not plan.ws[L.off_sync:].any()
+    # segment table: one segment per distinct kept voxel, prefix consistent
+    n_hit = np.unique(vox[vox >= 0]).size
+    r0, tn = plan.tile_row0.cpu().numpy().astype(np.int64), plan.tile_nseg.cpu().numpy().astype(np.int64)
+    assert int(plan.n_rows.item()) == n_hit == tn.sum()
+    used = np.zeros(n_hit + 1, np.int64)                     # the tiles' row ranges tile [0, n_hit) exactly
+    np.add.at(used, r0[tn > 0], 1)
+    np.add.at(used, (r0 + tn)[tn > 0], -1)
+    assert np.all(np.cumsum(used)[:-1] == 1)
     # reference order: flat index of x[kept][sorts]
     order = ops.reference_order(plan).cpu().numpy()
     rs = O.ranks_and_sort(idx, kept, cfg.B, g["nx"])
@@ -188,6 +196,10 @@ def test_splat_sorted_bit_exact_vs_sequential_oracle(case, tile_cols):
     bev_cl = ops.splat_fwd(prob, plan, pr, ct, "sorted", True)
     assert bev_cl.is_contiguous(memory_format=torch.channels_last) and tuple(bev_cl.shape) == prob.bev_shape
     assert np.array_equal(bev_cl.cpu().numpy(), want)
+    # both kernels of the deterministic mode (8-lane groups / warp per chunk) give the same bits
+    for variant in ("warp", "group"):
+        for cl in (False, True):
+            assert np.array_equal(ops.splat_fwd(prob, plan, pr, ct, "sorted", cl, variant=variant).cpu().numpy(), want)
     # run-to-run determinism
     assert torch.equal(bev, ops.splat_fwd(prob, plan, pr, ct, "sorted", False))
 
@@ -242,7 +254,7 @@ def test_all_points_dropped_gives_zero_bev():
     assert not gr.any()
 
 
-@pytest.mark.parametrize("C,ny,nz", [(48, 37, 1), (8, 200, 3), (96, 16, 2), (130, 9, 1)])
+@pytest.mark.parametrize("C,ny,nz", [(48, 37, 1), (8, 200, 3), (96, 16, 2), (130, 9, 1), (128, 24, 2), (64, 13, 1)])
 def test_odd_shapes(C, ny, nz):
     """Channel counts that are not multiples of 32, grids that are not multiples of the tile width."""
     rng = np.random.RandomState(C + ny)
