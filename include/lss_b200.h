@@ -102,6 +102,8 @@ typedef struct lss_plan_layout {
     size_t off_key_count;   /* int32 [B*N*fW]     sorted plans: records in every bucket              */
     size_t off_mixed_recs;  /* int32 [n_rows_cap,4] sorted plans: records of the voxels that hold    */
                             /*                    points of several camera columns (not bucketed)    */
+    size_t off_prow;        /* int32 [n_points]   sorted plans: compact row of the point's voxel, -1 */
+                            /*                    for dropped points (backward gather)               */
     size_t off_counters;    /* int32 [64]         [0] = non-empty voxels of the batch (rows in use), */
                             /*                    [1] = records in mixed_recs                        */
     int64_t n_rows_cap;     /* min(n_points, B*nx*ny*nz): capacity of the voxel_sums workspace       */
@@ -197,11 +199,13 @@ int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
 /* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
  * autograd backward of models.py:58-59,:199-200,:240-244):
  *   grad_depthnet f32[B*N, D+C, fH, fW]  (first D channels: logits through the softmax; last C: context)
- * `grad_rows` is a caller workspace f32[B*nz*nx*ny, C] used only for LSS_LAYOUT_NCHW (rows of hit
- * voxels are transposed into it); may be null for channels_last. */
+ * `grad_rows` is a caller workspace f32[B*nz*nx*ny, C]: the gradient rows of the non-empty voxels are
+ * gathered into it, channel-contiguous (compact row order for sorted plans, voxel order otherwise); it may
+ * be null only for channels_last gradients.  `plan_sorted` != 0 promises that the plan was built with
+ * sorted=1, which enables the compact-row kernels (C in {32,64,128}). */
 int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                   const float *grad_bev, int layout, const float *prob, const float *ctx_t,
-                  float *grad_rows, float *grad_depthnet, void *stream);
+                  float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream);
 
 /* Debug hook (profiling aid, not part of the reference surface): when non-null, the GROUP kernels stamp
  * %globaltimer at their phase boundaries into `store_buf` (device, 8 x u64 per tile) and `gather_buf`

@@ -31,7 +31,7 @@ class LssProblem(C.Structure):
 class LssPlanLayout(C.Structure):
     _fields_ = [("tile_cols", C.c_int32), ("tiles_per_row", C.c_int32), ("n_tiles", C.c_int32),
                 ("n_points", C.c_int64), ("off_vox", C.c_size_t), ("off_entries", C.c_size_t),
-                ("off_tile_start", C.c_size_t), ("off_segs", C.c_size_t), ("off_tile_nseg", C.c_size_t), ("off_tile_row0", C.c_size_t), ("off_seg_recs", C.c_size_t), ("off_key_count", C.c_size_t), ("off_mixed_recs", C.c_size_t), ("off_counters", C.c_size_t),
+                ("off_tile_start", C.c_size_t), ("off_segs", C.c_size_t), ("off_tile_nseg", C.c_size_t), ("off_tile_row0", C.c_size_t), ("off_seg_recs", C.c_size_t), ("off_key_count", C.c_size_t), ("off_mixed_recs", C.c_size_t), ("off_prow", C.c_size_t), ("off_counters", C.c_size_t),
                 ("n_rows_cap", C.c_int64),
                 ("off_tile_count", C.c_size_t), ("off_cursor", C.c_size_t),
                 ("off_sync", C.c_size_t), ("bytes", C.c_size_t)]
@@ -67,7 +67,7 @@ SIGNATURES = {
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P]),
     "lss_quickcumsum_scratch_elems": (C.c_size_t, [C.c_int64]),

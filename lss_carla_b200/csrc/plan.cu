@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256)
 k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, int32_t *__restrict__ vox,
               long long *__restrict__ idx, uint8_t *__restrict__ kept, long long *__restrict__ rank,
               int32_t *__restrict__ tile_count, int32_t *__restrict__ tile_start, int32_t *__restrict__ cursor,
-              int32_t *__restrict__ sync, int32_t *__restrict__ counters, int32_t *__restrict__ key_count) {
+              int32_t *__restrict__ sync, int32_t *__restrict__ counters, int32_t *__restrict__ key_count,
+              int32_t *__restrict__ prow) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < d.n_points;
     int v = -1;
@@ -128,6 +129,7 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
         long long ii[3];
         v = voxel_of_point(d, b, g, ii);
         if (vox) vox[p] = v;
+        if (COUNT && v < 0) prow[p] = -1;         // kept points get their compact row from k_plan_sort
         if (idx) { idx[(size_t)p * 3 + 0] = ii[0]; idx[(size_t)p * 3 + 1] = ii[1]; idx[(size_t)p * 3 + 2] = ii[2]; }
         if (kept) kept[p] = v >= 0;
         if (rank)   // models.py:226-229, int64
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(LSS_SORT_THREADS)
 k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries,
             uint32_t *__restrict__ segs, int32_t *__restrict__ tile_nseg, int32_t *__restrict__ tile_row0,
             int4 *__restrict__ seg_recs, int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
-            int32_t *__restrict__ counters) {
+            int32_t *__restrict__ counters, int32_t *__restrict__ prow) {
     extern __shared__ int s_int[];                 // start[TY+1], cursor[TY], mixed[TY]
     __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
     __shared__ int s_warp[LSS_SORT_THREADS / 32];
@@ -355,6 +357,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
             while (j < n && (g[j] >> LSS_PIDX_BITS) == col) ++j;
             segs[s + k] = (col << LSS_PIDX_BITS) | (uint32_t)i;
             emit_voxel_record(d, b, g[i], 2, s + i, j - i, row0 + k, seg_recs, key_count, mixed_recs, counters);
+            for (int q = i; q < j; ++q) prow[(size_t)b * d.P + (g[q] & LSS_PIDX_MASK)] = row0 + k;
         });
         return;
     }
@@ -399,10 +402,16 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     const int ns = block_enumerate<true>(TY, s_warp, hit, [](int, int) {});
     const int row0 = reserve(ns);
     block_enumerate<false>(TY, s_warp, hit, [&](int k, int c) {
+        mixed[c] |= k << 2;                       // the voxel's ordinal in the tile, for the per-point rows below
         segs[s + k] = ((uint32_t)c << LSS_PIDX_BITS) | (uint32_t)start[c];
-        emit_voxel_record(d, b, (uint32_t)cursor[c], mixed[c], s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
+        emit_voxel_record(d, b, (uint32_t)cursor[c], mixed[c] & 3, s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
                           mixed_recs, counters);
     });
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+        const uint32_t e = s_grp[i];
+        prow[(size_t)b * d.P + (e & LSS_PIDX_MASK)] = row0 + (mixed[e >> LSS_PIDX_BITS] >> 2);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -486,6 +495,7 @@ extern "C" int lss_plan_layout_init(const lss_problem *p, int tile_cols, lss_pla
     out->off_seg_recs = off;   off += up((size_t)d.n_points * 16);
     out->off_key_count = off;  off += up((size_t)p->B * p->N * p->fW * 4);
     out->off_mixed_recs = off; off += up((size_t)out->n_rows_cap * 16);
+    out->off_prow = off;       off += up((size_t)d.n_points * 4);
     out->off_counters = off;   off += up(64 * 4);
     out->off_tile_count = off; off += up((size_t)nt * 4);
     out->off_cursor = off;     off += up((size_t)nt * 4);
@@ -537,10 +547,10 @@ extern "C" int lss_voxel_index(const lss_problem *p, const float *geom, const fl
     cudaStream_t s = (cudaStream_t)stream;
     if (from_geom)
         k_voxel_index<true, false><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, (long long *)idx, kept, (long long *)rank,
-                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
         k_voxel_index<false, false><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, (long long *)idx, kept, (long long *)rank,
-                                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -570,10 +580,10 @@ extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, vo
     cudaStream_t s = (cudaStream_t)stream;
     if (from_geom)
         k_voxel_index<true, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
-                                                       tile_start, cursor, sync, counters, key_count);
+                                                       tile_start, cursor, sync, counters, key_count, (int32_t *)(w + L->off_prow));
     else
         k_voxel_index<false, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
-                                                        tile_start, cursor, sync, counters, key_count);
+                                                        tile_start, cursor, sync, counters, key_count, (int32_t *)(w + L->off_prow));
     LSS_CHECK_LAUNCH();
     k_plan_scatter<<<grid, 256, 0, s>>>(d, tl, vox, tile_start, cursor, entries);
     LSS_CHECK_LAUNCH();
@@ -585,7 +595,7 @@ extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, vo
         k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, (size_t)(3 * tl.TY + 1) * sizeof(int), s>>>(
             d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
             (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
-            (int4 *)(w + L->off_mixed_recs), counters);
+            (int4 *)(w + L->off_mixed_recs), counters, (int32_t *)(w + L->off_prow));
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;

@@ -18,6 +18,8 @@
 // Backward is a pure gather (tools.py:212-219): for NCHW gradients a tile-owner kernel first gathers the
 // channels of every hit voxel into a channel-contiguous row; a pixel-owner kernel then reads one row per
 // frustum point and fuses the outer-product and softmax backward.
+#include <cstdlib>
+
 #include "common.cuh"
 
 #define SPLAT_THREADS 256
@@ -292,7 +294,7 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
     const bool column = (int)blockIdx.x < n_keys;        // else: a CTA of the mixed-voxel queue
     const int key = column ? blockIdx.x : 0;             // camera column (b, n, w0)
-    if (column) lss_stamp<true>(key, 0);
+    lss_stamp<true>(blockIdx.x, 0);
     const int n_rec = column ? __ldg(key_count + key) : __ldg(counters + 1);
     const int w0 = column ? key % d.fW : -1, bn = key / d.fW;
     const int n0 = column ? bn % d.N : -1;
@@ -323,7 +325,8 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
         rec = __ldg(recs + r);
         if (rec.y > 0 && gl < rec.y) e0 = __ldg(entries + rec.x + gl);
     }
-    if (column) { __syncthreads(); lss_stamp<true>(key, 1); }
+    if (column) __syncthreads();
+    lss_stamp<true>(blockIdx.x, 1);
     while (__any_sync(LSS_FULL_MASK, r < n_rec)) {
         const int nr = r + stride;
         const float *prob_b = prob + (size_t)rec.z * d.P;
@@ -402,7 +405,8 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
         rec = nrec;
         if (rec.y > 0 && gl < rec.y) e0 = __ldg(entries + rec.x + gl);    // generic voxel: its first 8 entries
     }
-    if (column && lane == 0 && g_lss_timeline_gather != nullptr) {
+    if (lane == 0 && g_lss_timeline_gather != nullptr) {
+        const int key = blockIdx.x;
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         atomicMax(g_lss_timeline_gather + (size_t)key * 8 + 3, t);
@@ -421,30 +425,33 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
 // registers, non-empty slots looked up through a column map -- was measured slower: 28 us vs 19 us.)
 template <bool CL, bool VEC4>
 __global__ void __launch_bounds__(SPLAT_THREADS)
-k_fwd_store(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
+k_fwd_store(Dims d, Tiling tl, int CH, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
             const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
             float *__restrict__ bev) {
     extern __shared__ __align__(16) float smem[];
     const int tile = blockIdx.x;
-    lss_stamp(tile, 0);
+    const int c0 = blockIdx.y * CH;                       // this CTA owns channels [c0, c0 + CH) of the tile
+    if (blockIdx.y == 0) lss_stamp(tile, 0);
     const TileCoord tc = tile_coord(d, tl, tile);
-    const Tile2D t2 = tile_2d<CL>(d, tl, tc);
+    Tile2D t2 = tile_2d<CL>(d, tl, tc);
+    if (CL) { t2.RL = CH; t2.SRS = CH; t2.gbase += c0; }
+    else { t2.NR = CH; t2.gbase += (size_t)c0 * t2.GRS; }
     const int nseg = __ldg(tile_nseg + tile);
-    if (nseg == 0) { store_tile<VEC4>(t2, nullptr, bev); lss_stamp(tile, 3); return; }
+    if (nseg == 0) { store_tile<VEC4>(t2, nullptr, bev); if (blockIdx.y == 0) lss_stamp(tile, 3); return; }
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
-    const int C = d.C, c4 = C >> 2;                       // C % 4 == 0 on this path
-    const int per_pass = SPLAT_THREADS / c4;              // rows per pass (C=64: 16)
+    const int C = d.C, c4 = CH >> 2;                      // C % 4 == 0 and CH % 4 == 0 on this path
+    const int per_pass = SPLAT_THREADS / c4;              // rows per pass
     const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
-    lss_stamp(tile, 1);
+    if (blockIdx.y == 0) lss_stamp(tile, 1);
     // request the first rows before zero-filling the staging tile
     int col0 = 0;
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool has0 = r0 < per_pass && r0 < nseg;
     if (has0) {
         col0 = (int)(__ldg(segs + s + r0) >> LSS_PIDX_BITS);
-        v0 = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + r0) * C) + q);
+        v0 = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + r0) * C + c0) + q);
     }
-    zero_smem(smem, CL ? tl.TY * C : C * t2.SRS);
+    zero_smem(smem, CL ? tl.TY * CH : CH * t2.SRS);
     __syncthreads();
     if (r0 < per_pass) {
         for (int r = r0; r < nseg; r += per_pass) {
@@ -452,10 +459,10 @@ k_fwd_store(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const int
             if (r == r0) { col = col0; v = v0; }
             else {
                 col = (int)(__ldg(segs + s + r) >> LSS_PIDX_BITS);
-                v = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + r) * C) + q);
+                v = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + r) * C + c0) + q);
             }
             if (CL) {
-                *reinterpret_cast<float4 *>(smem + col * C + 4 * q) = v;
+                *reinterpret_cast<float4 *>(smem + col * CH + 4 * q) = v;
             } else {
                 float *dst = smem + (4 * q) * t2.SRS + col;
                 dst[0] = v.x; dst[t2.SRS] = v.y; dst[2 * t2.SRS] = v.z; dst[3 * t2.SRS] = v.w;
@@ -463,10 +470,10 @@ k_fwd_store(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const int
         }
     }
     __syncthreads();
-    lss_stamp(tile, 2);
+    if (blockIdx.y == 0) lss_stamp(tile, 2);
     store_tile<VEC4>(t2, smem, bev);
-    lss_stamp(tile, 3);
-    if (threadIdx.x == 0 && g_lss_timeline != nullptr) g_lss_timeline[(size_t)tile * 8 + 7] = nseg;
+    if (blockIdx.y == 0) lss_stamp(tile, 3);
+    if (threadIdx.x == 0 && blockIdx.y == 0 && g_lss_timeline != nullptr) g_lss_timeline[(size_t)tile * 8 + 7] = nseg;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -655,6 +662,161 @@ k_bwd_gather(Dims d, const int32_t *__restrict__ vox, const float *__restrict__ 
     }
 }
 
+// ---- backward through the plan's compact rows (sorted plans, C in {32, 64, 128})
+//
+// (1) k_bwd_rows_compact: gradient rows of the non-empty voxels, channel-contiguous, in the plan's compact
+// row order (the mirror image of k_fwd_store).  NCHW: a warp owns 8 channels, a lane one voxel of the
+// tile: 8 independent 4-byte loads per lane (neighbouring columns share 32-byte sectors), one full
+// 32-byte sector written per lane.  channels_last: plain 16-byte copies.
+template <bool CL>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_bwd_rows_compact(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
+                   const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs,
+                   const float *__restrict__ grad_bev, float *__restrict__ grows) {
+    const int tile = blockIdx.x;
+    const int nseg = __ldg(tile_nseg + tile);
+    if (nseg == 0) return;
+    const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
+    const TileCoord tc = tile_coord(d, tl, tile);
+    const int C = d.C;
+    if (CL) {
+        const int c4 = C >> 2, per_pass = SPLAT_THREADS / c4;
+        const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
+        const size_t GRS = (size_t)d.nz * C;
+        const float *gsrc = grad_bev + ((size_t)(tc.b * d.nx + tc.ix) * d.ny + tc.y0) * GRS + (size_t)tc.iz * C;
+        if (r0 < per_pass)
+            for (int k = r0; k < nseg; k += per_pass) {
+                const int col = (int)(__ldg(segs + s + k) >> LSS_PIDX_BITS);
+                reinterpret_cast<float4 *>(grows + (size_t)(row0 + k) * C)[q] =
+                    __ldg(reinterpret_cast<const float4 *>(gsrc + (size_t)col * GRS) + q);
+            }
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t plane = (size_t)d.nx * d.ny;
+    const float *gsrc = grad_bev + ((size_t)(tc.b * d.nz + tc.iz) * C) * plane + (size_t)tc.ix * d.ny + tc.y0;
+    for (int k0 = 0; k0 < nseg; k0 += 32) {
+        const int k = k0 + lane;
+        const bool live = k < nseg;
+        const int col = live ? (int)(__ldg(segs + s + k) >> LSS_PIDX_BITS) : 0;
+        for (int oct = warp; oct < (C >> 3); oct += SPLAT_WARPS) {
+            const float *src = gsrc + (size_t)(oct * 8) * plane + col;
+            float v[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) v[a] = live ? __ldg(src + (size_t)a * plane) : 0.f;
+            if (live) {
+                float4 *dst = reinterpret_cast<float4 *>(grows + (size_t)(row0 + k) * C + oct * 8);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+}
+
+// (2) k_bwd_gather_px: pixel owner, like k_bwd_gather, but a GROUP of 8 lanes owns a camera pixel (lane gl
+// keeps channel quads gl, gl+8, ... of the context and of its gradient), and one CTA owns all fH image
+// rows of WC neighbouring columns: the fH pixels of a column hit the same voxel at every depth, so their
+// gradient rows are L1 hits for all but the first.  The compact row index and the softmax weight of all
+// the CTA's points are staged in shared memory first (one round of coalesced loads); the depth loop then
+// reads shared memory, keeps LF gradient rows in flight and needs no control flow (dropped points read
+// row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
+template <int CPL>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *__restrict__ prob,
+                const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int LF = CPL <= 8 ? 4 : 2;
+    const int bn = blockIdx.y, w0 = blockIdx.x * WC;
+    const int D = d.D, C = d.C, fH = d.fH, DC = D + C;
+    const int npx = fH * WC;                              // pixels of the CTA (<= 32), group g <-> pixel (h, wl)
+    float *s_p = smem;                                    // [32][D] softmax weight
+    int *s_row = reinterpret_cast<int *>(smem + 32 * D);  // [32][D] compact row or -1
+    float *s_gp = smem + 64 * D;                          // [32][D] <grad row, ctx>
+    float *s_out = smem + 96 * D;                         // [D + C][npx] staged outputs
+    for (int i = threadIdx.x; i < npx * D; i += SPLAT_THREADS) {
+        const int dd = i / npx, px = i - dd * npx;        // px = h * WC + wl: consecutive threads walk a pixel row
+        const int h = px / WC, wl = px - h * WC;
+        const bool ok = w0 + wl < d.fW;
+        const size_t p = ((size_t)(bn * D + dd) * fH + h) * d.fW + w0 + wl;
+        s_p[px * D + dd] = ok ? __ldg(prob + p) : 0.f;
+        s_row[px * D + dd] = ok ? __ldg(prow + p) : -1;
+    }
+    const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
+    const int h = g / WC, wl = g - h * WC;
+    const bool active = g < npx && w0 + wl < d.fW;
+    float ctx[CPL], dctx[CPL];
+    {
+        const float4 *cp = reinterpret_cast<const float4 *>(ctx_t + ((size_t)bn * d.HW + (active ? h * d.fW + w0 + wl : 0)) * C) + gl;
+#pragma unroll
+        for (int q = 0; q < CPL / 4; ++q) {
+            const float4 v = __ldg(cp + 8 * q);
+            ctx[4 * q] = v.x; ctx[4 * q + 1] = v.y; ctx[4 * q + 2] = v.z; ctx[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int a = 0; a < CPL; ++a) dctx[a] = 0.f;
+    }
+    __syncthreads();
+    const float *my_p = s_p + (g < npx ? g : 0) * D;
+    const int *my_row = s_row + (g < npx ? g : 0) * D;
+    const float4 *rows4 = reinterpret_cast<const float4 *>(grows) + gl;
+    const int c4 = C >> 2;
+    for (int d0 = 0; d0 < D; d0 += LF) {                  // warp-uniform: every group walks all D depths
+        float x[LF][CPL];
+        float pj[LF];
+#pragma unroll
+        for (int u = 0; u < LF; ++u) {
+            const int dd = min(d0 + u, D - 1);
+            const int rj = active ? my_row[dd] : -1;
+            pj[u] = (rj >= 0 && d0 + u < D) ? my_p[dd] : 0.f;     // dropped point / padding: weight 0, row 0
+            const float4 *rp = rows4 + (size_t)max(rj, 0) * c4;
+#pragma unroll
+            for (int q = 0; q < CPL / 4; ++q) {
+                const float4 v = __ldg(rp + 8 * q);
+                x[u][4 * q] = v.x; x[u][4 * q + 1] = v.y; x[u][4 * q + 2] = v.z; x[u][4 * q + 3] = v.w;
+            }
+            if (rj < 0 || d0 + u >= D) {
+#pragma unroll
+                for (int a = 0; a < CPL; ++a) x[u][a] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LF; ++u) {
+            float dot = 0.f;
+#pragma unroll
+            for (int a = 0; a < CPL; ++a) { dot = fmaf(x[u][a], ctx[a], dot); dctx[a] = fmaf(pj[u], x[u][a], dctx[a]); }
+            dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 1);
+            dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 2);
+            dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 4);
+            if (gl == 0 && g < npx && d0 + u < D) s_gp[g * D + d0 + u] = dot;
+        }
+    }
+    __syncwarp();
+    // softmax backward (models.py:50): d_logit_d = p_d * (gp_d - sum_d' p_d' gp_d'); dropped points take part
+    {
+        const int gg = g < npx ? g : 0;                   // idle groups mirror group 0 (shuffles stay warp-uniform)
+        const float *pp = s_p + gg * D, *gp = s_gp + gg * D;
+        float sd = 0.f;
+        for (int dd = gl; dd < D; dd += 8) sd = fmaf(pp[dd], gp[dd], sd);
+        sd += __shfl_xor_sync(LSS_FULL_MASK, sd, 1);
+        sd += __shfl_xor_sync(LSS_FULL_MASK, sd, 2);
+        sd += __shfl_xor_sync(LSS_FULL_MASK, sd, 4);
+        if (g < npx) {
+            for (int dd = gl; dd < D; dd += 8) s_out[dd * npx + g] = pp[dd] * (gp[dd] - sd);
+#pragma unroll
+            for (int q = 0; q < CPL / 4; ++q)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) s_out[(D + 4 * (gl + 8 * q) + a) * npx + g] = dctx[4 * q + a];
+        }
+    }
+    __syncthreads();
+    float *out = grad_dn + (size_t)bn * DC * d.HW + w0;
+    for (int i = threadIdx.x; i < DC * npx; i += SPLAT_THREADS) {
+        const int c = i / npx, px = i - c * npx;
+        const int hh = px / WC, ww = px - hh * WC;
+        if (w0 + ww < d.fW) out[(size_t)c * d.HW + hh * d.fW + ww] = s_out[i];
+    }
+}
+
 // operator-level backward of voxel_pooling: grad_x[p, :] = row of p's voxel, or 0
 template <bool CL>
 __global__ void __launch_bounds__(SPLAT_THREADS)
@@ -730,12 +892,15 @@ static inline PlanPtrs plan_ptrs(const lss_plan_layout *L, const void *workspace
 
 template <bool CL, bool VEC4>
 static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, cudaStream_t s) {
-    const size_t smem = (size_t)(CL ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
+    static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;   // tuning knob
+    int CH = ch_override > 0 ? ch_override : 32;          // channels per CTA: smaller staging tile, more CTAs per SM
+    if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
+    const size_t smem = (size_t)(CL ? tl.TY * CH : CH * (tl.TY + 4)) * 4;
     auto kern = k_fwd_store<CL, VEC4>;
     static bool configured = false;
     int st = opt_in_smem(kern, smem, configured);
     if (st != LSS_OK) return st;
-    kern<<<tl.n_tiles, SPLAT_THREADS, smem, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
+    kern<<<dim3(tl.n_tiles, d.C / CH), SPLAT_THREADS, smem, s>>>(d, tl, CH, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -938,9 +1103,37 @@ static int run_gather(bool cl, cudaStream_t s, const Dims &d, const int32_t *vox
     return dispatch_gather<0, 8>(cl, s, d, vox, prob, ctx_t, rows, grad_dn);
 }
 
+static bool bwd_compact_ok(const Dims &d, const float *ctx_t, const float *grows) {
+    return (d.C == 32 || d.C == 64 || d.C == 128) && d.fH <= 32 && lss_aligned(ctx_t, 16) && lss_aligned(grows, 16);
+}
+
+// compact-row backward (sorted plans): gradient rows of the non-empty voxels, then the pixel-owner gather
+static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanPtrs &pp, const int32_t *prow,
+                           const float *grad_bev, const float *prob, const float *ctx_t, float *grows, float *grad_dn,
+                           cudaStream_t s) {
+    if (cl) k_bwd_rows_compact<true><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
+    else k_bwd_rows_compact<false><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
+    LSS_CHECK_LAUNCH();
+    const int WC = max(1, 32 / d.fH);
+    const dim3 grid((d.fW + WC - 1) / WC, d.B * d.N);
+    const size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+#define GPX(CPL)                                                                                                 \
+    do {                                                                                                         \
+        static bool configured = false;                                                                          \
+        int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
+        if (st != LSS_OK) return st;                                                                             \
+        k_bwd_gather_px<CPL><<<grid, SPLAT_THREADS, smem, s>>>(d, WC, prow, prob, ctx_t, grows, grad_dn);        \
+    } while (0)
+    if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
+#undef GPX
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
 extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                              const float *grad_bev, int layout, const float *prob, const float *ctx_t,
-                             float *grad_rows, float *grad_depthnet, void *stream) {
+                             float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
@@ -950,20 +1143,20 @@ extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, con
     const Dims d = make_dims(p);
     LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
     const Tiling tl = make_tiling(L);
-    const char *w = (const char *)workspace;
-    const int32_t *vox = (const int32_t *)(w + L->off_vox);
-    const uint32_t *entries = (const uint32_t *)(w + L->off_entries);
-    const int32_t *tile_start = (const int32_t *)(w + L->off_tile_start);
+    const PlanPtrs pp = plan_ptrs(L, workspace);
     cudaStream_t s = (cudaStream_t)stream;
     const bool cl = layout == LSS_LAYOUT_CHANNELS_LAST;
+    if (plan_sorted && grad_rows != nullptr && bwd_compact_ok(d, ctx_t, grad_rows))
+        return run_bwd_compact(cl, d, tl, pp, (const int32_t *)((const char *)workspace + L->off_prow), grad_bev, prob,
+                               ctx_t, grad_rows, grad_depthnet, s);
     const float *rows = grad_bev;
     if (!cl) {
         LSS_REQUIRE(grad_rows != nullptr, LSS_ERR_WORKSPACE);
-        st = launch_bwd_rows(d, tl, tile_start, entries, grad_bev, grad_rows, s);
+        st = launch_bwd_rows(d, tl, pp.tile_start, pp.entries, grad_bev, grad_rows, s);
         if (st != LSS_OK) return st;
         rows = grad_rows;
     }
-    return run_gather(cl, s, d, vox, prob, ctx_t, rows, grad_depthnet);
+    return run_gather(cl, s, d, pp.vox, prob, ctx_t, rows, grad_depthnet);
 }
 
 extern "C" int lss_voxel_pooling_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,

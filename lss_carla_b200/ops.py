@@ -271,11 +271,11 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
 
 def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None):
     g, layout = _bev_layout(_f32c_keep(grad_bev))
-    if layout == LAYOUT_NCHW and grad_rows is None:
+    if grad_rows is None and (layout == LAYOUT_NCHW or plan.sorted):
         grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
     out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
     check(lib().lss_splat_bwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), layout, _ptr(pr), _ptr(ct),
-                              _ptr(grad_rows), _ptr(out), _stream()), "lss_splat_bwd")
+                              _ptr(grad_rows), _ptr(out), 1 if plan.sorted else 0, _stream()), "lss_splat_bwd")
     return out
 
 

@@ -17,7 +17,8 @@ calib = (ls.frustum, b["post_trans"].to(dev).reshape(-1, 3), M1.reshape(-1, 3, 3
 plan = ops.build_plan(prob, calib=calib, sorted=True, tile_cols=int(os.environ.get("TC", "0")))
 NT, NK = plan.layout.n_tiles, cfg.B * cfg.N * cfg.fHW[1]
 tb = torch.zeros(NT * 8, dtype=torch.int64, device=dev)
-tg = torch.zeros(NK * 8, dtype=torch.int64, device=dev)
+NM = 2 * 148
+tg = torch.zeros((NK + NM) * 8, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().lss_debug_set_timeline(C.c_void_p(tb.data_ptr()), C.c_void_p(tg.data_ptr())))
 vs = torch.empty((plan.layout.n_rows_cap, prob.C), device=dev)
 junk = torch.empty(64 * 1024 * 1024, device=dev)
@@ -33,7 +34,9 @@ for it in range(3):
 us = lambda a: a / 1e3
 def stat(name, a):
     print("%-26s mean %6.2f  p50 %6.2f  p90 %6.2f  max %6.2f" % (name, a.mean(), np.percentile(a, 50), np.percentile(a, 90), a.max()))
-g = tg.cpu().numpy().reshape(NK, 8).astype(np.float64)
+gall = tg.cpu().numpy().reshape(NK + NM, 8).astype(np.float64)
+g, gm = gall[:NK], gall[NK:]
+print('mixed-queue CTAs: records', int(plan._view(plan.layout.off_counters, 2, torch.int32)[1]), ' start us', us(gm[:, 0].min() - g[:, 0].min()), ' end mean/max us', us(gm[:, 3].mean() - g[:, 0].min()), us(gm[:, 3].max() - g[:, 0].min()))
 t = tb.cpu().numpy().reshape(NT, 8).astype(np.float64)
 g0 = g[:, 0].min()
 ne = g[:, 7] > 0

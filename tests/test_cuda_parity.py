@@ -323,6 +323,11 @@ def test_backward_vs_oracle_and_reference_autograd(case):
         got = ops.splat_bwd(prob, plan, gb.to(dev()).contiguous(memory_format=fmt), pr, ct).cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)                 # float64 analytic gradient
         np.testing.assert_allclose(got, g["grad_in"], rtol=RTOL, atol=ATOL)         # the reference's autograd
+    # plans without the in-bucket sort (atomic modes) take the voxel-order kernels
+    plan_u = ops.build_plan(prob, calib=calib_of(g), sorted=False)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        got = ops.splat_bwd(prob, plan_u, gb.to(dev()).contiguous(memory_format=fmt), pr, ct).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
     # through torch.autograd
     x = dn.to(dev()).requires_grad_(True)
     bev = ops.lift_splat(x, prob, plan, "sorted", False)
