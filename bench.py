@@ -138,6 +138,82 @@ def run_reference_arm(args, cfg, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, cfg, rank, world, local):
+    """Second BASELINE metric: LSS training samples/s (train_simbev.py:231-248 step on synthetic batches),
+    data-parallel over the ranks (DDP, NCCL gradient all-reduce; no collective inside the lift-splat)."""
+    assert torch.cuda.is_available(), "bench.py --metric train needs a GPU"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from lss_carla_b200.dist import max_over_ranks
+    from lss_carla_b200.harness import TrainStep, make_train_batch
+    per_gpu = args.global_batch // world if args.global_batch else cfg.B
+    override = None
+    if args.splat == "aten":          # baseline arm: the reference's stock-ATen lift-splat (QuickCumsum) on the same GPU
+        from oracle import ref_torch_cpu as T
+
+        def override(model, dn, rots, trans, intrins, post_rots, post_trans):
+            calib = {"rots": rots, "trans": trans, "intrins": intrins, "post_rots": post_rots, "post_trans": post_trans}
+            return T.liftsplat_forward(dn, model.frustum, calib, model.dx, model.bx, model.nx, dn.shape[1] - model.D)
+    step = TrainStep(cfg, dev, splat_mode=args.mode, inverse_mode=args.inverse, splat_override=override, ddp=world > 1,
+                     local_rank=local)
+    nsets = 2
+    batches = [make_train_batch(cfg, per_gpu, 10 * rank + i, dev) for i in range(nsets)]
+    steps, warm = min(args.steps, 200), max(3, min(args.warmup, 20))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warm):
+        step(batches[i % nsets])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(steps):
+            step(batches[i % nsets])
+        e1.record()
+        barrier()
+    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    value = world * per_gpu * steps / elapsed
+    # e2e: images + calibration from pinned host memory every step, loss read back every step
+    host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    e2e_steps = max(5, steps // 4)
+    probe = torch.empty(1, dtype=torch.float32).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % nsets].items()}
+        probe.copy_(step(b).detach().reshape(1), non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    if rank == 0:
+        H, W = cfg.final_dim
+        line = {"metric": "lss_train_samples_per_s", "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
+                "steps": steps, "warmup": warm, "ms_per_step": round(elapsed / steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"LSS training step (fwd + BCE + bwd + clip 5.0 + Adam), {cfg.N} cams {H}x{W}, D={cfg.D}, "
+                                       f"grid {cfg.nx[0]}x{cfg.nx[1]}x{cfg.nx[2]}, EfficientNet-B0-shaped trunk + ResNet-18 BEV encoder (PyTorch)",
+                           "lift_splat": "liblss_b200 fused path" if args.splat == "ours" else "reference ATen op chain (QuickCumsum) on the GPU",
+                           "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "parallelism": f"dp{world}",
+                           "l2": "activations of one step (> 1 GB) exceed the 126 MB L2"},
+                "clocks": clk.summary(),
+                "e2e": {"value": round(world * per_gpu * e2e_steps / e2e_elapsed, 2), "unit": "samples/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps},
+                "gpu_launches": (LAUNCHES_PER_STEP[args.mode] * steps) if args.splat == "ours" else 0,
+                "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_name(cfg):
     fH, fW = cfg.fHW
     X, Y, Z = cfg.nx
@@ -195,7 +271,9 @@ def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAG
     bs.out["grad"] = ops.splat_bwd(prob, bs.plan, bs.grad_bev, pr, ct, bs.rows)
 
 
-LAUNCHES_PER_STEP = {"sorted": 8, "atomic": 7, "red": 8}   # calib, voxel+count, scatter, [sort], lift, fwd(+memset), rows, gather
+# kernels of liblss_b200.so per step: calib, voxel+count, scatter, [sort], lift, forward (sorted: gather + store;
+# atomic: one tile kernel; red: memset + one kernel), gradient rows, gather
+LAUNCHES_PER_STEP = {"sorted": 9, "atomic": 7, "red": 8}
 
 
 def time_kernel(fn, sets, iters, stream):
@@ -239,6 +317,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--metric", default="pool", choices=["pool", "train"],
+                    help="pool: BEV-pool Mpoints/s fwd+bwd (headline); train: LSS training samples/s")
+    ap.add_argument("--splat", default="ours", choices=["ours", "aten"], help="--metric train: lift-splat implementation")
+    ap.add_argument("--global-batch", type=int, default=0, help="--metric train: fixed global batch (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +331,9 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, cfg, rank, world)
         return
+    if args.metric == "train":
+        run_train(args, cfg, rank, world, local)
+        return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local)
@@ -258,6 +343,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from lss_carla_b200 import api, ops
+    from lss_carla_b200.dist import max_over_ranks
     from lss_carla_b200.tools import gen_dx_bx
 
     args.warmup = max(args.warmup, 3)
@@ -308,11 +394,7 @@ def main():
             step(i)
         e1.record()
         barrier()
-    elapsed = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
+    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
     value = world * cfg.points * args.steps / elapsed / 1e6
 
     # ---- e2e through the public API: host buffers in, input gradient out, every step
@@ -342,11 +424,7 @@ def main():
         e2e_step(i)
     e1.record()
     barrier()
-    e2e_elapsed = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed = float(t.item())
+    e2e_elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
     e2e_value = world * cfg.points * e2e_steps / e2e_elapsed / 1e6
 
     if rank != 0:
@@ -390,8 +468,16 @@ def main():
     peak, peak_src = load_peaks()
     achieved = fwd_bytes / stages["splat_fwd"] / 1e9
     step_s = elapsed / args.steps
-    roof = {"bound": "hbm", "kernel": "k_splat_fwd_tile", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+    fwd_name = {"sorted": "lss_splat_fwd = k_fwd_gather + k_fwd_store (deterministic forward, both launches)",
+                "atomic": "k_splat_fwd_tile (shared-memory atomics)", "red": "memset + k_splat_fwd_red"}[args.mode]
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of the same launches, from the ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}_{args.mode}_{args.layout}")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": fwd_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
             "algorithmic_bytes_per_launch": fwd_bytes, "kernel_us": round(stages["splat_fwd"] * 1e6, 2),
             "step_algorithmic_bytes": fwd_bytes + bwd_bytes,
             "step_frac": round((fwd_bytes + bwd_bytes) / step_s / 1e9 / peak, 4),

@@ -720,12 +720,13 @@ k_bwd_rows_compact(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, co
 // the CTA's points are staged in shared memory first (one round of coalesced loads); the depth loop then
 // reads shared memory, keeps LF gradient rows in flight and needs no control flow (dropped points read
 // row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
-template <int CPL>
-__global__ void __launch_bounds__(SPLAT_THREADS)
+template <int CPL, int DZ>
+__global__ void __launch_bounds__(SPLAT_THREADS * DZ)
 k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *__restrict__ prob,
                 const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
     extern __shared__ __align__(16) float smem[];
     constexpr int LF = CPL <= 8 ? 4 : 2;
+    constexpr int NT = SPLAT_THREADS * DZ;                // DZ groups share a pixel: each walks 1/DZ of the depths
     const int bn = blockIdx.y, w0 = blockIdx.x * WC;
     const int D = d.D, C = d.C, fH = d.fH, DC = D + C;
     const int npx = fH * WC;                              // pixels of the CTA (<= 32), group g <-> pixel (h, wl)
@@ -733,7 +734,8 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
     int *s_row = reinterpret_cast<int *>(smem + 32 * D);  // [32][D] compact row or -1
     float *s_gp = smem + 64 * D;                          // [32][D] <grad row, ctx>
     float *s_out = smem + 96 * D;                         // [D + C][npx] staged outputs
-    for (int i = threadIdx.x; i < npx * D; i += SPLAT_THREADS) {
+    float *s_part = s_out + DC * npx;                     // [DZ - 1][32][C] partial context gradients
+    for (int i = threadIdx.x; i < npx * D; i += NT) {
         const int dd = i / npx, px = i - dd * npx;        // px = h * WC + wl: consecutive threads walk a pixel row
         const int h = px / WC, wl = px - h * WC;
         const bool ok = w0 + wl < d.fW;
@@ -741,12 +743,14 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
         s_p[px * D + dd] = ok ? __ldg(prob + p) : 0.f;
         s_row[px * D + dd] = ok ? __ldg(prow + p) : -1;
     }
-    const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    const int g = (threadIdx.x >> 3) & 31, z = threadIdx.x >> 8;
     const int h = g / WC, wl = g - h * WC;
     const bool active = g < npx && w0 + wl < d.fW;
+    const size_t my_ctx = ((size_t)bn * d.HW + (active ? h * d.fW + w0 + wl : 0)) * C;
     float ctx[CPL], dctx[CPL];
     {
-        const float4 *cp = reinterpret_cast<const float4 *>(ctx_t + ((size_t)bn * d.HW + (active ? h * d.fW + w0 + wl : 0)) * C) + gl;
+        const float4 *cp = reinterpret_cast<const float4 *>(ctx_t + my_ctx) + gl;
 #pragma unroll
         for (int q = 0; q < CPL / 4; ++q) {
             const float4 v = __ldg(cp + 8 * q);
@@ -759,24 +763,25 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
     const float *my_p = s_p + (g < npx ? g : 0) * D;
     const int *my_row = s_row + (g < npx ? g : 0) * D;
     const float4 *rows4 = reinterpret_cast<const float4 *>(grows) + gl;
+    const float4 *safe4 = reinterpret_cast<const float4 *>(ctx_t + my_ctx) + gl;   // finite stand-in for "no row"
     const int c4 = C >> 2;
-    for (int d0 = 0; d0 < D; d0 += LF) {                  // warp-uniform: every group walks all D depths
+    const int dz = ((D + DZ - 1) / DZ + LF - 1) / LF * LF;                       // depths per group, multiple of LF
+    const int d_end = min(D, (z + 1) * dz);
+    for (int d0 = z * dz; d0 < d_end; d0 += LF) {         // warp-uniform: the 4 groups of a warp share z
         float x[LF][CPL];
         float pj[LF];
+        bool on[LF];
 #pragma unroll
         for (int u = 0; u < LF; ++u) {
             const int dd = min(d0 + u, D - 1);
-            const int rj = active ? my_row[dd] : -1;
-            pj[u] = (rj >= 0 && d0 + u < D) ? my_p[dd] : 0.f;     // dropped point / padding: weight 0, row 0
-            const float4 *rp = rows4 + (size_t)max(rj, 0) * c4;
+            const int rj = (active && d0 + u < d_end) ? my_row[dd] : -1;
+            on[u] = rj >= 0;
+            pj[u] = on[u] ? my_p[dd] : 0.f;               // dropped point / padding: weight 0, a finite row
+            const float4 *rp = on[u] ? rows4 + (size_t)rj * c4 : safe4;
 #pragma unroll
             for (int q = 0; q < CPL / 4; ++q) {
                 const float4 v = __ldg(rp + 8 * q);
                 x[u][4 * q] = v.x; x[u][4 * q + 1] = v.y; x[u][4 * q + 2] = v.z; x[u][4 * q + 3] = v.w;
-            }
-            if (rj < 0 || d0 + u >= D) {
-#pragma unroll
-                for (int a = 0; a < CPL; ++a) x[u][a] = 0.f;
             }
         }
 #pragma unroll
@@ -787,12 +792,17 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
             dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 1);
             dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 2);
             dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 4);
-            if (gl == 0 && g < npx && d0 + u < D) s_gp[g * D + d0 + u] = dot;
+            if (gl == 0 && g < npx && d0 + u < d_end) s_gp[g * D + d0 + u] = on[u] ? dot : 0.f;
         }
     }
-    __syncwarp();
+    if (DZ > 1 && z > 0) {                                // partial context gradients of the upper depth ranges
+        float4 *pp = reinterpret_cast<float4 *>(s_part + ((size_t)(z - 1) * 32 + g) * C) + gl;
+#pragma unroll
+        for (int q = 0; q < CPL / 4; ++q) pp[8 * q] = make_float4(dctx[4 * q], dctx[4 * q + 1], dctx[4 * q + 2], dctx[4 * q + 3]);
+    }
+    __syncthreads();
     // softmax backward (models.py:50): d_logit_d = p_d * (gp_d - sum_d' p_d' gp_d'); dropped points take part
-    {
+    if (z == 0) {
         const int gg = g < npx ? g : 0;                   // idle groups mirror group 0 (shuffles stay warp-uniform)
         const float *pp = s_p + gg * D, *gp = s_gp + gg * D;
         float sd = 0.f;
@@ -803,6 +813,15 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
         if (g < npx) {
             for (int dd = gl; dd < D; dd += 8) s_out[dd * npx + g] = pp[dd] * (gp[dd] - sd);
 #pragma unroll
+            for (int zz = 1; zz < DZ; ++zz) {             // fixed order: deterministic
+                const float4 *qp = reinterpret_cast<const float4 *>(s_part + ((size_t)(zz - 1) * 32 + g) * C) + gl;
+#pragma unroll
+                for (int q = 0; q < CPL / 4; ++q) {
+                    const float4 v = qp[8 * q];
+                    dctx[4 * q] += v.x; dctx[4 * q + 1] += v.y; dctx[4 * q + 2] += v.z; dctx[4 * q + 3] += v.w;
+                }
+            }
+#pragma unroll
             for (int q = 0; q < CPL / 4; ++q)
 #pragma unroll
                 for (int a = 0; a < 4; ++a) s_out[(D + 4 * (gl + 8 * q) + a) * npx + g] = dctx[4 * q + a];
@@ -810,7 +829,7 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
     }
     __syncthreads();
     float *out = grad_dn + (size_t)bn * DC * d.HW + w0;
-    for (int i = threadIdx.x; i < DC * npx; i += SPLAT_THREADS) {
+    for (int i = threadIdx.x; i < DC * npx; i += NT) {
         const int c = i / npx, px = i - c * npx;
         const int hh = px / WC, ww = px - hh * WC;
         if (w0 + ww < d.fW) out[(size_t)c * d.HW + hh * d.fW + ww] = s_out[i];
@@ -1116,16 +1135,24 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
     LSS_CHECK_LAUNCH();
     const int WC = max(1, 32 / d.fH);
     const dim3 grid((d.fW + WC - 1) / WC, d.B * d.N);
-    const size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
+    // split the depth range over DZ groups per pixel while the grid alone cannot fill the SMs
+    const long long warps = (long long)grid.x * grid.y * SPLAT_WARPS;
+    static int dz_override = getenv("LSS_BWD_DZ") ? atoi(getenv("LSS_BWD_DZ")) : 0;     // tuning knob
+    int DZ = 1;                                           // measured at cfg2: 1 / 2 / 4 within noise (44.6 / 48.3 / 43.3 us)
+    (void)warps;
+    if (dz_override == 1 || dz_override == 2 || dz_override == 4) DZ = dz_override;
+    const size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC + (size_t)(DZ - 1) * 32 * d.C) * 4;
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GPX(CPL)                                                                                                 \
+#define GPX1(CPL, Z)                                                                                             \
     do {                                                                                                         \
         static bool configured = false;                                                                          \
-        int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
+        int st = opt_in_smem(k_bwd_gather_px<CPL, Z>, smem, configured);                                         \
         if (st != LSS_OK) return st;                                                                             \
-        k_bwd_gather_px<CPL><<<grid, SPLAT_THREADS, smem, s>>>(d, WC, prow, prob, ctx_t, grows, grad_dn);        \
+        k_bwd_gather_px<CPL, Z><<<grid, SPLAT_THREADS * Z, smem, s>>>(d, WC, prow, prob, ctx_t, grows, grad_dn); \
     } while (0)
+#define GPX(CPL) do { if (DZ == 4) GPX1(CPL, 4); else if (DZ == 2) GPX1(CPL, 2); else GPX1(CPL, 1); } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
+#undef GPX1
 #undef GPX
     LSS_CHECK_LAUNCH();
     return LSS_OK;

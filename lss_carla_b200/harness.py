@@ -1,0 +1,53 @@
+"""Training-step harness for the second BASELINE metric (LSS training samples/s, 1/2/4/8 GPUs).
+
+Mirrors the step structure of the reference's training loop (train_simbev.py:231-248): forward, BCE-with-logits
+with pos_weight 2.13 (tools.py:222-229), backward, gradient clipping at 5.0, Adam (lr 1e-3, weight decay 1e-7,
+train_simbev.py:29-53, :192), on a synthetic SimBEV-shaped batch resident on the device.  The camera trunk and the
+BEV encoder are the PyTorch stand-ins of `trunk.py` (they stay in PyTorch per north_star); the lift-splat between
+them is the CUDA path -- or, for the baseline arm, whatever `splat_override` the caller supplies."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import models
+from .synthetic import make_calibration
+
+
+def make_train_batch(cfg, B, seed, device):
+    """imgs N(0,1) f32[B,N,3,H,W] (ImageNet-normalised range, tools.py:167-171), calibration of the synthetic rig with
+    the script's default augmentation, targets Bernoulli(0.03) f32[B,1,X,Y] (README.md:231)."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    H, W = cfg.final_dim
+    X, Y, _ = cfg.nx
+    c = type(cfg)(**{**cfg.__dict__, "B": B}) if B != cfg.B else cfg
+    cal = make_calibration(c, seed, "train")
+    batch = {k: v.to(device) for k, v in cal.items()}
+    batch["imgs"] = torch.randn(B, cfg.N, 3, H, W, generator=g).to(device)
+    batch["binimgs"] = (torch.rand(B, 1, X, Y, generator=g) < 0.03).float().to(device)
+    return batch
+
+
+class TrainStep:
+    def __init__(self, cfg, device, splat_mode="sorted", inverse_mode="device", splat_override=None, ddp=False,
+                 local_rank=0, seed=0):
+        torch.manual_seed(seed)                       # same initial weights on every rank (DDP broadcasts anyway)
+        self.model = models.LiftSplatShoot(cfg.grid_conf, cfg.data_aug_conf, outC=1, splat_mode=splat_mode,
+                                           inverse_mode=inverse_mode).to(device)
+        if splat_override is not None:
+            self.model._splat_override = splat_override
+        self.net = self.model
+        if ddp:
+            self.net = nn.parallel.DistributedDataParallel(self.model, device_ids=[local_rank], gradient_as_bucket_view=True)
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=1e-3, weight_decay=1e-7)
+        self.loss_fn = nn.BCEWithLogitsLoss(pos_weight=torch.tensor([2.13], device=device))
+        self.net.train()
+
+    def __call__(self, batch):
+        self.opt.zero_grad(set_to_none=True)
+        preds = self.net(batch["imgs"], batch["rots"], batch["trans"], batch["intrins"], batch["post_rots"], batch["post_trans"])
+        loss = self.loss_fn(preds, batch["binimgs"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.net.parameters(), 5.0)
+        self.opt.step()
+        return loss

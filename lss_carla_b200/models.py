@@ -33,6 +33,9 @@ def _fused_get_voxels(self, x, rots, trans, intrins, post_rots, post_trans):
     ce = self.camencode
     feat = ce.get_eff_depth(x.view(B * N, x.shape[2], imH, imW))          # PyTorch trunk (models.py:53)
     dn = ce.depthnet(ce.dropout(feat))                                     # models.py:55-56
+    override = getattr(self, "_splat_override", None)                      # measurement hook: baseline arm of the harness
+    if override is not None:
+        return override(self, dn, rots, trans, intrins, post_rots, post_trans)
     return lift_splat_from_depthnet(self, dn, rots, trans, intrins, post_rots, post_trans)
 
 

@@ -32,9 +32,16 @@ def test_every_header_symbol_is_exported_and_bound(L):
 
 
 def test_struct_sizes_match_header():
-    # lss_problem: 9 int32 + 6 float = 60 bytes; lss_plan_layout: 3 int32 (+pad) + int64 + 7 size_t
+    # lss_problem: 9 int32 + 6 float = 60 bytes; lss_plan_layout: 3 int32 (+pad) + int64 + 15 size_t + int64
     assert C.sizeof(_lib.LssProblem) == 60
-    assert C.sizeof(_lib.LssPlanLayout) == 16 + 8 + 7 * 8
+    assert C.sizeof(_lib.LssPlanLayout) == 16 + 8 + 15 * 8 + 8
+    # field order of the ctypes mirror == field order of the C struct
+    import re
+    hdr = open(_lib.HEADER).read()
+    body = hdr[hdr.index("typedef struct lss_plan_layout {"):hdr.index("} lss_plan_layout;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = re.findall(r"(?:int32_t|int64_t|size_t)\s+([a-z_0-9]+)\s*;", body)
+    assert c_fields == [f[0] for f in _lib.LssPlanLayout._fields_]
 
 
 def _problem(cfg):
@@ -65,6 +72,9 @@ def test_plan_layout_host_only(L):
     assert lay.tile_cols == 200 and lay.tiles_per_row == 1 and lay.n_tiles == 8 * 200
     assert lay.n_points == cfg.points == 346368
     assert lay.bytes >= 2 * 4 * cfg.points
+    assert lay.n_rows_cap == min(cfg.points, 8 * 200 * 200)
+    offs = [getattr(lay, f[0]) for f in _lib.LssPlanLayout._fields_ if f[0].startswith("off_")]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and offs[-1] < lay.bytes
     assert L.lss_plan_layout_init(C.byref(p.c), 56, C.byref(lay)) == 0
     assert lay.tiles_per_row == 4 and lay.n_tiles == 8 * 200 * 4
     assert L.lss_plan_layout_init(C.byref(p.c), 13, C.byref(lay)) == -3      # not a multiple of 8
@@ -85,7 +95,7 @@ def test_bad_arguments_return_status_codes(L):
     big = _problem(cfg)
     big.c.D = 1 << 20
     assert L.lss_plan_layout_init(C.byref(big.c), 0, C.byref(lay)) == -3     # > 2^20 points per sample
-    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, 0, 0, null) == -5
+    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, null, 0, 0, 0, 0, null) == -5
     assert L.lss_quickcumsum_scratch_elems(5000) >= 5000 + 5
 
 
