@@ -171,9 +171,11 @@ int lss_plan_reference_order(const lss_problem *p, const lss_plan_layout *L, con
 
 /* CamEncode.get_depth_dist + the operand layout of get_depth_feat (models.py:49-61):
  *   depthnet_out f32[B*N, D+C, fH, fW]  ->  prob f32[B*N, D, fH, fW] = softmax over D,
- *                                            ctx_t f32[B*N, fH*fW, C] = context, pixel-major. */
+ *                                            ctx_t f32[B*N, fH*fW, C] = context, pixel-major;
+ *   optional (may be null) prob_col f32[B*N, fW, D, fH]: the same weights, camera-column major -- the block
+ *   the GROUP forward gather stages per column; pass it on to lss_splat_fwd. */
 int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
-                     void *stream);
+                     float *prob_col, void *stream);
 
 /* Kernel variants of the tile-owner forward in SORTED mode (bit-identical results). */
 enum { LSS_VARIANT_AUTO = 0,   /* GROUP when the shape and workspace allow it, else WARP                          */
@@ -190,11 +192,12 @@ int lss_bev_clear(const lss_problem *p, float *bev, void *stream);
  * them:  bev[b, iz*C+c, ix, iy] = sum_{p in voxel} prob[p] * ctx_t[pixel(p), c].
  * Modes SORTED / SMEM_ATOMIC write every BEV element exactly once (zeros included): no memset, no global
  * atomics.  `precleared` != 0 promises that `bev` is already all-zero (only RED_GLOBAL looks at it).
+ * `prob_col`: optional column-major weights from lss_lift_prepare (null: staged from `prob`).
  * `voxel_sums`: caller workspace f32[min(n_points, B*nx*ny*nz), C] for the GROUP variant (may be null:
  * the WARP variant is used).  bev f32[B, nz*C, nx, ny] in `layout`. */
 int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
-                  const float *prob, const float *ctx_t, float *voxel_sums, float *bev, int mode, int layout,
-                  int variant, int precleared, void *stream);
+                  const float *prob, const float *ctx_t, const float *prob_col, float *voxel_sums, float *bev,
+                  int mode, int layout, int variant, int precleared, void *stream);
 
 /* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
  * autograd backward of models.py:58-59,:199-200,:240-244):

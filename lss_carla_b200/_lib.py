@@ -63,10 +63,10 @@ SIGNATURES = {
     "lss_voxel_index": (C.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lss_plan_build": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
-    "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P]),
+    "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
-    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P]),

@@ -17,7 +17,8 @@
 #define LIFT_WARPS 8
 
 __global__ void __launch_bounds__(LIFT_THREADS)
-k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, float *__restrict__ ctx_t) {
+k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, float *__restrict__ ctx_t,
+               float *__restrict__ prob_col) {
     extern __shared__ float smem[];                 // [D+C][33]
     __shared__ float s_red[LIFT_WARPS][LIFT_PX];
     const int chunks = (d.HW + LIFT_PX - 1) / LIFT_PX;
@@ -54,7 +55,14 @@ k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, f
     for (int w = 0; w < LIFT_WARPS; ++w) sum += s_red[w][lane];
     if (live) {
         float *pdst = prob + (size_t)bn * d.D * d.HW + hw;
-        for (int dd = warp; dd < d.D; dd += LIFT_WARPS) pdst[(size_t)dd * d.HW] = smem[dd * S + lane] / sum;
+        // optional second copy, camera-column major [bn][w][D][fH]: the operand block the forward gather stages
+        const int h = hw / d.fW, w = hw - h * d.fW;
+        float *cdst = prob_col ? prob_col + ((size_t)(bn * d.fW + w) * d.D) * d.fH + h : nullptr;
+        for (int dd = warp; dd < d.D; dd += LIFT_WARPS) {
+            const float pv = smem[dd * S + lane] / sum;
+            pdst[(size_t)dd * d.HW] = pv;
+            if (cdst) cdst[dd * d.fH] = pv;
+        }
     }
 
     // ---- context transpose [C][HW] -> [HW][C]
@@ -66,7 +74,7 @@ k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, f
 }
 
 extern "C" int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
-                                void *stream) {
+                                float *prob_col, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(depthnet_out && prob && ctx_t, LSS_ERR_BAD_ARG);
@@ -77,7 +85,7 @@ extern "C" int lss_lift_prepare(const lss_problem *p, const float *depthnet_out,
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_lift_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return LSS_ERR_CUDA;
-    k_lift_prepare<<<d.B * d.N * chunks, LIFT_THREADS, smem, (cudaStream_t)stream>>>(d, depthnet_out, prob, ctx_t);
+    k_lift_prepare<<<d.B * d.N * chunks, LIFT_THREADS, smem, (cudaStream_t)stream>>>(d, depthnet_out, prob, ctx_t, prob_col);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }

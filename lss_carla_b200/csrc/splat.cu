@@ -43,6 +43,7 @@ __device__ __forceinline__ void lss_stamp(int tile, int slot) {
 struct SrcArgs {
     const float *base;   // LIFT: ctx_t [B*N, HW, C]        DENSE: x with strides s[0..5]
     const float *prob;   // LIFT: prob [B*N, D, HW]         DENSE: unused
+    const float *prob_col;   // LIFT, optional: prob in camera-column order [B*N, fW, D, fH]
     long long s[6];
 };
 
@@ -113,26 +114,42 @@ __device__ __forceinline__ Tile2D tile_2d(const Dims &d, const Tiling &tl, const
     return t;
 }
 
-// Stream a tile to global memory (src == nullptr: zeros).  Division-free walk: every thread advances by
-// SPLAT_THREADS vector slots per iteration.
+// Stream a tile to global memory (src == nullptr: zeros).  A warp walks whole rows (or 32/vpr rows at once when a
+// row has fewer than 32 vector slots), so the inner loop is one shared load, one global store and two pointer
+// increments: the store stream, not index arithmetic, has to be the limit here.
 template <bool VEC4>
 __device__ __forceinline__ void store_tile(const Tile2D &t, const float *__restrict__ src, float *__restrict__ bev) {
-    constexpr int W = VEC4 ? 4 : 1;
-    const int vpr = t.RL / W;                       // vector slots per row
-    const int total = t.NR * vpr;
-    int row = threadIdx.x / vpr, v = threadIdx.x - row * vpr;
-    const int dr = SPLAT_THREADS / vpr, dv = SPLAT_THREADS - dr * vpr;
     float *g = bev + t.gbase;
-    for (int i = threadIdx.x; i < total; i += SPLAT_THREADS) {
-        if (VEC4) {
-            const float4 val = src ? *reinterpret_cast<const float4 *>(src + row * t.SRS + v * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(g + (size_t)row * t.GRS + v * 4) = val;
-        } else {
+    if (!VEC4) {
+        const int total = t.NR * t.RL;
+        int row = threadIdx.x / t.RL, v = threadIdx.x - row * t.RL;
+        const int dr = SPLAT_THREADS / t.RL, dv = SPLAT_THREADS - dr * t.RL;
+        for (int i = threadIdx.x; i < total; i += SPLAT_THREADS) {
             g[(size_t)row * t.GRS + v] = src ? src[row * t.SRS + v] : 0.f;
+            v += dv; row += dr;
+            if (v >= t.RL) { v -= t.RL; ++row; }
         }
-        v += dv; row += dr;
-        if (v >= vpr) { v -= vpr; ++row; }
+        return;
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vpr = t.RL >> 2;                              // 16-byte slots per row
+    const int rpw = vpr >= 32 ? 1 : 32 / vpr;               // rows a warp covers per pass
+    const int sub = rpw == 1 ? 0 : lane / vpr;
+    const int v0 = rpw == 1 ? lane : lane - sub * vpr;
+    if (sub >= rpw) return;
+    const int row0 = warp * rpw + sub, rstep = SPLAT_WARPS * rpw;
+    float4 *gp = reinterpret_cast<float4 *>(g + (size_t)row0 * t.GRS) + v0;
+    const size_t gstep = (size_t)rstep * t.GRS / 4;         // GRS % 4 == 0 on the vector path
+    if (src == nullptr) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int row = row0; row < t.NR; row += rstep, gp += gstep)
+            for (int v = v0; v < vpr; v += 32) gp[v - v0] = z;
+        return;
+    }
+    const float4 *sp = reinterpret_cast<const float4 *>(src + row0 * t.SRS) + v0;
+    const int sstep = rstep * t.SRS / 4;                    // SRS % 4 == 0
+    for (int row = row0; row < t.NR; row += rstep, gp += gstep, sp += sstep)
+        for (int v = v0; v < vpr; v += 32) gp[v - v0] = sp[v - v0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,14 +304,14 @@ template <int CPL>
 __global__ void __launch_bounds__(GATHER_THREADS, 1024 / GATHER_THREADS)
 k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const int4 *__restrict__ seg_recs,
              const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs,
-             const uint32_t *__restrict__ entries, const float *__restrict__ prob, const float *__restrict__ ctx_t,
-             float *__restrict__ vsum) {
+             const uint32_t *__restrict__ entries, const float *__restrict__ prob, const float *__restrict__ prob_col,
+             const float *__restrict__ ctx_t, float *__restrict__ vsum) {
     extern __shared__ __align__(16) float s_col[];       // [fH][C] context rows of the column, [D][fH] softmax weights
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
-    const bool column = (int)blockIdx.x < n_keys;        // else: a CTA of the mixed-voxel queue
-    const int key = column ? blockIdx.x : 0;             // camera column (b, n, w0)
-    lss_stamp<true>(blockIdx.x, 0);
+    const bool column = (int)blockIdx.x < n_keys;        // else: a CTA of the mixed-voxel queue (group per voxel, all
+    const int key = column ? blockIdx.x : 0;             // operands from global memory); measured: a warp per mixed
+    lss_stamp<true>(blockIdx.x, 0);                      // voxel (16 rows in flight, sum handed on by shuffle) is slower
     const int n_rec = column ? __ldg(key_count + key) : __ldg(counters + 1);
     const int w0 = column ? key % d.fW : -1, bn = key / d.fW;
     const int n0 = column ? bn % d.N : -1;
@@ -307,8 +324,13 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
             const int h = i / c4, q = i - h * c4;
             reinterpret_cast<float4 *>(s_col)[i] = __ldg(src + (size_t)h * d.fW * c4 + q);
         }
-        const float *psrc = prob + (size_t)bn * d.DHW + w0;
-        for (int i = threadIdx.x; i < d.D * d.fH; i += GATHER_THREADS) s_prob[i] = __ldg(psrc + (size_t)i * d.fW);
+        if (prob_col != nullptr) {                       // contiguous block [D][fH] of this column
+            const float *psrc = prob_col + (size_t)key * d.D * d.fH;
+            for (int i = threadIdx.x; i < d.D * d.fH; i += GATHER_THREADS) s_prob[i] = __ldg(psrc + i);
+        } else {
+            const float *psrc = prob + (size_t)bn * d.DHW + w0;
+            for (int i = threadIdx.x; i < d.D * d.fH; i += GATHER_THREADS) s_prob[i] = __ldg(psrc + (size_t)i * d.fW);
+        }
     }
     const int4 *recs = column ? seg_recs + (size_t)key * (d.D * d.fH) : mixed_recs;
     const int lane = threadIdx.x & 31;
@@ -321,10 +343,8 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
     // costs a MATCH per shuffle), so every loop below is warp-uniform and the groups are predicated.
     int4 rec = make_int4(0, 0, 0, 0);                    // {first entry, length, batch index, compact row}
     uint32_t e0 = 0;
-    if (r < n_rec) {
-        rec = __ldg(recs + r);
-        if (rec.y > 0 && gl < rec.y) e0 = __ldg(entries + rec.x + gl);
-    }
+    if (r < n_rec) rec = __ldg(recs + r);
+    if (rec.y > 0 && gl < rec.y) e0 = __ldg(entries + rec.x + gl);
     if (column) __syncthreads();
     lss_stamp<true>(blockIdx.x, 1);
     while (__any_sync(LSS_FULL_MASK, r < n_rec)) {
@@ -430,13 +450,15 @@ k_fwd_store(Dims d, Tiling tl, int CH, const int32_t *__restrict__ tile_start, c
             float *__restrict__ bev) {
     extern __shared__ __align__(16) float smem[];
     const int tile = blockIdx.x;
-    const int c0 = blockIdx.y * CH;                       // this CTA owns channels [c0, c0 + CH) of the tile
+    const int c0 = blockIdx.y * (CH < 0 ? -CH : CH);      // this CTA owns channels [c0, c0 + CH) of the tile
     if (blockIdx.y == 0) lss_stamp(tile, 0);
     const TileCoord tc = tile_coord(d, tl, tile);
     Tile2D t2 = tile_2d<CL>(d, tl, tc);
-    if (CL) { t2.RL = CH; t2.SRS = CH; t2.gbase += c0; }
-    else { t2.NR = CH; t2.gbase += (size_t)c0 * t2.GRS; }
-    const int nseg = __ldg(tile_nseg + tile);
+    { const int ch = CH < 0 ? -CH : CH;
+      if (CL) { t2.RL = ch; t2.SRS = ch; t2.gbase += c0; }
+      else { t2.NR = ch; t2.gbase += (size_t)c0 * t2.GRS; } }
+    const int nseg = CH < 0 ? 0 : __ldg(tile_nseg + tile);      // CH < 0: measurement aid, zero tiles only
+    if (CH < 0) CH = -CH;
     if (nseg == 0) { store_tile<VEC4>(t2, nullptr, bev); if (blockIdx.y == 0) lss_stamp(tile, 3); return; }
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
     const int C = d.C, c4 = CH >> 2;                      // C % 4 == 0 and CH % 4 == 0 on this path
@@ -912,26 +934,28 @@ static inline PlanPtrs plan_ptrs(const lss_plan_layout *L, const void *workspace
 template <bool CL, bool VEC4>
 static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, cudaStream_t s) {
     static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;   // tuning knob
-    int CH = ch_override > 0 ? ch_override : 32;          // channels per CTA: smaller staging tile, more CTAs per SM
+    int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
     if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
     const size_t smem = (size_t)(CL ? tl.TY * CH : CH * (tl.TY + 4)) * 4;
     auto kern = k_fwd_store<CL, VEC4>;
     static bool configured = false;
     int st = opt_in_smem(kern, smem, configured);
     if (st != LSS_OK) return st;
-    kern<<<dim3(tl.n_tiles, d.C / CH), SPLAT_THREADS, smem, s>>>(d, tl, CH, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
+    static int zero_only = getenv("LSS_STORE_ZERO") ? 1 : 0;                                // measurement aid
+    kern<<<dim3(tl.n_tiles, d.C / CH), SPLAT_THREADS, smem, s>>>(d, tl, zero_only ? -CH : CH, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
 
 // GROUP variant of the deterministic forward: gather into compact rows, then stream the tiles out
 static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, const PlanPtrs &pp, long long L_rows_cap,
-                         const float *prob, const float *ctx_t, float *vsum, float *bev, cudaStream_t s) {
+                         const float *prob, const float *prob_col, const float *ctx_t, float *vsum, float *bev,
+                         cudaStream_t s) {
     const int n_keys = d.B * d.N * d.fW;                 // one CTA per camera column ...
     const int grid = n_keys + 2 * num_sms();             // ... plus the CTAs that drain the mixed-voxel queue
     const size_t gsm = (size_t)(d.fH * d.C + d.D * d.fH) * 4;
     if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GATHER_ARGS d, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, pp.entries, prob, ctx_t, vsum
+#define GATHER_ARGS d, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, pp.entries, prob, prob_col, ctx_t, vsum
     if (d.C == 32) k_fwd_gather<4><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else if (d.C == 64) k_fwd_gather<8><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else k_fwd_gather<16><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
@@ -969,7 +993,7 @@ static int dispatch_fwd(bool atomic, bool cl, int variant, const Dims &d, const 
                           (d.C == 32 || d.C == 64 || d.C == 128) && (long long)d.N * d.HW * d.C < (1ll << 31) &&
                           (size_t)(d.fH * d.C + d.D * d.fH) * 4 <= 48 * 1024;
     if (variant == LSS_VARIANT_GROUP && !group_ok) return LSS_ERR_UNSUPPORTED;
-    if (group_ok && variant != LSS_VARIANT_WARP) return run_fwd_group(cl, vec4, d, tl, pp, rows_cap, src.prob, src.base, vsum, bev, s);
+    if (group_ok && variant != LSS_VARIANT_WARP) return run_fwd_group(cl, vec4, d, tl, pp, rows_cap, src.prob, src.prob_col, src.base, vsum, bev, s);
     const int32_t *ts = pp.tile_start;
     const uint32_t *en = pp.entries;
     if (!DENSE && rows16) {
@@ -1000,8 +1024,8 @@ extern "C" int lss_bev_clear(const lss_problem *p, float *bev, void *stream) {
 }
 
 extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace, const float *prob,
-                             const float *ctx_t, float *voxel_sums, float *bev, int mode, int layout, int variant,
-                             int precleared, void *stream) {
+                             const float *ctx_t, const float *prob_col, float *voxel_sums, float *bev, int mode,
+                             int layout, int variant, int precleared, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
@@ -1017,7 +1041,7 @@ extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, con
     cudaStream_t s = (cudaStream_t)stream;
     const bool cl = layout == LSS_LAYOUT_CHANNELS_LAST;
     SrcArgs src{};
-    src.base = ctx_t; src.prob = prob;
+    src.base = ctx_t; src.prob = prob; src.prob_col = prob_col;
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
         return dispatch_fwd<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, d, tl, plan_ptrs(L, workspace), L->n_rows_cap, src, voxel_sums, bev, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {

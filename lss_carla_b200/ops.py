@@ -226,10 +226,19 @@ def lift_prepare(prob: Problem, depthnet_out):
     BN, HW = prob.B * prob.N, prob.fH * prob.fW
     if tuple(x.shape) != (BN, prob.D + prob.C, prob.fH, prob.fW):
         raise ValueError(f"depthnet_out has shape {tuple(x.shape)}, expected {(BN, prob.D + prob.C, prob.fH, prob.fW)}")
-    pr = torch.empty((BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device)
+    both = torch.empty((2, BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device)
+    pr = both[0]                                   # [BN, D, fH, fW]; both[1] holds the column-major copy [BN, fW, D, fH]
     ct = torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device)
-    check(lib().lss_lift_prepare(C.byref(prob.c), _ptr(x), _ptr(pr), _ptr(ct), _stream()), "lss_lift_prepare")
+    check(lib().lss_lift_prepare(C.byref(prob.c), _ptr(x), _ptr(pr), _ptr(ct), _ptr(both[1]), _stream()), "lss_lift_prepare")
     return pr, ct
+
+
+def _prob_col(pr):
+    """The column-major copy that lift_prepare wrote right behind `pr` (None for foreign tensors)."""
+    base = pr._base if pr._base is not None else None
+    if base is not None and base.dim() == 5 and base.shape[0] == 2 and base.data_ptr() == pr.data_ptr() and pr.is_contiguous():
+        return base[1]
+    return None
 
 
 def _empty_bev(prob: Problem, device, channels_last: bool):
@@ -263,7 +272,7 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
     if voxel_sums is None and mode == "sorted" and variant != "warp" and prob.C in (32, 64, 128):
         voxel_sums = torch.empty((plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=pr.device)
     check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct),
-                              _ptr(voxel_sums), _ptr(bev),
+                              _ptr(_prob_col(pr)), _ptr(voxel_sums), _ptr(bev),
                               SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW,
                               VARIANTS[variant], 1 if out is not None else 0, _stream()), "lss_splat_fwd")
     return bev

@@ -88,14 +88,14 @@ def test_bad_arguments_return_status_codes(L):
     p = _problem(cfg)
     null = C.c_void_p(0)
     assert L.lss_geometry(C.byref(p.c), null, null, null, null, null, null, null) == -1
-    assert L.lss_lift_prepare(C.byref(p.c), null, null, null, null) == -1
+    assert L.lss_lift_prepare(C.byref(p.c), null, null, null, null, null) == -1
     bad = _lib.LssProblem()
     lay = _lib.LssPlanLayout()
     assert L.lss_plan_layout_init(C.byref(bad), 0, C.byref(lay)) == -1       # zero dims
     big = _problem(cfg)
     big.c.D = 1 << 20
     assert L.lss_plan_layout_init(C.byref(big.c), 0, C.byref(lay)) == -3     # > 2^20 points per sample
-    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, null, 0, 0, 0, 0, null) == -5
+    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, null, null, 0, 0, 0, 0, null) == -5
     assert L.lss_quickcumsum_scratch_elems(5000) >= 5000 + 5
 
 
