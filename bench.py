@@ -240,15 +240,25 @@ class BufferSet:
         self.plan = ops.Plan(prob, dev, tile_cols)
         self.rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=dev)
         self.vsum = torch.empty((self.plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=dev)
+        self.lift_out = (torch.empty((2, prob.B * prob.N, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=dev),
+                         torch.empty((prob.B * prob.N, prob.fH * prob.fW, prob.C), dtype=torch.float32, device=dev))
+        self.side = torch.cuda.Stream(device=dev)      # lift operands are independent of the plan: second stream
         self.out = {}
 
 
 STAGES = ("calib", "plan_build", "lift_prepare", "splat_fwd", "splat_bwd")
+NO_OVERLAP = bool(os.environ.get("LSS_BENCH_NO_OVERLAP"))
 
 
 def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAGES)):
     """The whole path for one batch; every launch goes through the C ABI on the current stream.
     `upto` < 5 runs only the first stages (used to attribute in-step time to each stage)."""
+    cur = torch.cuda.current_stream()
+    overlap = upto >= 3 and not NO_OVERLAP
+    if overlap:                                        # lift_prepare next to the plan build (fork / join)
+        bs.side.wait_stream(cur)
+        with torch.cuda.stream(bs.side):
+            pr, ct = ops.lift_prepare(prob, bs.dn, out=bs.lift_out)
     if inverse == "device":
         M1, M2 = ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots)
     else:
@@ -260,7 +270,10 @@ def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAG
     ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=bs.plan)
     if upto < 3:
         return
-    pr, ct = ops.lift_prepare(prob, bs.dn)
+    if overlap:
+        cur.wait_stream(bs.side)
+    else:
+        pr, ct = ops.lift_prepare(prob, bs.dn, out=bs.lift_out)
     bs.out.update({"pr": pr, "ct": ct})
     if upto < 4:
         return
@@ -317,6 +330,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-inverse", default="device", choices=["device", "reference"])
     ap.add_argument("--metric", default="pool", choices=["pool", "train"],
                     help="pool: BEV-pool Mpoints/s fwd+bwd (headline); train: LSS training samples/s")
     ap.add_argument("--splat", default="ours", choices=["ours", "aten"], help="--metric train: lift-splat implementation")
@@ -351,7 +365,7 @@ def main():
     dx, bx, nx = gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
     fH, fW = cfg.fHW
     prob = ops.Problem.from_grid(cfg.B, cfg.N, cfg.D, fH, fW, cfg.C, dx, bx, nx)
-    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, splat_mode=args.mode, inverse_mode="reference",
+    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, splat_mode=args.mode, inverse_mode=args.e2e_inverse,
                        bev_channels_last=channels_last, device=dev, tile_cols=args.tile_cols)
     frustum = ls.frustum
     sets = [BufferSet(cfg, prob, 100 * rank + i, dev, channels_last, args.tile_cols) for i in range(args.sets)]
@@ -410,11 +424,11 @@ def main():
 
     def e2e_step(i):
         h, bs = pinned[i % len(pinned)], sets[i % len(sets)]
-        x = h["depthnet_out"].to(dev, non_blocking=True).requires_grad_(True)
+        x = ls.upload(h["depthnet_out"]).requires_grad_(True)
         bev = ls(x, h["rots"], h["trans"], h["intrins"], h["post_rots"], h["post_trans"])
         bev.backward(bs.grad_bev)
-        h["grad_out"].copy_(x.grad, non_blocking=True)
-        h["probe"].copy_(bev.detach().reshape(-1)[:1024], non_blocking=True)
+        ls.download(x.grad, h["grad_out"])
+        ls.download(bev.detach().reshape(-1)[:1024], h["probe"])
 
     for i in range(args.warmup):
         e2e_step(i)
@@ -501,7 +515,8 @@ def main():
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": round(e2e_elapsed / e2e_steps * 1e3, 4),
-                    "api": "lss_carla_b200.api.LiftSplat.__call__ + autograd backward; host LAPACK inverses (reference mode)"},
+                    "api": f"lss_carla_b200.api.LiftSplat.__call__ + autograd backward + LiftSplat.download; inverse_mode={args.e2e_inverse}; "
+                           "stream-ordered pinned H2D/D2H copies inside the timed region"},
             "gpu_launches": LAUNCHES_PER_STEP[args.mode] * args.steps,
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -220,15 +220,19 @@ def reference_order(plan: Plan):
 # lift + splat
 # ------------------------------------------------------------------------------------------------
 
-def lift_prepare(prob: Problem, depthnet_out):
-    """softmax over depth + pixel-major context (models.py:49-61) -> (prob [BN,D,fH,fW], ctx_t [BN,HW,C])."""
+def lift_prepare(prob: Problem, depthnet_out, out=None):
+    """softmax over depth + pixel-major context (models.py:49-61) -> (prob [BN,D,fH,fW], ctx_t [BN,HW,C]).
+    `out`: optional preallocated (f32[2,BN,D,fH,fW], f32[BN,HW,C]) pair, e.g. when the call runs on a side stream."""
     x = _f32c(depthnet_out, "depthnet_out")
     BN, HW = prob.B * prob.N, prob.fH * prob.fW
     if tuple(x.shape) != (BN, prob.D + prob.C, prob.fH, prob.fW):
         raise ValueError(f"depthnet_out has shape {tuple(x.shape)}, expected {(BN, prob.D + prob.C, prob.fH, prob.fW)}")
-    both = torch.empty((2, BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device)
+    if out is not None:
+        both, ct = out
+    else:
+        both = torch.empty((2, BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device)
+        ct = torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device)
     pr = both[0]                                   # [BN, D, fH, fW]; both[1] holds the column-major copy [BN, fW, D, fH]
-    ct = torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device)
     check(lib().lss_lift_prepare(C.byref(prob.c), _ptr(x), _ptr(pr), _ptr(ct), _ptr(both[1]), _stream()), "lss_lift_prepare")
     return pr, ct
 
