@@ -469,6 +469,11 @@ def main():
     stages["lift_prepare"] = time_kernel(lambda bs: ops.lift_prepare(prob, bs.dn), sets, kiters, stream)
     stages["splat_fwd"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last, voxel_sums=bs.vsum),
                                       sets, kiters, stream)
+    if args.mode == "sorted":      # the two kernels of the deterministic forward, each alone
+        stages["k_fwd_gather"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last,
+                                                                      variant="group_gather", voxel_sums=bs.vsum, out=bs.out["bev"]), sets, kiters, stream)
+        stages["k_fwd_store"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last,
+                                                                     variant="group_store", voxel_sums=bs.vsum, out=bs.out["bev"]), sets, kiters, stream)
     stages["splat_bwd"] = time_kernel(lambda bs: ops.splat_bwd(prob, bs.plan, bs.grad_bev, bs.out["pr"], bs.out["ct"], bs.rows),
                                       sets, kiters, stream)
 
@@ -480,19 +485,26 @@ def main():
     fwd_bytes = IN + G                                    # forward (fused)
     bwd_bytes = 4 * cfg.C * v_hit + 2 * IN                # backward (fused)
     peak, peak_src = load_peaks()
-    achieved = fwd_bytes / stages["splat_fwd"] / 1e9
     step_s = elapsed / args.steps
-    fwd_name = {"sorted": "lss_splat_fwd = k_fwd_gather + k_fwd_store (deterministic forward, both launches)",
-                "atomic": "k_splat_fwd_tile (shared-memory atomics)", "red": "memset + k_splat_fwd_red"}[args.mode]
+    if args.mode == "sorted":
+        # dominant HBM-bound kernel: k_fwd_store writes every BEV element once (G) and reads the compact voxel rows
+        kname, kbytes, ksec = "k_fwd_store", G + 4 * cfg.C * v_hit, stages["k_fwd_store"]
+    else:
+        kname = {"atomic": "k_splat_fwd_tile (shared-memory atomics)", "red": "memset + k_splat_fwd_red"}[args.mode]
+        kbytes, ksec = fwd_bytes, stages["splat_fwd"]
+    achieved = kbytes / ksec / 1e9
     traffic = None
-    try:      # dram__bytes_read.sum + dram__bytes_write.sum of the same launches, from the ncu --set full capture
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel, from the ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f).get(f"{args.workload}_{args.mode}_{args.layout}")
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": fwd_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
-            "algorithmic_bytes_per_launch": fwd_bytes, "kernel_us": round(stages["splat_fwd"] * 1e6, 2),
+            "algorithmic_bytes_per_launch": kbytes, "kernel_us": round(ksec * 1e6, 2),
+            "kernel_share_of_step": round(ksec / step_s, 3),
+            "forward_op": {"what": "lss_splat_fwd (all its launches), IN + G bytes", "bytes": fwd_bytes,
+                           "us": round(stages["splat_fwd"] * 1e6, 2), "frac": round(fwd_bytes / stages["splat_fwd"] / 1e9 / peak, 4)},
             "step_algorithmic_bytes": fwd_bytes + bwd_bytes,
             "step_frac": round((fwd_bytes + bwd_bytes) / step_s / 1e9 / peak, 4),
             "stage_us_in_step": {k: round(v * 1e6, 2) for k, v in instep.items()},

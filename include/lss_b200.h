@@ -102,8 +102,8 @@ typedef struct lss_plan_layout {
     size_t off_key_count;   /* int32 [B*N*fW]     sorted plans: records in every bucket              */
     size_t off_mixed_recs;  /* int32 [n_rows_cap,4] sorted plans: records of the voxels that hold    */
                             /*                    points of several camera columns (not bucketed)    */
-    size_t off_prow;        /* int32 [n_points]   sorted plans: compact row of the point's voxel, -1 */
-                            /*                    for dropped points (backward gather)               */
+    size_t off_prow;        /* int32 [B,N,fW,D,fH] sorted plans: compact row of the point's voxel, -1 */
+                            /*                    for dropped points, camera-column major (backward) */
     size_t off_counters;    /* int32 [64]         [0] = non-empty voxels of the batch (rows in use), */
                             /*                    [1] = records in mixed_recs                        */
     int64_t n_rows_cap;     /* min(n_points, B*nx*ny*nz): capacity of the voxel_sums workspace       */
@@ -180,9 +180,11 @@ int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *pro
 /* Kernel variants of the tile-owner forward in SORTED mode (bit-identical results). */
 enum { LSS_VARIANT_AUTO = 0,   /* GROUP when the shape and workspace allow it, else WARP                          */
        LSS_VARIANT_WARP = 1,   /* ONE tile-owner kernel: a warp per 32-entry chunk, lane = channel; any C         */
-       LSS_VARIANT_GROUP = 2   /* TWO kernels: register-only gather by 8-lane groups (lane = C/8 contiguous        */
-                               /* channels) into compact per-voxel rows, then a streaming tile-owner store;       */
-                               /* C in {32,64,128}, fused level only, needs the `voxel_sums` workspace            */ };
+       LSS_VARIANT_GROUP = 2,  /* TWO kernels: gather by 8-lane groups (lane = C/8 channels, operands staged per   */
+                               /* camera column) into compact per-voxel rows, then a streaming tile-owner store;  */
+                               /* C in {32,64,128}, fused level only, needs the `voxel_sums` workspace            */
+       LSS_VARIANT_GROUP_GATHER = 3, /* measurement aid: only the gather kernel of GROUP (fills `voxel_sums`)   */
+       LSS_VARIANT_GROUP_STORE = 4   /* measurement aid: only the store kernel of GROUP (reads `voxel_sums`)    */ };
 
 /* Zero a BEV tensor (what `torch.zeros` does at models.py:240).  Only the RED_GLOBAL mode needs a zeroed
  * grid; callers may issue the clear early / on another stream and pass precleared=1 to lss_splat_fwd. */
@@ -205,9 +207,10 @@ int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
  * `grad_rows` is a caller workspace f32[B*nz*nx*ny, C]: the gradient rows of the non-empty voxels are
  * gathered into it, channel-contiguous (compact row order for sorted plans, voxel order otherwise); it may
  * be null only for channels_last gradients.  `plan_sorted` != 0 promises that the plan was built with
- * sorted=1, which enables the compact-row kernels (C in {32,64,128}). */
+ * sorted=1, which (together with `prob_col` from lss_lift_prepare) enables the compact-row kernels
+ * (C in {32,64,128}); `prob_col` may be null. */
 int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
-                  const float *grad_bev, int layout, const float *prob, const float *ctx_t,
+                  const float *grad_bev, int layout, const float *prob, const float *ctx_t, const float *prob_col,
                   float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream);
 
 /* Debug hook (profiling aid, not part of the reference surface): when non-null, the GROUP kernels stamp

@@ -45,7 +45,7 @@ class LssLimits(C.Structure):
 LAYOUT_NCHW, LAYOUT_CHANNELS_LAST = 0, 1
 SPLAT_SORTED, SPLAT_SMEM_ATOMIC, SPLAT_RED_GLOBAL = 0, 1, 2
 SPLAT_MODES = {"sorted": SPLAT_SORTED, "atomic": SPLAT_SMEM_ATOMIC, "red": SPLAT_RED_GLOBAL}
-VARIANTS = {"auto": 0, "warp": 1, "group": 2}
+VARIANTS = {"auto": 0, "warp": 1, "group": 2, "group_gather": 3, "group_store": 4}
 
 _P = C.c_void_p
 _PP = C.POINTER(LssProblem)
@@ -67,7 +67,7 @@ SIGNATURES = {
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
+    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P]),
     "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P]),
     "lss_quickcumsum_scratch_elems": (C.c_size_t, [C.c_int64]),

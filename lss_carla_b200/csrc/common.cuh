@@ -79,6 +79,17 @@ struct Tiling {
 
 __host__ __device__ __forceinline__ int lss_kc_for(int C) { return (C + 31) / 32; }
 
+// Camera-column-major position of the point-in-sample index pidx = ((n*D + d)*fH + h)*fW + w:
+// ((n*fW + w)*D + d)*fH + h.  All points of one camera column (n, w) are contiguous, depth-major.
+__device__ __forceinline__ unsigned lss_column_major(const Dims &d, unsigned pidx) {
+    const unsigned cam = lss_div20(pidx, d.mDHW);
+    const unsigned r = pidx - cam * d.DHW;
+    const unsigned dd = lss_div20(r, d.mHW);
+    const unsigned hw = r - dd * d.HW;
+    const unsigned h = hw / (unsigned)d.fW, w = hw - h * d.fW;
+    return ((cam * d.fW + w) * d.D + dd) * d.fH + h;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LSS_FULL_MASK, v, o);

@@ -129,7 +129,8 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
         long long ii[3];
         v = voxel_of_point(d, b, g, ii);
         if (vox) vox[p] = v;
-        if (COUNT && v < 0) prow[p] = -1;         // kept points get their compact row from k_plan_sort
+        if (COUNT && v < 0)                      // kept points get their compact row from k_plan_sort
+            prow[(size_t)b * d.P + lss_column_major(d, (unsigned)(p - b * d.P))] = -1;
         if (idx) { idx[(size_t)p * 3 + 0] = ii[0]; idx[(size_t)p * 3 + 1] = ii[1]; idx[(size_t)p * 3 + 2] = ii[2]; }
         if (kept) kept[p] = v >= 0;
         if (rank)   // models.py:226-229, int64
@@ -151,9 +152,11 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
     __shared__ int s_last;
     __shared__ int s_warp[8];
     __shared__ int s_carry;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(sync, 1) == (int)gridDim.x - 1);
+    __syncthreads();                               // the CTA's histogram atomics are ordered before thread 0's fence
+    if (threadIdx.x == 0) {
+        __threadfence();                           // (cumulative): release them device-wide, then take a ticket
+        s_last = (atomicAdd(sync, 1) == (int)gridDim.x - 1);
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -357,7 +360,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
             while (j < n && (g[j] >> LSS_PIDX_BITS) == col) ++j;
             segs[s + k] = (col << LSS_PIDX_BITS) | (uint32_t)i;
             emit_voxel_record(d, b, g[i], 2, s + i, j - i, row0 + k, seg_recs, key_count, mixed_recs, counters);
-            for (int q = i; q < j; ++q) prow[(size_t)b * d.P + (g[q] & LSS_PIDX_MASK)] = row0 + k;
+            for (int q = i; q < j; ++q) prow[(size_t)b * d.P + lss_column_major(d, g[q] & LSS_PIDX_MASK)] = row0 + k;
         });
         return;
     }
@@ -410,7 +413,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
         const uint32_t e = s_grp[i];
-        prow[(size_t)b * d.P + (e & LSS_PIDX_MASK)] = row0 + (mixed[e >> LSS_PIDX_BITS] >> 2);
+        prow[(size_t)b * d.P + lss_column_major(d, e & LSS_PIDX_MASK)] = row0 + (mixed[e >> LSS_PIDX_BITS] >> 2);
     }
 }
 

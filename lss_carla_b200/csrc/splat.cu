@@ -691,7 +691,7 @@ k_bwd_gather(Dims d, const int32_t *__restrict__ vox, const float *__restrict__ 
 // tile: 8 independent 4-byte loads per lane (neighbouring columns share 32-byte sectors), one full
 // 32-byte sector written per lane.  channels_last: plain 16-byte copies.
 template <bool CL>
-__global__ void __launch_bounds__(SPLAT_THREADS)
+__global__ void __launch_bounds__(SPLAT_THREADS, 4)
 k_bwd_rows_compact(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                    const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs,
                    const float *__restrict__ grad_bev, float *__restrict__ grows) {
@@ -742,13 +742,13 @@ k_bwd_rows_compact(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, co
 // the CTA's points are staged in shared memory first (one round of coalesced loads); the depth loop then
 // reads shared memory, keeps LF gradient rows in flight and needs no control flow (dropped points read
 // row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
-template <int CPL, int DZ>
-__global__ void __launch_bounds__(SPLAT_THREADS * DZ)
-k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *__restrict__ prob,
+template <int CPL>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_bwd_gather_px(Dims d, int WC, int stage_rows, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
                 const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
     extern __shared__ __align__(16) float smem[];
     constexpr int LF = CPL <= 8 ? 4 : 2;
-    constexpr int NT = SPLAT_THREADS * DZ;                // DZ groups share a pixel: each walks 1/DZ of the depths
+    constexpr int NT = SPLAT_THREADS;
     const int bn = blockIdx.y, w0 = blockIdx.x * WC;
     const int D = d.D, C = d.C, fH = d.fH, DC = D + C;
     const int npx = fH * WC;                              // pixels of the CTA (<= 32), group g <-> pixel (h, wl)
@@ -756,17 +756,20 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
     int *s_row = reinterpret_cast<int *>(smem + 32 * D);  // [32][D] compact row or -1
     float *s_gp = smem + 64 * D;                          // [32][D] <grad row, ctx>
     float *s_out = smem + 96 * D;                         // [D + C][npx] staged outputs
-    float *s_part = s_out + DC * npx;                     // [DZ - 1][32][C] partial context gradients
-    for (int i = threadIdx.x; i < npx * D; i += NT) {
-        const int dd = i / npx, px = i - dd * npx;        // px = h * WC + wl: consecutive threads walk a pixel row
-        const int h = px / WC, wl = px - h * WC;
-        const bool ok = w0 + wl < d.fW;
-        const size_t p = ((size_t)(bn * D + dd) * fH + h) * d.fW + w0 + wl;
-        s_p[px * D + dd] = ok ? __ldg(prob + p) : 0.f;
-        s_row[px * D + dd] = ok ? __ldg(prow + p) : -1;
+    float *s_g = smem + ((96 * D + DC * npx + 3) & ~3);   // [WC][D][C] rows of the columns' primary voxels (16-byte aligned)
+    {   // the CTA's columns are one contiguous block [wl][D][fH] in the column-major arrays
+        const int ncol = min(WC, d.fW - w0), per = D * fH;
+        const size_t base = ((size_t)bn * d.fW + w0) * per;
+        for (int i = threadIdx.x; i < WC * per; i += NT) {
+            const int wl = i / per, r = i - wl * per;
+            const int dd = r / fH, h = r - dd * fH;
+            const bool ok = wl < ncol;
+            s_p[(h * WC + wl) * D + dd] = ok ? __ldg(prob_col + base + i) : 0.f;
+            s_row[(h * WC + wl) * D + dd] = ok ? __ldg(prow + base + i) : -1;
+        }
     }
     const int lane = threadIdx.x & 31, gl = lane & 7;
-    const int g = (threadIdx.x >> 3) & 31, z = threadIdx.x >> 8;
+    const int g = threadIdx.x >> 3;
     const int h = g / WC, wl = g - h * WC;
     const bool active = g < npx && w0 + wl < d.fW;
     const size_t my_ctx = ((size_t)bn * d.HW + (active ? h * d.fW + w0 + wl : 0)) * C;
@@ -782,50 +785,104 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
         for (int a = 0; a < CPL; ++a) dctx[a] = 0.f;
     }
     __syncthreads();
-    const float *my_p = s_p + (g < npx ? g : 0) * D;
-    const int *my_row = s_row + (g < npx ? g : 0) * D;
+    const int gg = g < npx ? g : 0;                       // idle groups mirror group 0 (shuffles stay warp-uniform)
+    const float *my_p = s_p + gg * D;
+    const int *my_row = s_row + gg * D;
     const float4 *rows4 = reinterpret_cast<const float4 *>(grows) + gl;
-    const float4 *safe4 = reinterpret_cast<const float4 *>(ctx_t + my_ctx) + gl;   // finite stand-in for "no row"
     const int c4 = C >> 2;
-    const int dz = ((D + DZ - 1) / DZ + LF - 1) / LF * LF;                       // depths per group, multiple of LF
-    const int d_end = min(D, (z + 1) * dz);
-    for (int d0 = z * dz; d0 < d_end; d0 += LF) {         // warp-uniform: the 4 groups of a warp share z
-        float x[LF][CPL];
-        float pj[LF];
-        bool on[LF];
-#pragma unroll
-        for (int u = 0; u < LF; ++u) {
-            const int dd = min(d0 + u, D - 1);
-            const int rj = (active && d0 + u < d_end) ? my_row[dd] : -1;
-            on[u] = rj >= 0;
-            pj[u] = on[u] ? my_p[dd] : 0.f;               // dropped point / padding: weight 0, a finite row
-            const float4 *rp = on[u] ? rows4 + (size_t)rj * c4 : safe4;
-#pragma unroll
-            for (int q = 0; q < CPL / 4; ++q) {
-                const float4 v = __ldg(rp + 8 * q);
-                x[u][4 * q] = v.x; x[u][4 * q + 1] = v.y; x[u][4 * q + 2] = v.z; x[u][4 * q + 3] = v.w;
-            }
+    if (stage_rows) {
+        // Almost always the fH pixels of a column hit the same voxel at a given depth.  Fetch that "primary" row
+        // (the one of pixel h = 0) ONCE per (column, depth), all of them in flight together, zeros where there is
+        // none; the depth loop then reads shared memory only and has no control flow.
+        for (int i = threadIdx.x; i < WC * D * c4; i += NT) {
+            const int cd = i / c4, q = i - cd * c4;       // cd = wl * D + dd; pixel (h = 0, wl) has index wl
+            const int r = s_row[cd];
+            reinterpret_cast<float4 *>(s_g)[i] = r >= 0 ? __ldg(reinterpret_cast<const float4 *>(grows) + (size_t)r * c4 + q)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll
-        for (int u = 0; u < LF; ++u) {
+        __syncthreads();
+        const int *col_row = s_row + (g < npx ? wl : 0) * D;
+        const float4 *my_sg = reinterpret_cast<const float4 *>(s_g + (size_t)(g < npx ? wl : 0) * D * C) + gl;
+        unsigned exc = 0;                                 // does this pixel hit other voxels than the primary ones?
+#pragma unroll 4
+        for (int dd = 0; dd < D; ++dd) {
+            const int rj = my_row[dd];
+            const bool same = rj == col_row[dd];
+            exc |= (active && rj >= 0 && !same) ? 1u : 0u;
+            const float pj = (active && same) ? my_p[dd] : 0.f;       // dropped: the staged row is zero anyway
             float dot = 0.f;
 #pragma unroll
-            for (int a = 0; a < CPL; ++a) { dot = fmaf(x[u][a], ctx[a], dot); dctx[a] = fmaf(pj[u], x[u][a], dctx[a]); }
+            for (int q = 0; q < CPL / 4; ++q) {
+                const float4 v = my_sg[dd * c4 + 8 * q];
+                dot = fmaf(v.x, ctx[4 * q], dot); dot = fmaf(v.y, ctx[4 * q + 1], dot);
+                dot = fmaf(v.z, ctx[4 * q + 2], dot); dot = fmaf(v.w, ctx[4 * q + 3], dot);
+                dctx[4 * q] = fmaf(pj, v.x, dctx[4 * q]); dctx[4 * q + 1] = fmaf(pj, v.y, dctx[4 * q + 1]);
+                dctx[4 * q + 2] = fmaf(pj, v.z, dctx[4 * q + 2]); dctx[4 * q + 3] = fmaf(pj, v.w, dctx[4 * q + 3]);
+            }
             dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 1);
             dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 2);
             dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 4);
-            if (gl == 0 && g < npx && d0 + u < d_end) s_gp[g * D + d0 + u] = on[u] ? dot : 0.f;
+            if (gl == 0 && g < npx) s_gp[g * D + dd] = (active && same) ? dot : 0.f;
+        }
+        // the exceptions (voxels shared with another column / camera at the frustum borders): rows from global memory
+        if (__any_sync(LSS_FULL_MASK, exc != 0u)) {
+            for (int dd = 0; dd < D; ++dd) {
+                const int rj = my_row[dd];
+                const bool mine = active && rj >= 0 && rj != col_row[dd];
+                if (!__any_sync(LSS_FULL_MASK, mine)) continue;
+                const float pj = mine ? my_p[dd] : 0.f;
+                float dot = 0.f;
+                if (mine) {
+#pragma unroll
+                    for (int q = 0; q < CPL / 4; ++q) {
+                        const float4 v = __ldg(rows4 + (size_t)rj * c4 + 8 * q);
+                        dot = fmaf(v.x, ctx[4 * q], dot); dot = fmaf(v.y, ctx[4 * q + 1], dot);
+                        dot = fmaf(v.z, ctx[4 * q + 2], dot); dot = fmaf(v.w, ctx[4 * q + 3], dot);
+                        dctx[4 * q] = fmaf(pj, v.x, dctx[4 * q]); dctx[4 * q + 1] = fmaf(pj, v.y, dctx[4 * q + 1]);
+                        dctx[4 * q + 2] = fmaf(pj, v.z, dctx[4 * q + 2]); dctx[4 * q + 3] = fmaf(pj, v.w, dctx[4 * q + 3]);
+                    }
+                }
+                dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 1);
+                dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 2);
+                dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 4);
+                if (mine && gl == 0) s_gp[g * D + dd] = dot;
+            }
+        }
+    } else {
+        // no room to stage the rows: LF rows in flight from global memory, dropped points read a finite stand-in
+        const float4 *safe4 = reinterpret_cast<const float4 *>(ctx_t + my_ctx) + gl;
+        for (int d0 = 0; d0 < D; d0 += LF) {
+            float x[LF][CPL];
+            float pj[LF];
+            bool on[LF];
+#pragma unroll
+            for (int u = 0; u < LF; ++u) {
+                const int dd = min(d0 + u, D - 1);
+                const int rj = (active && d0 + u < D) ? my_row[dd] : -1;
+                on[u] = rj >= 0;
+                pj[u] = on[u] ? my_p[dd] : 0.f;
+                const float4 *rp = on[u] ? rows4 + (size_t)rj * c4 : safe4;
+#pragma unroll
+                for (int q = 0; q < CPL / 4; ++q) {
+                    const float4 v = __ldg(rp + 8 * q);
+                    x[u][4 * q] = v.x; x[u][4 * q + 1] = v.y; x[u][4 * q + 2] = v.z; x[u][4 * q + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < LF; ++u) {
+                float dot = 0.f;
+#pragma unroll
+                for (int a = 0; a < CPL; ++a) { dot = fmaf(x[u][a], ctx[a], dot); dctx[a] = fmaf(pj[u], x[u][a], dctx[a]); }
+                dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 1);
+                dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 2);
+                dot += __shfl_xor_sync(LSS_FULL_MASK, dot, 4);
+                if (gl == 0 && g < npx && d0 + u < D) s_gp[g * D + d0 + u] = on[u] ? dot : 0.f;
+            }
         }
     }
-    if (DZ > 1 && z > 0) {                                // partial context gradients of the upper depth ranges
-        float4 *pp = reinterpret_cast<float4 *>(s_part + ((size_t)(z - 1) * 32 + g) * C) + gl;
-#pragma unroll
-        for (int q = 0; q < CPL / 4; ++q) pp[8 * q] = make_float4(dctx[4 * q], dctx[4 * q + 1], dctx[4 * q + 2], dctx[4 * q + 3]);
-    }
-    __syncthreads();
+    __syncwarp();
     // softmax backward (models.py:50): d_logit_d = p_d * (gp_d - sum_d' p_d' gp_d'); dropped points take part
-    if (z == 0) {
-        const int gg = g < npx ? g : 0;                   // idle groups mirror group 0 (shuffles stay warp-uniform)
+    {
         const float *pp = s_p + gg * D, *gp = s_gp + gg * D;
         float sd = 0.f;
         for (int dd = gl; dd < D; dd += 8) sd = fmaf(pp[dd], gp[dd], sd);
@@ -834,15 +891,6 @@ k_bwd_gather_px(Dims d, int WC, const int32_t *__restrict__ prow, const float *_
         sd += __shfl_xor_sync(LSS_FULL_MASK, sd, 4);
         if (g < npx) {
             for (int dd = gl; dd < D; dd += 8) s_out[dd * npx + g] = pp[dd] * (gp[dd] - sd);
-#pragma unroll
-            for (int zz = 1; zz < DZ; ++zz) {             // fixed order: deterministic
-                const float4 *qp = reinterpret_cast<const float4 *>(s_part + ((size_t)(zz - 1) * 32 + g) * C) + gl;
-#pragma unroll
-                for (int q = 0; q < CPL / 4; ++q) {
-                    const float4 v = qp[8 * q];
-                    dctx[4 * q] += v.x; dctx[4 * q + 1] += v.y; dctx[4 * q + 2] += v.z; dctx[4 * q + 3] += v.w;
-                }
-            }
 #pragma unroll
             for (int q = 0; q < CPL / 4; ++q)
 #pragma unroll
@@ -950,7 +998,9 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
 // GROUP variant of the deterministic forward: gather into compact rows, then stream the tiles out
 static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, const PlanPtrs &pp, long long L_rows_cap,
                          const float *prob, const float *prob_col, const float *ctx_t, float *vsum, float *bev,
-                         cudaStream_t s) {
+                         int variant, cudaStream_t s) {
+    if (variant == LSS_VARIANT_GROUP_STORE) goto store;
+    {
     const int n_keys = d.B * d.N * d.fW;                 // one CTA per camera column ...
     const int grid = n_keys + 2 * num_sms();             // ... plus the CTAs that drain the mixed-voxel queue
     const size_t gsm = (size_t)(d.fH * d.C + d.D * d.fH) * 4;
@@ -960,7 +1010,10 @@ static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, co
     else if (d.C == 64) k_fwd_gather<8><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else k_fwd_gather<16><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
 #undef GATHER_ARGS
+    }
     LSS_CHECK_LAUNCH();
+    if (variant == LSS_VARIANT_GROUP_GATHER) return LSS_OK;
+store:
     if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, s);
     return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, s);
 }
@@ -992,8 +1045,8 @@ static int dispatch_fwd(bool atomic, bool cl, int variant, const Dims &d, const 
     const bool group_ok = !DENSE && !atomic && vsum != nullptr && rows16 && lss_aligned(vsum, 16) &&
                           (d.C == 32 || d.C == 64 || d.C == 128) && (long long)d.N * d.HW * d.C < (1ll << 31) &&
                           (size_t)(d.fH * d.C + d.D * d.fH) * 4 <= 48 * 1024;
-    if (variant == LSS_VARIANT_GROUP && !group_ok) return LSS_ERR_UNSUPPORTED;
-    if (group_ok && variant != LSS_VARIANT_WARP) return run_fwd_group(cl, vec4, d, tl, pp, rows_cap, src.prob, src.prob_col, src.base, vsum, bev, s);
+    if (variant >= LSS_VARIANT_GROUP && !group_ok) return LSS_ERR_UNSUPPORTED;
+    if (group_ok && variant != LSS_VARIANT_WARP) return run_fwd_group(cl, vec4, d, tl, pp, rows_cap, src.prob, src.prob_col, src.base, vsum, bev, variant, s);
     const int32_t *ts = pp.tile_start;
     const uint32_t *en = pp.entries;
     if (!DENSE && rows16) {
@@ -1152,31 +1205,26 @@ static bool bwd_compact_ok(const Dims &d, const float *ctx_t, const float *grows
 
 // compact-row backward (sorted plans): gradient rows of the non-empty voxels, then the pixel-owner gather
 static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanPtrs &pp, const int32_t *prow,
-                           const float *grad_bev, const float *prob, const float *ctx_t, float *grows, float *grad_dn,
+                           const float *grad_bev, const float *prob_col, const float *ctx_t, float *grows, float *grad_dn,
                            cudaStream_t s) {
     if (cl) k_bwd_rows_compact<true><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
     else k_bwd_rows_compact<false><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
     LSS_CHECK_LAUNCH();
     const int WC = max(1, 32 / d.fH);
     const dim3 grid((d.fW + WC - 1) / WC, d.B * d.N);
-    // split the depth range over DZ groups per pixel while the grid alone cannot fill the SMs
-    const long long warps = (long long)grid.x * grid.y * SPLAT_WARPS;
-    static int dz_override = getenv("LSS_BWD_DZ") ? atoi(getenv("LSS_BWD_DZ")) : 0;     // tuning knob
-    int DZ = 1;                                           // measured at cfg2: 1 / 2 / 4 within noise (44.6 / 48.3 / 43.3 us)
-    (void)warps;
-    if (dz_override == 1 || dz_override == 2 || dz_override == 4) DZ = dz_override;
-    const size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC + (size_t)(DZ - 1) * 32 * d.C) * 4;
+    size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GPX1(CPL, Z)                                                                                             \
+    const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16;  // staged gradient rows (+ alignment), if they fit next to a second CTA
+    const int stage_rows = smem + rows_smem <= 100 * 1024;
+    if (stage_rows) smem += rows_smem;
+#define GPX(CPL)                                                                                                 \
     do {                                                                                                         \
         static bool configured = false;                                                                          \
-        int st = opt_in_smem(k_bwd_gather_px<CPL, Z>, smem, configured);                                         \
+        int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
         if (st != LSS_OK) return st;                                                                             \
-        k_bwd_gather_px<CPL, Z><<<grid, SPLAT_THREADS * Z, smem, s>>>(d, WC, prow, prob, ctx_t, grows, grad_dn); \
+        k_bwd_gather_px<CPL><<<grid, SPLAT_THREADS, smem, s>>>(d, WC, stage_rows, prow, prob_col, ctx_t, grows, grad_dn); \
     } while (0)
-#define GPX(CPL) do { if (DZ == 4) GPX1(CPL, 4); else if (DZ == 2) GPX1(CPL, 2); else GPX1(CPL, 1); } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
-#undef GPX1
 #undef GPX
     LSS_CHECK_LAUNCH();
     return LSS_OK;
@@ -1184,7 +1232,7 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
 
 extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                              const float *grad_bev, int layout, const float *prob, const float *ctx_t,
-                             float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream) {
+                             const float *prob_col, float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
@@ -1197,8 +1245,8 @@ extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, con
     const PlanPtrs pp = plan_ptrs(L, workspace);
     cudaStream_t s = (cudaStream_t)stream;
     const bool cl = layout == LSS_LAYOUT_CHANNELS_LAST;
-    if (plan_sorted && grad_rows != nullptr && bwd_compact_ok(d, ctx_t, grad_rows))
-        return run_bwd_compact(cl, d, tl, pp, (const int32_t *)((const char *)workspace + L->off_prow), grad_bev, prob,
+    if (plan_sorted && prob_col != nullptr && grad_rows != nullptr && bwd_compact_ok(d, ctx_t, grad_rows))
+        return run_bwd_compact(cl, d, tl, pp, (const int32_t *)((const char *)workspace + L->off_prow), grad_bev, prob_col,
                                ctx_t, grad_rows, grad_depthnet, s);
     const float *rows = grad_bev;
     if (!cl) {

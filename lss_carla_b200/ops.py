@@ -282,13 +282,15 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
     return bev
 
 
-def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None):
+def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_col=None):
     g, layout = _bev_layout(_f32c_keep(grad_bev))
     if grad_rows is None and (layout == LAYOUT_NCHW or plan.sorted):
         grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
     out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
+    if prob_col is None:
+        prob_col = _prob_col(pr)
     check(lib().lss_splat_bwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), layout, _ptr(pr), _ptr(ct),
-                              _ptr(grad_rows), _ptr(out), 1 if plan.sorted else 0, _stream()), "lss_splat_bwd")
+                              _ptr(prob_col), _ptr(grad_rows), _ptr(out), 1 if plan.sorted else 0, _stream()), "lss_splat_bwd")
     return out
 
 
@@ -306,14 +308,14 @@ class _LiftSplatFn(torch.autograd.Function):
         pr, ct = lift_prepare(prob, depthnet_out)
         bev = splat_fwd(prob, plan, pr, ct, mode, channels_last)
         ctx.prob, ctx.plan = prob, plan
-        ctx.save_for_backward(pr, ct)
+        ctx.save_for_backward(pr, ct, _prob_col(pr))
         plan.busy = bool(ctx.needs_input_grad[0])
         return bev
 
     @staticmethod
     def backward(ctx, grad_bev):
-        pr, ct = ctx.saved_tensors
-        out = splat_bwd(ctx.prob, ctx.plan, grad_bev, pr, ct)
+        pr, ct, pc = ctx.saved_tensors
+        out = splat_bwd(ctx.prob, ctx.plan, grad_bev, pr, ct, prob_col=pc)
         ctx.plan.busy = False
         return out, None, None, None, None
 
