@@ -243,11 +243,16 @@ class BufferSet:
         self.lift_out = (torch.empty((2, prob.B * prob.N, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=dev),
                          torch.empty((prob.B * prob.N, prob.fH * prob.fW, prob.C), dtype=torch.float32, device=dev))
         self.side = torch.cuda.Stream(device=dev)      # lift operands are independent of the plan: second stream
+        self.bev_out = torch.empty(prob.bev_shape, dtype=torch.float32, device=dev, memory_format=fmt)
+        self.grad_out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=dev)
         self.out = {}
 
 
 STAGES = ("calib", "plan_build", "lift_prepare", "splat_fwd", "splat_bwd")
 NO_OVERLAP = bool(os.environ.get("LSS_BENCH_NO_OVERLAP"))
+# sample-range pipelining of gather/store on two streams: measured slower at cfg 2 (2 parts: 2404, 4 parts: 1868 vs 2876
+# Mpoints/s unsplit) -- every kernel already fills the GPU, smaller launches only add tails -- so it stays off
+PARTS = 1 if NO_OVERLAP else int(os.environ.get("LSS_BENCH_PARTS", "1"))
 
 
 def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAGES)):
@@ -277,11 +282,17 @@ def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAG
     bs.out.update({"pr": pr, "ct": ct})
     if upto < 4:
         return
-    bev = ops.splat_fwd(prob, bs.plan, pr, ct, mode, channels_last, voxel_sums=bs.vsum)
+    if PARTS > 1 and mode == "sorted":      # sample ranges on two streams: stores / row gathers overlap the gathers
+        bev = ops.splat_fwd_pipelined(prob, bs.plan, pr, ct, bs.side, PARTS, channels_last, voxel_sums=bs.vsum, out=bs.bev_out)
+    else:
+        bev = ops.splat_fwd(prob, bs.plan, pr, ct, mode, channels_last, voxel_sums=bs.vsum)
     bs.out["bev"] = bev
     if upto < 5:
         return
-    bs.out["grad"] = ops.splat_bwd(prob, bs.plan, bs.grad_bev, pr, ct, bs.rows)
+    if PARTS > 1 and mode == "sorted":
+        bs.out["grad"] = ops.splat_bwd_pipelined(prob, bs.plan, bs.grad_bev, pr, ct, bs.side, PARTS, bs.rows, out=bs.grad_out)
+    else:
+        bs.out["grad"] = ops.splat_bwd(prob, bs.plan, bs.grad_bev, pr, ct, bs.rows)
 
 
 # kernels of liblss_b200.so per step: calib, voxel+count, scatter, [sort], lift, forward (sorted: gather + store;

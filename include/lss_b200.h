@@ -195,11 +195,14 @@ int lss_bev_clear(const lss_problem *p, float *bev, void *stream);
  * Modes SORTED / SMEM_ATOMIC write every BEV element exactly once (zeros included): no memset, no global
  * atomics.  `precleared` != 0 promises that `bev` is already all-zero (only RED_GLOBAL looks at it).
  * `prob_col`: optional column-major weights from lss_lift_prepare (null: staged from `prob`).
+ * `b0, b1`: sample range [b0, b1) to process ((0, 0) = all).  Samples are independent, so a caller can issue the
+ * GROUP variant in parts on two streams and let the store of one part overlap the gather of the next (the part
+ * that starts at sample 0 also sums the voxels shared between camera columns of ALL samples: issue it first).
  * `voxel_sums`: caller workspace f32[min(n_points, B*nx*ny*nz), C] for the GROUP variant (may be null:
  * the WARP variant is used).  bev f32[B, nz*C, nx, ny] in `layout`. */
 int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                   const float *prob, const float *ctx_t, const float *prob_col, float *voxel_sums, float *bev,
-                  int mode, int layout, int variant, int precleared, void *stream);
+                  int mode, int layout, int variant, int precleared, int b0, int b1, void *stream);
 
 /* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
  * autograd backward of models.py:58-59,:199-200,:240-244):
@@ -208,10 +211,13 @@ int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
  * gathered into it, channel-contiguous (compact row order for sorted plans, voxel order otherwise); it may
  * be null only for channels_last gradients.  `plan_sorted` != 0 promises that the plan was built with
  * sorted=1, which (together with `prob_col` from lss_lift_prepare) enables the compact-row kernels
- * (C in {32,64,128}); `prob_col` may be null. */
+ * (C in {32,64,128}); `prob_col` may be null.
+ * `stage`: 0 = everything, 1 = only the gradient-row gather, 2 = only the pixel gather (compact-row kernels);
+ * `b0, b1`: sample range as in lss_splat_fwd -- the DRAM-bound row gather of one part overlaps the pixel gather of
+ * the previous one when they are issued on two streams. */
 int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                   const float *grad_bev, int layout, const float *prob, const float *ctx_t, const float *prob_col,
-                  float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream);
+                  float *grad_rows, float *grad_depthnet, int plan_sorted, int stage, int b0, int b1, void *stream);
 
 /* Debug hook (profiling aid, not part of the reference surface): when non-null, the GROUP kernels stamp
  * %globaltimer at their phase boundaries into `store_buf` (device, 8 x u64 per tile) and `gather_buf`

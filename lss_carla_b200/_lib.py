@@ -66,8 +66,8 @@ SIGNATURES = {
     "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
-    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P]),
     "lss_quickcumsum_scratch_elems": (C.c_size_t, [C.c_int64]),

@@ -302,7 +302,7 @@ k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, cons
 // of vsum (L2-resident, 4*C*V_hit bytes).
 template <int CPL>
 __global__ void __launch_bounds__(GATHER_THREADS, 1024 / GATHER_THREADS)
-k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const int4 *__restrict__ seg_recs,
+k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_count, const int4 *__restrict__ seg_recs,
              const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs,
              const uint32_t *__restrict__ entries, const float *__restrict__ prob, const float *__restrict__ prob_col,
              const float *__restrict__ ctx_t, float *__restrict__ vsum) {
@@ -310,7 +310,7 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
     const bool column = (int)blockIdx.x < n_keys;        // else: a CTA of the mixed-voxel queue (group per voxel, all
-    const int key = column ? blockIdx.x : 0;             // operands from global memory); measured: a warp per mixed
+    const int key = column ? key_lo + (int)blockIdx.x : 0;   // operands from global memory); measured: a warp per mixed
     lss_stamp<true>(blockIdx.x, 0);                      // voxel (16 rows in flight, sum handed on by shuffle) is slower
     const int n_rec = column ? __ldg(key_count + key) : __ldg(counters + 1);
     const int w0 = column ? key % d.fW : -1, bn = key / d.fW;
@@ -445,11 +445,11 @@ k_fwd_gather(Dims d, int n_keys, const int32_t *__restrict__ key_count, const in
 // registers, non-empty slots looked up through a column map -- was measured slower: 28 us vs 19 us.)
 template <bool CL, bool VEC4>
 __global__ void __launch_bounds__(SPLAT_THREADS)
-k_fwd_store(Dims d, Tiling tl, int CH, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
+k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
             const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
             float *__restrict__ bev) {
     extern __shared__ __align__(16) float smem[];
-    const int tile = blockIdx.x;
+    const int tile = tile_lo + blockIdx.x;
     const int c0 = blockIdx.y * (CH < 0 ? -CH : CH);      // this CTA owns channels [c0, c0 + CH) of the tile
     if (blockIdx.y == 0) lss_stamp(tile, 0);
     const TileCoord tc = tile_coord(d, tl, tile);
@@ -692,10 +692,10 @@ k_bwd_gather(Dims d, const int32_t *__restrict__ vox, const float *__restrict__ 
 // 32-byte sector written per lane.  channels_last: plain 16-byte copies.
 template <bool CL>
 __global__ void __launch_bounds__(SPLAT_THREADS, 4)
-k_bwd_rows_compact(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
+k_bwd_rows_compact(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                    const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs,
                    const float *__restrict__ grad_bev, float *__restrict__ grows) {
-    const int tile = blockIdx.x;
+    const int tile = tile_lo + blockIdx.x;
     const int nseg = __ldg(tile_nseg + tile);
     if (nseg == 0) return;
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
@@ -744,12 +744,12 @@ k_bwd_rows_compact(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, co
 // row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
 template <int CPL>
 __global__ void __launch_bounds__(SPLAT_THREADS)
-k_bwd_gather_px(Dims d, int WC, int stage_rows, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
+k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
                 const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
     extern __shared__ __align__(16) float smem[];
     constexpr int LF = CPL <= 8 ? 4 : 2;
     constexpr int NT = SPLAT_THREADS;
-    const int bn = blockIdx.y, w0 = blockIdx.x * WC;
+    const int bn = bn_lo + blockIdx.y, w0 = blockIdx.x * WC;
     const int D = d.D, C = d.C, fH = d.fH, DC = D + C;
     const int npx = fH * WC;                              // pixels of the CTA (<= 32), group g <-> pixel (h, wl)
     float *s_p = smem;                                    // [32][D] softmax weight
@@ -980,7 +980,8 @@ static inline PlanPtrs plan_ptrs(const lss_plan_layout *L, const void *workspace
 }
 
 template <bool CL, bool VEC4>
-static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, cudaStream_t s) {
+static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
+                            cudaStream_t s) {
     static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;   // tuning knob
     int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
     if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
@@ -990,7 +991,8 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     int st = opt_in_smem(kern, smem, configured);
     if (st != LSS_OK) return st;
     static int zero_only = getenv("LSS_STORE_ZERO") ? 1 : 0;                                // measurement aid
-    kern<<<dim3(tl.n_tiles, d.C / CH), SPLAT_THREADS, smem, s>>>(d, tl, zero_only ? -CH : CH, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
+    const int tps = tl.n_tiles / d.B;                     // tiles per sample
+    kern<<<dim3((b1 - b0) * tps, d.C / CH), SPLAT_THREADS, smem, s>>>(d, tl, b0 * tps, zero_only ? -CH : CH, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -998,14 +1000,16 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
 // GROUP variant of the deterministic forward: gather into compact rows, then stream the tiles out
 static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, const PlanPtrs &pp, long long L_rows_cap,
                          const float *prob, const float *prob_col, const float *ctx_t, float *vsum, float *bev,
-                         int variant, cudaStream_t s) {
+                         int variant, int b0, int b1, cudaStream_t s) {
     if (variant == LSS_VARIANT_GROUP_STORE) goto store;
     {
-    const int n_keys = d.B * d.N * d.fW;                 // one CTA per camera column ...
-    const int grid = n_keys + 2 * num_sms();             // ... plus the CTAs that drain the mixed-voxel queue
+    const int key_lo = b0 * d.N * d.fW;
+    const int n_keys = (b1 - b0) * d.N * d.fW;           // one CTA per camera column of the samples [b0, b1) ...
+    // ... plus the CTAs that drain the queue of mixed voxels (of ALL samples): they ride with the part that starts at 0
+    const int grid = n_keys + (b0 == 0 ? 2 * num_sms() : 0);
     const size_t gsm = (size_t)(d.fH * d.C + d.D * d.fH) * 4;
     if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GATHER_ARGS d, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, pp.entries, prob, prob_col, ctx_t, vsum
+#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, pp.entries, prob, prob_col, ctx_t, vsum
     if (d.C == 32) k_fwd_gather<4><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else if (d.C == 64) k_fwd_gather<8><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else k_fwd_gather<16><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
@@ -1014,8 +1018,8 @@ static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, co
     LSS_CHECK_LAUNCH();
     if (variant == LSS_VARIANT_GROUP_GATHER) return LSS_OK;
 store:
-    if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, s);
-    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, s);
+    if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, b0, b1, s);
+    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, s);
 }
 
 template <int VW, int KC, bool DENSE>
@@ -1038,7 +1042,7 @@ static bool tile_vec4_ok(const Dims &d, const Tiling &tl, bool cl, const float *
 
 template <bool DENSE>
 static int dispatch_fwd(bool atomic, bool cl, int variant, const Dims &d, const Tiling &tl, const PlanPtrs &pp,
-                        long long rows_cap, const SrcArgs &src, float *vsum, float *bev, cudaStream_t s) {
+                        long long rows_cap, const SrcArgs &src, float *vsum, float *bev, int b0, int b1, cudaStream_t s) {
     const bool vec4 = tile_vec4_ok(d, tl, cl, bev);
     const bool rows16 = lss_aligned(src.base, 16);
     // GROUP kernels: deterministic mode, fused operands, 8 lanes x C/8 channels, 32-bit row offsets
@@ -1046,7 +1050,8 @@ static int dispatch_fwd(bool atomic, bool cl, int variant, const Dims &d, const 
                           (d.C == 32 || d.C == 64 || d.C == 128) && (long long)d.N * d.HW * d.C < (1ll << 31) &&
                           (size_t)(d.fH * d.C + d.D * d.fH) * 4 <= 48 * 1024;
     if (variant >= LSS_VARIANT_GROUP && !group_ok) return LSS_ERR_UNSUPPORTED;
-    if (group_ok && variant != LSS_VARIANT_WARP) return run_fwd_group(cl, vec4, d, tl, pp, rows_cap, src.prob, src.prob_col, src.base, vsum, bev, variant, s);
+    if (group_ok && variant != LSS_VARIANT_WARP) return run_fwd_group(cl, vec4, d, tl, pp, rows_cap, src.prob, src.prob_col, src.base, vsum, bev, variant, b0, b1, s);
+    if (b0 != 0 || b1 != d.B) return LSS_ERR_UNSUPPORTED;   // only the GROUP kernels take a sample range
     const int32_t *ts = pp.tile_start;
     const uint32_t *en = pp.entries;
     if (!DENSE && rows16) {
@@ -1078,13 +1083,15 @@ extern "C" int lss_bev_clear(const lss_problem *p, float *bev, void *stream) {
 
 extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace, const float *prob,
                              const float *ctx_t, const float *prob_col, float *voxel_sums, float *bev, int mode,
-                             int layout, int variant, int precleared, void *stream) {
+                             int layout, int variant, int precleared, int b0, int b1, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
     LSS_REQUIRE(prob && ctx_t && bev, LSS_ERR_BAD_ARG);
     LSS_REQUIRE(layout == LSS_LAYOUT_NCHW || layout == LSS_LAYOUT_CHANNELS_LAST, LSS_ERR_BAD_ARG);
     const Dims d = make_dims(p);
+    if (b1 <= 0) { b0 = 0; b1 = d.B; }                    // (0, 0) = all samples
+    LSS_REQUIRE(0 <= b0 && b0 < b1 && b1 <= d.B, LSS_ERR_BAD_ARG);
     LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
     const Tiling tl = make_tiling(L);
     const char *w = (const char *)workspace;
@@ -1096,8 +1103,9 @@ extern "C" int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, con
     SrcArgs src{};
     src.base = ctx_t; src.prob = prob; src.prob_col = prob_col;
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
-        return dispatch_fwd<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, d, tl, plan_ptrs(L, workspace), L->n_rows_cap, src, voxel_sums, bev, s);
+        return dispatch_fwd<false>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, d, tl, plan_ptrs(L, workspace), L->n_rows_cap, src, voxel_sums, bev, b0, b1, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {
+        LSS_REQUIRE(b0 == 0 && b1 == d.B, LSS_ERR_UNSUPPORTED);
         if (!precleared && cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
         const int npix = d.B * d.N * d.HW;
         const int grid = (npix + SPLAT_WARPS - 1) / SPLAT_WARPS;
@@ -1134,7 +1142,7 @@ extern "C" int lss_voxel_pooling_fwd(const lss_problem *p, const lss_plan_layout
     src.base = x; src.prob = nullptr;
     for (int i = 0; i < 6; ++i) src.s[i] = xs_host[i];
     if (mode == LSS_SPLAT_SORTED || mode == LSS_SPLAT_SMEM_ATOMIC)
-        return dispatch_fwd<true>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, d, tl, plan_ptrs(L, workspace), L->n_rows_cap, src, nullptr, bev, s);
+        return dispatch_fwd<true>(mode == LSS_SPLAT_SMEM_ATOMIC, cl, variant, d, tl, plan_ptrs(L, workspace), L->n_rows_cap, src, nullptr, bev, 0, d.B, s);
     if (mode == LSS_SPLAT_RED_GLOBAL) {
         if (!precleared && cudaMemsetAsync(bev, 0, bev_elems(d) * 4, s) != cudaSuccess) return LSS_ERR_CUDA;
         const int grid = (d.n_points + SPLAT_WARPS - 1) / SPLAT_WARPS;
@@ -1206,12 +1214,16 @@ static bool bwd_compact_ok(const Dims &d, const float *ctx_t, const float *grows
 // compact-row backward (sorted plans): gradient rows of the non-empty voxels, then the pixel-owner gather
 static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanPtrs &pp, const int32_t *prow,
                            const float *grad_bev, const float *prob_col, const float *ctx_t, float *grows, float *grad_dn,
-                           cudaStream_t s) {
-    if (cl) k_bwd_rows_compact<true><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
-    else k_bwd_rows_compact<false><<<tl.n_tiles, SPLAT_THREADS, 0, s>>>(d, tl, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
-    LSS_CHECK_LAUNCH();
+                           int stage, int b0, int b1, cudaStream_t s) {
+    const int tps = tl.n_tiles / d.B;                     // tiles per sample
+    if (stage != 2) {
+        if (cl) k_bwd_rows_compact<true><<<(b1 - b0) * tps, SPLAT_THREADS, 0, s>>>(d, tl, b0 * tps, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
+        else k_bwd_rows_compact<false><<<(b1 - b0) * tps, SPLAT_THREADS, 0, s>>>(d, tl, b0 * tps, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
+        LSS_CHECK_LAUNCH();
+        if (stage == 1) return LSS_OK;
+    }
     const int WC = max(1, 32 / d.fH);
-    const dim3 grid((d.fW + WC - 1) / WC, d.B * d.N);
+    const dim3 grid((d.fW + WC - 1) / WC, (b1 - b0) * d.N);
     size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
     const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16;  // staged gradient rows (+ alignment), if they fit next to a second CTA
@@ -1222,7 +1234,7 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
         static bool configured = false;                                                                          \
         int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
         if (st != LSS_OK) return st;                                                                             \
-        k_bwd_gather_px<CPL><<<grid, SPLAT_THREADS, smem, s>>>(d, WC, stage_rows, prow, prob_col, ctx_t, grows, grad_dn); \
+        k_bwd_gather_px<CPL><<<grid, SPLAT_THREADS, smem, s>>>(d, b0 * d.N, WC, stage_rows, prow, prob_col, ctx_t, grows, grad_dn); \
     } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
 #undef GPX
@@ -1232,7 +1244,8 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
 
 extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                              const float *grad_bev, int layout, const float *prob, const float *ctx_t,
-                             const float *prob_col, float *grad_rows, float *grad_depthnet, int plan_sorted, void *stream) {
+                             const float *prob_col, float *grad_rows, float *grad_depthnet, int plan_sorted, int stage,
+                             int b0, int b1, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
@@ -1240,6 +1253,8 @@ extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, con
     LSS_REQUIRE(layout == LSS_LAYOUT_NCHW || layout == LSS_LAYOUT_CHANNELS_LAST, LSS_ERR_BAD_ARG);
     LSS_REQUIRE(p->D <= LSS_MAX_DEPTH, LSS_ERR_UNSUPPORTED);
     const Dims d = make_dims(p);
+    if (b1 <= 0) { b0 = 0; b1 = d.B; }                    // (0, 0) = all samples
+    LSS_REQUIRE(0 <= b0 && b0 < b1 && b1 <= d.B && stage >= 0 && stage <= 2, LSS_ERR_BAD_ARG);
     LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
     const Tiling tl = make_tiling(L);
     const PlanPtrs pp = plan_ptrs(L, workspace);
@@ -1247,7 +1262,8 @@ extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, con
     const bool cl = layout == LSS_LAYOUT_CHANNELS_LAST;
     if (plan_sorted && prob_col != nullptr && grad_rows != nullptr && bwd_compact_ok(d, ctx_t, grad_rows))
         return run_bwd_compact(cl, d, tl, pp, (const int32_t *)((const char *)workspace + L->off_prow), grad_bev, prob_col,
-                               ctx_t, grad_rows, grad_depthnet, s);
+                               ctx_t, grad_rows, grad_depthnet, stage, b0, b1, s);
+    LSS_REQUIRE(stage == 0 && b0 == 0 && b1 == d.B, LSS_ERR_UNSUPPORTED);   // only the compact-row kernels take parts
     const float *rows = grad_bev;
     if (!cl) {
         LSS_REQUIRE(grad_rows != nullptr, LSS_ERR_WORKSPACE);

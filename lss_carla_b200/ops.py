@@ -267,9 +267,10 @@ def bev_clear(prob: Problem, device, channels_last=False):
 
 
 def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False, variant="auto", out=None,
-              voxel_sums=None):
-    """`out`: optional pre-zeroed BEV tensor (from bev_clear) for mode 'red'.  `voxel_sums`: optional
-    workspace f32[min(n_points, n_voxels), C] of the two-kernel GROUP variant (allocated when omitted)."""
+              voxel_sums=None, batch_range=(0, 0), precleared=None):
+    """`out`: optional output tensor (pre-zeroed, from bev_clear, for mode 'red').  `voxel_sums`: optional
+    workspace f32[min(n_points, n_voxels), C] of the two-kernel GROUP variant (allocated when omitted).
+    `batch_range` = (b0, b1): only these samples (GROUP variant; see splat_fwd_pipelined)."""
     if mode == "sorted" and not plan.sorted:
         raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
     bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
@@ -278,19 +279,73 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
     check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct),
                               _ptr(_prob_col(pr)), _ptr(voxel_sums), _ptr(bev),
                               SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW,
-                              VARIANTS[variant], 1 if out is not None else 0, _stream()), "lss_splat_fwd")
+                              VARIANTS[variant], int(out is not None if precleared is None else precleared),
+                              int(batch_range[0]), int(batch_range[1]), _stream()), "lss_splat_fwd")
     return bev
 
 
-def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_col=None):
+def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_col=None, out=None, stage=0,
+              batch_range=(0, 0)):
     g, layout = _bev_layout(_f32c_keep(grad_bev))
     if grad_rows is None and (layout == LAYOUT_NCHW or plan.sorted):
         grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
-    out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
+    if out is None:
+        out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
     if prob_col is None:
         prob_col = _prob_col(pr)
     check(lib().lss_splat_bwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), layout, _ptr(pr), _ptr(ct),
-                              _ptr(prob_col), _ptr(grad_rows), _ptr(out), 1 if plan.sorted else 0, _stream()), "lss_splat_bwd")
+                              _ptr(prob_col), _ptr(grad_rows), _ptr(out), 1 if plan.sorted else 0, int(stage),
+                              int(batch_range[0]), int(batch_range[1]), _stream()), "lss_splat_bwd")
+    return out
+
+
+def _parts(B, n):
+    n = max(1, min(int(n), B))
+    return [(i * B // n, (i + 1) * B // n) for i in range(n)]
+
+
+def splat_fwd_pipelined(prob: Problem, plan: Plan, pr, ct, side, parts=2, channels_last=False, voxel_sums=None, out=None):
+    """Deterministic forward issued in `parts` sample ranges on two streams: the current stream runs the gathers
+    back to back, `side` runs each part's store as soon as its gather is done, so the HBM-bound store of one part
+    overlaps the issue-bound gather of the next.  Same kernels, same bits as splat_fwd(mode="sorted")."""
+    if not plan.sorted or prob.C not in (32, 64, 128):
+        return splat_fwd(prob, plan, pr, ct, "sorted", channels_last, voxel_sums=voxel_sums, out=out)
+    cur = torch.cuda.current_stream()
+    bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
+    if voxel_sums is None:
+        voxel_sums = torch.empty((plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=pr.device)
+    for t in (bev, voxel_sums, pr, ct):
+        t.record_stream(side)
+    for rng in _parts(prob.B, parts):
+        splat_fwd(prob, plan, pr, ct, "sorted", channels_last, variant="group_gather", out=bev, voxel_sums=voxel_sums,
+                  batch_range=rng, precleared=0)
+        side.wait_stream(cur)                       # this part's rows are complete
+        with torch.cuda.stream(side):
+            splat_fwd(prob, plan, pr, ct, "sorted", channels_last, variant="group_store", out=bev, voxel_sums=voxel_sums,
+                      batch_range=rng, precleared=0)
+    cur.wait_stream(side)
+    return bev
+
+
+def splat_bwd_pipelined(prob: Problem, plan: Plan, grad_bev, pr, ct, side, parts=2, grad_rows=None, prob_col=None, out=None):
+    """Backward in `parts` sample ranges on two streams: the DRAM-bound gradient-row gather of one part (current
+    stream) overlaps the pixel gather of the previous part (`side`)."""
+    g, layout = _bev_layout(_f32c_keep(grad_bev))
+    if not plan.sorted or prob.C not in (32, 64, 128) or (prob_col is None and _prob_col(pr) is None):
+        return splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out)
+    cur = torch.cuda.current_stream()
+    if grad_rows is None:
+        grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
+    if out is None:
+        out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
+    for t in (g, grad_rows, out, pr, ct):
+        t.record_stream(side)
+    for rng in _parts(prob.B, parts):
+        splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out, stage=1, batch_range=rng)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out, stage=2, batch_range=rng)
+    cur.wait_stream(side)
     return out
 
 

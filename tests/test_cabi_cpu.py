@@ -95,7 +95,7 @@ def test_bad_arguments_return_status_codes(L):
     big = _problem(cfg)
     big.c.D = 1 << 20
     assert L.lss_plan_layout_init(C.byref(big.c), 0, C.byref(lay)) == -3     # > 2^20 points per sample
-    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, null, null, 0, 0, 0, 0, null) == -5
+    assert L.lss_splat_fwd(C.byref(p.c), None, null, null, null, null, null, null, 0, 0, 0, 0, 0, 0, null) == -5
     assert L.lss_quickcumsum_scratch_elems(5000) >= 5000 + 5
 
 

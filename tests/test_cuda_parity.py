@@ -453,6 +453,28 @@ def test_full_size_properties(name, aug, seed):
     assert float(gr[:, :cfg.D].sum(1).abs().max()) < 1e-3
 
 
+@pytest.mark.parametrize("case,parts", [("cfg2_train_s0", 2), ("cfg2_train_s0", 3), ("tiny_full_s1", 2), ("cfg4_train_s0", 4)])
+def test_pipelined_parts_give_identical_bits(case, parts):
+    """Sample ranges on two streams (store / row gather of one part overlapping the gather of the next)."""
+    g = load_golden(case)
+    cfg = CONFIGS[str(g["cfg"])]
+    prob = problem_of(cfg, g)
+    plan = ops.build_plan(prob, calib=calib_of(g), sorted=True)
+    pr, ct = ops.lift_prepare(prob, make_depthnet_out(cfg, 7).to(dev()))
+    side = torch.cuda.Stream()
+    gb = make_bev_grad(cfg, 7).to(dev())
+    for cl in (False, True):
+        ref = ops.splat_fwd(prob, plan, pr, ct, "sorted", cl)
+        got = ops.splat_fwd_pipelined(prob, plan, pr, ct, side, parts, cl)
+        torch.cuda.synchronize()
+        assert torch.equal(ref, got)
+        gbc = gb.contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+        gref = ops.splat_bwd(prob, plan, gbc, pr, ct)
+        ggot = ops.splat_bwd_pipelined(prob, plan, gbc, pr, ct, side, parts)
+        torch.cuda.synchronize()
+        assert torch.equal(gref, ggot)
+
+
 def test_model_install_style_get_voxels():
     """lift_splat_from_depthnet (what install()/LiftSplatShoot.get_voxels call) in both inverse modes."""
     from types import SimpleNamespace
