@@ -250,6 +250,7 @@ class BufferSet:
 
 STAGES = ("calib", "plan_build", "lift_prepare", "splat_fwd", "splat_bwd")
 NO_OVERLAP = bool(os.environ.get("LSS_BENCH_NO_OVERLAP"))
+NO_FUSED_CALIB = bool(os.environ.get("LSS_BENCH_NO_FUSED_CALIB"))
 # sample-range pipelining of gather/store on two streams: measured slower at cfg 2 (2 parts: 2404, 4 parts: 1868 vs 2876
 # Mpoints/s unsplit) -- every kernel already fills the GPU, smaller launches only add tails -- so it stays off
 PARTS = 1 if NO_OVERLAP else int(os.environ.get("LSS_BENCH_PARTS", "1"))
@@ -264,15 +265,21 @@ def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAG
         bs.side.wait_stream(cur)
         with torch.cuda.stream(bs.side):
             pr, ct = ops.lift_prepare(prob, bs.dn, out=bs.lift_out)
-    if inverse == "device":
-        M1, M2 = ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots)
+    if inverse == "device" and not NO_FUSED_CALIB:
+        if upto < 2:                                   # (attribution only: the fused build has no calib launch)
+            return
+        ops.build_plan_raw(prob, frustum, bs.rots, bs.trans, bs.intrins, bs.post_rots, bs.post_trans,
+                           sorted=(mode == "sorted"), plan=bs.plan)
     else:
-        M1, M2 = ops.calib_matrices_reference(bs.rots, bs.intrins, bs.post_rots)
-    bs.out.update({"M1": M1, "M2": M2})
-    if upto < 2:
-        return
-    calib = (frustum, bs.post_trans, M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), bs.trans)
-    ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=bs.plan)
+        if inverse == "device":
+            M1, M2 = ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots)
+        else:
+            M1, M2 = ops.calib_matrices_reference(bs.rots, bs.intrins, bs.post_rots)
+        bs.out.update({"M1": M1, "M2": M2})
+        if upto < 2:
+            return
+        calib = (frustum, bs.post_trans, M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), bs.trans)
+        ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=bs.plan)
     if upto < 3:
         return
     if overlap:
@@ -297,7 +304,7 @@ def one_step(ops, prob, frustum, bs, mode, channels_last, inverse, upto=len(STAG
 
 # kernels of liblss_b200.so per step: calib, voxel+count, scatter, [sort], lift, forward (sorted: gather + store;
 # atomic: one tile kernel; red: memset + one kernel), gradient rows, gather
-LAUNCHES_PER_STEP = {"sorted": 9, "atomic": 7, "red": 8}
+LAUNCHES_PER_STEP = {"sorted": 9, "atomic": 7, "red": 8}     # minus 1 with the calibration fused into the plan build
 
 
 def time_kernel(fn, sets, iters, stream):
@@ -473,10 +480,16 @@ def main():
         prev = tk
     stages = {}
     stages["calib"] = time_kernel(lambda bs: ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots), sets, kiters, stream)
-    stages["plan_build"] = time_kernel(
-        lambda bs: ops.build_plan(prob, calib=(frustum, bs.post_trans, bs.out["M1"].reshape(-1, 3, 3),
-                                               bs.out["M2"].reshape(-1, 3, 3), bs.trans),
-                                  sorted=(args.mode == "sorted"), plan=bs.plan), sets, kiters, stream)
+    fused_calib = args.inverse == "device" and not NO_FUSED_CALIB
+    if fused_calib:
+        stages["plan_build"] = time_kernel(
+            lambda bs: ops.build_plan_raw(prob, frustum, bs.rots, bs.trans, bs.intrins, bs.post_rots, bs.post_trans,
+                                          sorted=(args.mode == "sorted"), plan=bs.plan), sets, kiters, stream)
+    else:
+        stages["plan_build"] = time_kernel(
+            lambda bs: ops.build_plan(prob, calib=(frustum, bs.post_trans, bs.out["M1"].reshape(-1, 3, 3),
+                                                   bs.out["M2"].reshape(-1, 3, 3), bs.trans),
+                                      sorted=(args.mode == "sorted"), plan=bs.plan), sets, kiters, stream)
     stages["lift_prepare"] = time_kernel(lambda bs: ops.lift_prepare(prob, bs.dn), sets, kiters, stream)
     stages["splat_fwd"] = time_kernel(lambda bs: ops.splat_fwd(prob, bs.plan, bs.out["pr"], bs.out["ct"], args.mode, channels_last, voxel_sums=bs.vsum),
                                       sets, kiters, stream)
@@ -532,7 +545,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 5), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(cfg), "splat_mode": args.mode, "bev_layout": args.layout,
-                       "inverse": args.inverse, "cuda_graph": use_graph,
+                       "inverse": args.inverse + (" (fused into the plan build)" if (args.inverse == "device" and not NO_FUSED_CALIB) else ""),
+                       "cuda_graph": use_graph,
                        "l2": f"{args.sets} rotating buffer sets (~{(2 * G + IN) * (1 if channels_last else 1.5) / 1e6:.0f} MB each) > 126 MB L2",
                        "points_per_step_per_gpu": cfg.points, "voxels_hit": v_hit},
             "clocks": clk.summary(),
@@ -540,7 +554,7 @@ def main():
                     "steps": e2e_steps, "ms_per_step": round(e2e_elapsed / e2e_steps * 1e3, 4),
                     "api": f"lss_carla_b200.api.LiftSplat.__call__ + autograd backward + LiftSplat.download; inverse_mode={args.e2e_inverse}; "
                            "stream-ordered pinned H2D/D2H copies inside the timed region"},
-            "gpu_launches": LAUNCHES_PER_STEP[args.mode] * args.steps,
+            "gpu_launches": (LAUNCHES_PER_STEP[args.mode] - (1 if (args.inverse == "device" and not NO_FUSED_CALIB) else 0)) * args.steps,
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -158,6 +158,14 @@ int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, void *workspa
                    const float *frustum, const float *post_trans, const float *M1, const float *M2,
                    const float *trans, int sorted, void *stream);
 
+/* Same plan straight from the raw calibration of LiftSplatShoot.forward (models.py:256): the closed-form 3x3
+ * inverses of lss_calib_matrices are evaluated inside the voxel-index kernel (identical bits), which saves
+ * a launch per batch.  rots, intrins, post_rots f32[B*N,3,3]; trans, post_trans f32[B*N,3].
+ * LSS_ERR_UNSUPPORTED if a camera has fewer than 43 frustum points (use lss_calib_matrices + lss_plan_build). */
+int lss_plan_build_raw(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *frustum,
+                       const float *rots, const float *trans, const float *intrins, const float *post_rots,
+                       const float *post_trans, int sorted, void *stream);
+
 /* Parity dump: the reference's sort permutation.  order_out int64[n_points] receives, for
  * i < n_kept, the flat point index of the i-th element of `x[kept][sorts]` (models.py:222-231), and -1
  * for i >= n_kept; n_kept_out int32[1].  Needs a plan built with sorted=1.  scratch int32[n_ranks+1]

@@ -62,6 +62,7 @@ SIGNATURES = {
     "lss_geometry": (C.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P]),
     "lss_voxel_index": (C.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lss_plan_build": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "lss_plan_build_raw": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
     "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),

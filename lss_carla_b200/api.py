@@ -58,10 +58,11 @@ class LiftSplat:
                 M1 = torch.inverse(post_rots.cpu() if post_rots.is_cuda else post_rots)
                 M2h = torch.inverse(intrins.cpu() if intrins.is_cuda else intrins)
                 M1, M2 = self._dev(M1), self._dev(rots).matmul(self._dev(M2h))
+                calib = (self.frustum, self._dev(post_trans).reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3),
+                         self._dev(trans).reshape(-1, 3))
+                plan = ops.build_plan(prob, calib=calib, sorted=(self.splat_mode == "sorted"),
+                                      plan=models._cached_plan(self, prob, self.device))
             else:
-                M1, M2 = ops.calib_matrices_device(self._dev(rots), self._dev(intrins), self._dev(post_rots))
-            calib = (self.frustum, self._dev(post_trans).reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3),
-                     self._dev(trans).reshape(-1, 3))
-            plan = ops.build_plan(prob, calib=calib, sorted=(self.splat_mode == "sorted"),
-                                  plan=models._cached_plan(self, prob, self.device))
+                plan = models.plan_from_calibration(self, prob, self._dev(rots), self._dev(trans), self._dev(intrins),
+                                                    self._dev(post_rots), self._dev(post_trans))
         return ops.lift_splat(self._dev(depthnet_out), prob, plan, self.splat_mode, self.bev_channels_last)

@@ -19,26 +19,27 @@ struct CalibPtrs {
     const float *M1;          // [B*N,3,3] inverse(post_rots)
     const float *M2;          // [B*N,3,3] rots @ inverse(intrins)
     const float *trans;       // [B*N,3]
+    const float *rots, *intrins, *post_rots;   // raw calibration [B*N,3,3] (fused plan build: M1/M2 made on the fly)
 };
 
 __device__ __forceinline__ float row_dot_unfused(const float *__restrict__ m, float v0, float v1, float v2) {
     // (a0*v0 + a1*v1) + a2*v2, one rounding per operation  (models.py:180,187 as ATen's CPU bmm evaluates it)
-    return __fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + 0), v0), __fmul_rn(__ldg(m + 1), v1)), __fmul_rn(__ldg(m + 2), v2));
+    return __fadd_rn(__fadd_rn(__fmul_rn(m[0], v0), __fmul_rn(m[1], v1)), __fmul_rn(m[2], v2));
 }
 
-__device__ __forceinline__ void ego_point(const CalibPtrs &c, int cam, int in_cam, float out[3]) {
+__device__ __forceinline__ void ego_point(const CalibPtrs &c, int cam, int in_cam, float out[3],
+                                          const float *m1 = nullptr, const float *m2 = nullptr) {
+    if (m1 == nullptr) { m1 = c.M1 + cam * 9; m2 = c.M2 + cam * 9; }
     const float *fr = c.frustum + (size_t)in_cam * 3;
     const float *pt = c.post_trans + cam * 3;
     const float p0 = __fsub_rn(__ldg(fr + 0), __ldg(pt + 0));   // models.py:179
     const float p1 = __fsub_rn(__ldg(fr + 1), __ldg(pt + 1));
     const float p2 = __fsub_rn(__ldg(fr + 2), __ldg(pt + 2));
-    const float *m1 = c.M1 + cam * 9;
     const float q0 = row_dot_unfused(m1 + 0, p0, p1, p2);       // models.py:180
     const float q1 = row_dot_unfused(m1 + 3, p0, p1, p2);
     const float q2 = row_dot_unfused(m1 + 6, p0, p1, p2);
     const float r0 = __fmul_rn(q0, q2);                         // models.py:183-185
     const float r1 = __fmul_rn(q1, q2);
-    const float *m2 = c.M2 + cam * 9;
     const float *tr = c.trans + cam * 3;
     out[0] = __fadd_rn(row_dot_unfused(m2 + 0, r0, r1, q2), __ldg(tr + 0));   // models.py:187-188
     out[1] = __fadd_rn(row_dot_unfused(m2 + 3, r0, r1, q2), __ldg(tr + 1));
@@ -65,31 +66,39 @@ __device__ __forceinline__ int voxel_of_point(const Dims &d, int b, const float 
 // kernels: calibration matrices, geometry, voxel index (+ tile histogram)
 // ------------------------------------------------------------------------------------------------
 
+// Closed-form inverse with one explicit rounding per operation (no FMA contraction), so that every kernel that
+// inlines it produces the same bits.
+__device__ __forceinline__ float det2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, c)); }
 __device__ __forceinline__ void inv3x3(const float *a, float *o) {
-    const float c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
-    const float det = a[0] * c00 + a[1] * c01 + a[2] * c02;
-    const float r = 1.0f / det;
-    o[0] = c00 * r; o[1] = (a[2] * a[7] - a[1] * a[8]) * r; o[2] = (a[1] * a[5] - a[2] * a[4]) * r;
-    o[3] = c01 * r; o[4] = (a[0] * a[8] - a[2] * a[6]) * r; o[5] = (a[2] * a[3] - a[0] * a[5]) * r;
-    o[6] = c02 * r; o[7] = (a[1] * a[6] - a[0] * a[7]) * r; o[8] = (a[0] * a[4] - a[1] * a[3]) * r;
+    const float c00 = det2(a[4], a[5], a[7], a[8]), c01 = det2(a[5], a[3], a[8], a[6]), c02 = det2(a[3], a[4], a[6], a[7]);
+    const float det = __fadd_rn(__fadd_rn(__fmul_rn(a[0], c00), __fmul_rn(a[1], c01)), __fmul_rn(a[2], c02));
+    const float r = __frcp_rn(det);
+    o[0] = __fmul_rn(c00, r); o[1] = __fmul_rn(det2(a[2], a[1], a[8], a[7]), r); o[2] = __fmul_rn(det2(a[1], a[2], a[4], a[5]), r);
+    o[3] = __fmul_rn(c01, r); o[4] = __fmul_rn(det2(a[0], a[2], a[6], a[8]), r); o[5] = __fmul_rn(det2(a[2], a[0], a[5], a[3]), r);
+    o[6] = __fmul_rn(c02, r); o[7] = __fmul_rn(det2(a[1], a[0], a[7], a[6]), r); o[8] = __fmul_rn(det2(a[0], a[1], a[3], a[4]), r);
+}
+
+// M1 = inverse(post_rots), M2 = rots @ inverse(intrins) of one camera (models.py:180,186 without the host round trip)
+__device__ __forceinline__ void calib_matrices_of(const float *rots, const float *intrins, const float *post_rots, int cam,
+                                                  float *M1, float *M2) {
+    float a[9], inv[9];
+    for (int i = 0; i < 9; ++i) a[i] = post_rots[cam * 9 + i];
+    inv3x3(a, inv);
+    for (int i = 0; i < 9; ++i) M1[i] = inv[i];
+    for (int i = 0; i < 9; ++i) a[i] = intrins[cam * 9 + i];
+    inv3x3(a, inv);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            const float *R = rots + cam * 9 + r * 3;
+            M2[r * 3 + c] = __fadd_rn(__fadd_rn(__fmul_rn(R[0], inv[c]), __fmul_rn(R[1], inv[3 + c])), __fmul_rn(R[2], inv[6 + c]));
+        }
 }
 
 __global__ void k_calib_matrices(int n_cams, const float *__restrict__ rots, const float *__restrict__ intrins,
                                  const float *__restrict__ post_rots, float *__restrict__ M1, float *__restrict__ M2) {
     const int cam = blockIdx.x * blockDim.x + threadIdx.x;
     if (cam >= n_cams) return;
-    float a[9], inv[9];
-    for (int i = 0; i < 9; ++i) a[i] = post_rots[cam * 9 + i];
-    inv3x3(a, inv);
-    for (int i = 0; i < 9; ++i) M1[cam * 9 + i] = inv[i];
-    for (int i = 0; i < 9; ++i) a[i] = intrins[cam * 9 + i];
-    inv3x3(a, inv);
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-            const float *R = rots + cam * 9 + r * 3;
-            M2[cam * 9 + r * 3 + c] = __fadd_rn(__fadd_rn(__fmul_rn(R[0], inv[c]), __fmul_rn(R[1], inv[3 + c])),
-                                                __fmul_rn(R[2], inv[6 + c]));
-        }
+    calib_matrices_of(rots, intrins, post_rots, cam, M1 + cam * 9, M2 + cam * 9);
 }
 
 __global__ void k_geometry(Dims d, CalibPtrs c, float *__restrict__ geom) {
@@ -105,7 +114,8 @@ __global__ void k_geometry(Dims d, CalibPtrs c, float *__restrict__ geom) {
 
 // One thread per frustum point.  COUNT adds the per-tile histogram of kept points and, in the last CTA
 // to finish, the exclusive scan tile_count -> tile_start (and leaves tile_count / cursor zeroed).
-template <bool FROM_GEOM, bool COUNT>
+#define LSS_RAW_CAMS 8    // cameras a 256-point CTA may span in the fused (RAW) build
+template <bool FROM_GEOM, bool COUNT, bool RAW = false>
 __global__ void __launch_bounds__(256)
 k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, int32_t *__restrict__ vox,
               long long *__restrict__ idx, uint8_t *__restrict__ kept, long long *__restrict__ rank,
@@ -114,6 +124,13 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
               int32_t *__restrict__ prow) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < d.n_points;
+    __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
+    const int cam0 = (int)((blockIdx.x * blockDim.x) / (unsigned)d.DHW);
+    if (RAW) {      // the calibration matrices of the few cameras this CTA touches, made on the fly (no extra launch)
+        const int cam = cam0 + (int)threadIdx.x;
+        if (threadIdx.x < LSS_RAW_CAMS && cam < d.B * d.N) calib_matrices_of(c.rots, c.intrins, c.post_rots, cam, s_m[threadIdx.x], s_m[threadIdx.x] + 9);
+        __syncthreads();
+    }
     int v = -1;
     if (live) {
         const int b = p / d.P;
@@ -124,7 +141,8 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
             g[2] = __ldg(geom + (size_t)p * 3 + 2);
         } else {
             const int cam = p / d.DHW;
-            ego_point(c, cam, p - cam * d.DHW, g);
+            if (RAW) ego_point(c, cam, p - cam * d.DHW, g, s_m[cam - cam0], s_m[cam - cam0] + 9);
+            else ego_point(c, cam, p - cam * d.DHW, g);
         }
         long long ii[3];
         v = voxel_of_point(d, b, g, ii);
@@ -530,7 +548,7 @@ extern "C" int lss_geometry(const lss_problem *p, const float *frustum, const fl
     if (st != LSS_OK) return st;
     LSS_REQUIRE(frustum && post_trans && M1 && M2 && trans && geom_out, LSS_ERR_BAD_ARG);
     const Dims d = make_dims(p);
-    CalibPtrs c{frustum, post_trans, M1, M2, trans};
+    CalibPtrs c{frustum, post_trans, M1, M2, trans, nullptr, nullptr, nullptr};
     k_geometry<<<(d.n_points + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d, c, geom_out);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
@@ -544,7 +562,7 @@ extern "C" int lss_voxel_index(const lss_problem *p, const float *geom, const fl
     const bool from_geom = geom != nullptr;
     LSS_REQUIRE(from_geom || (frustum && post_trans && M1 && M2 && trans), LSS_ERR_BAD_ARG);
     const Dims d = make_dims(p);
-    CalibPtrs c{frustum, post_trans, M1, M2, trans};
+    CalibPtrs c{frustum, post_trans, M1, M2, trans, nullptr, nullptr, nullptr};
     Tiling tl{8, 1, 1};
     const int grid = (d.n_points + 255) / 256;
     cudaStream_t s = (cudaStream_t)stream;
@@ -558,14 +576,8 @@ extern "C" int lss_voxel_index(const lss_problem *p, const float *geom, const fl
     return LSS_OK;
 }
 
-extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *geom,
-                              const float *frustum, const float *post_trans, const float *M1, const float *M2,
-                              const float *trans, int sorted, void *stream) {
-    int st = lss_check_problem(p);
-    if (st != LSS_OK) return st;
-    LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
-    const bool from_geom = geom != nullptr;
-    LSS_REQUIRE(from_geom || (frustum && post_trans && M1 && M2 && trans), LSS_ERR_BAD_ARG);
+static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *geom,
+                           const CalibPtrs &c, bool raw, int sorted, cudaStream_t s) {
     const Dims d = make_dims(p);
     LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
     const Tiling tl = make_tiling(L);
@@ -578,15 +590,13 @@ extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, vo
     int32_t *sync = (int32_t *)(w + L->off_sync);
     int32_t *counters = (int32_t *)(w + L->off_counters);
     int32_t *key_count = (int32_t *)(w + L->off_key_count);
-    CalibPtrs c{frustum, post_trans, M1, M2, trans};
+    int32_t *prow = (int32_t *)(w + L->off_prow);
     const int grid = (d.n_points + 255) / 256;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (from_geom)
-        k_voxel_index<true, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
-                                                       tile_start, cursor, sync, counters, key_count, (int32_t *)(w + L->off_prow));
-    else
-        k_voxel_index<false, true><<<grid, 256, 0, s>>>(d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count,
-                                                        tile_start, cursor, sync, counters, key_count, (int32_t *)(w + L->off_prow));
+#define VI_ARGS d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count, tile_start, cursor, sync, counters, key_count, prow
+    if (geom != nullptr) k_voxel_index<true, true><<<grid, 256, 0, s>>>(VI_ARGS);
+    else if (raw) k_voxel_index<false, true, true><<<grid, 256, 0, s>>>(VI_ARGS);
+    else k_voxel_index<false, true><<<grid, 256, 0, s>>>(VI_ARGS);
+#undef VI_ARGS
     LSS_CHECK_LAUNCH();
     k_plan_scatter<<<grid, 256, 0, s>>>(d, tl, vox, tile_start, cursor, entries);
     LSS_CHECK_LAUNCH();
@@ -595,13 +605,37 @@ extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, vo
         if (sort_smem > 24 * 1024 &&
             cudaFuncSetAttribute(k_plan_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess)
             return LSS_ERR_CUDA;
-        k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, (size_t)(3 * tl.TY + 1) * sizeof(int), s>>>(
+        k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, sort_smem, s>>>(
             d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
             (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
-            (int4 *)(w + L->off_mixed_recs), counters, (int32_t *)(w + L->off_prow));
+            (int4 *)(w + L->off_mixed_recs), counters, prow);
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;
+}
+
+extern "C" int lss_plan_build(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *geom,
+                              const float *frustum, const float *post_trans, const float *M1, const float *M2,
+                              const float *trans, int sorted, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
+    LSS_REQUIRE(geom != nullptr || (frustum && post_trans && M1 && M2 && trans), LSS_ERR_BAD_ARG);
+    CalibPtrs c{frustum, post_trans, M1, M2, trans, nullptr, nullptr, nullptr};
+    return plan_build_impl(p, L, workspace, geom, c, false, sorted, (cudaStream_t)stream);
+}
+
+extern "C" int lss_plan_build_raw(const lss_problem *p, const lss_plan_layout *L, void *workspace, const float *frustum,
+                                  const float *rots, const float *trans, const float *intrins, const float *post_rots,
+                                  const float *post_trans, int sorted, void *stream) {
+    int st = lss_check_problem(p);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
+    LSS_REQUIRE(frustum && rots && trans && intrins && post_rots && post_trans, LSS_ERR_BAD_ARG);
+    const long long dhw = (long long)p->D * p->fH * p->fW;
+    LSS_REQUIRE(256 / dhw + 2 <= LSS_RAW_CAMS, LSS_ERR_UNSUPPORTED);   // cameras one 256-point CTA may span
+    CalibPtrs c{frustum, post_trans, nullptr, nullptr, trans, rots, intrins, post_rots};
+    return plan_build_impl(p, L, workspace, nullptr, c, true, sorted, (cudaStream_t)stream);
 }
 
 extern "C" int lss_plan_reference_order(const lss_problem *p, const lss_plan_layout *L, const void *workspace,

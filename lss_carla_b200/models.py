@@ -46,13 +46,23 @@ def lift_splat_from_depthnet(model, depthnet_out, rots, trans, intrins, post_rot
     C = depthnet_out.shape[1] - model.D
     prob = _problem_for(model, B, N, fH, fW, C)
     if plan is None:
-        M1, M2 = _calib_matrices(model, rots, intrins, post_rots)
-        calib = (model.frustum.detach(), post_trans.reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3),
-                 trans.reshape(-1, 3))
-        mode = getattr(model, "splat_mode", "sorted")
-        plan = ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=_cached_plan(model, prob, rots.device))
+        plan = plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans)
     return ops.lift_splat(depthnet_out, prob, plan, getattr(model, "splat_mode", "sorted"),
                           getattr(model, "bev_channels_last", False))
+
+
+def plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans):
+    """Voxel ids + buckets for one batch from the calibration of `forward` (models.py:256).  inverse_mode "device"
+    evaluates the 3x3 inverses inside the plan build (one launch less, no host round trip); "reference" prepares
+    M1/M2 with the reference's own torch calls (bit-identical geometry)."""
+    mode = getattr(model, "splat_mode", "sorted")
+    ws = _cached_plan(model, prob, rots.device)
+    frustum = model.frustum.detach()
+    if getattr(model, "inverse_mode", "reference") == "device" and 256 // (prob.D * prob.fH * prob.fW) + 2 <= 8:
+        return ops.build_plan_raw(prob, frustum, rots, trans, intrins, post_rots, post_trans, sorted=(mode == "sorted"), plan=ws)
+    M1, M2 = _calib_matrices(model, rots, intrins, post_rots)
+    calib = (frustum, post_trans.reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), trans.reshape(-1, 3))
+    return ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=ws)
 
 
 def _calib_matrices(model, rots, intrins, post_rots):

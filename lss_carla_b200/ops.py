@@ -203,6 +203,20 @@ def build_plan(prob: Problem, geom=None, calib=None, sorted: bool = True, plan: 
     return plan
 
 
+def build_plan_raw(prob: Problem, frustum, rots, trans, intrins, post_rots, post_trans, sorted: bool = True,
+                   plan: Plan | None = None, tile_cols: int = 0) -> Plan:
+    """build_plan straight from the raw calibration (device inverse mode): the 3x3 inverses are evaluated inside
+    the voxel-index kernel, no separate calib launch.  Same bits as calib_matrices_device + build_plan."""
+    ts = [_f32c(t, n) for t, n in ((frustum, "frustum"), (rots, "rots"), (trans, "trans"), (intrins, "intrins"),
+                                   (post_rots, "post_rots"), (post_trans, "post_trans"))]
+    if plan is None:
+        plan = Plan(prob, ts[0].device, tile_cols)
+    check(lib().lss_plan_build_raw(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), *[_ptr(t) for t in ts],
+                                   1 if sorted else 0, _stream()), "lss_plan_build_raw")
+    plan.sorted, plan.built, plan._keepalive = bool(sorted), True, ts
+    return plan
+
+
 def reference_order(plan: Plan):
     """The reference's `sorts` (models.py:230) as flat point indices, int64[n_kept]."""
     prob = plan.prob

@@ -132,6 +132,22 @@ def test_voxel_index_edge_values():
     assert kept.tolist() == [True, False, True, False, False, False, False, False]
 
 
+def test_plan_build_raw_equals_calib_plus_build():
+    """Fused plan build (3x3 inverses inside the voxel-index kernel) == lss_calib_matrices + lss_plan_build, bit for bit."""
+    for name, aug, seed in [("cfg2", "train", 0), ("cfg4", "train", 0), ("tiny", "full", 1)]:
+        cfg = CONFIGS[name]
+        b = make_batch(cfg, seed, aug)
+        g = load_golden(f"{name}_{aug}_s{seed}")
+        prob = problem_of(cfg, g)
+        t = {k: b[k].to(dev()) for k in ("rots", "trans", "intrins", "post_rots", "post_trans")}
+        M1, M2 = ops.calib_matrices_device(t["rots"], t["intrins"], t["post_rots"])
+        cal = (cu(g["frustum"]), t["post_trans"].reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), t["trans"].reshape(-1, 3))
+        ref = ops.build_plan(prob, calib=cal, sorted=True)
+        got = ops.build_plan_raw(prob, cu(g["frustum"]), t["rots"], t["trans"], t["intrins"], t["post_rots"], t["post_trans"], sorted=True)
+        assert torch.equal(ref.vox, got.vox) and torch.equal(ref.entries, got.entries) and torch.equal(ref.tile_start, got.tile_start)
+        assert int(ref.n_rows.item()) == int(got.n_rows.item())
+
+
 def test_device_inverse_mode_voxel_agreement():
     """Closed-form device inverse vs the reference's LAPACK inverse: report flips, require none here."""
     for name, aug, seed in [("cfg2", "train", 0), ("cfg2", "full", 3), ("cfg4", "train", 0), ("cfg1", "eval", 1)]:
