@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/lss_b200.h"
 
@@ -22,6 +23,25 @@
     do {                        \
         if (!(cond)) return (code); \
     } while (0)
+
+// Kernel launch with optional programmatic dependent launch (PDL): with `pdl`, the grid may start while the
+// previous kernel of the stream is still draining; the kernel must execute lss_pdl_wait() before it reads anything that
+// kernel wrote, and producers call lss_pdl_trigger() early.  Captured into CUDA graphs as programmatic edges.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lss_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                     Args... args) {
+    static const bool no_pdl = getenv("LSS_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && !no_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define lss_pdl_wait() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define lss_pdl_trigger() asm volatile("griddepcontrol.launch_dependents;")
 
 static inline bool lss_aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 

@@ -122,6 +122,7 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
               int32_t *__restrict__ tile_count, int32_t *__restrict__ tile_start, int32_t *__restrict__ cursor,
               int32_t *__restrict__ sync, int32_t *__restrict__ counters, int32_t *__restrict__ key_count,
               int32_t *__restrict__ prow) {
+    if (COUNT) lss_pdl_trigger();                  // the scatter kernel may be scheduled while this grid drains
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < d.n_points;
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
@@ -218,6 +219,8 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
 __global__ void __launch_bounds__(256)
 k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, const int32_t *__restrict__ tile_start,
                int32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+    lss_pdl_trigger();
+    lss_pdl_wait();                                // voxel ids and tile_start come from k_voxel_index
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int v = -1;
@@ -356,6 +359,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
     __shared__ int s_warp[LSS_SORT_THREADS / 32];
     __shared__ int s_row0;
+    lss_pdl_wait();                                // the buckets come from k_plan_scatter
     const int t = blockIdx.x;
     const int s = tile_start[t], n = tile_start[t + 1] - s;
     const int b = t / (tl.nty * d.nx * d.nz);
@@ -598,17 +602,17 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
     else k_voxel_index<false, true><<<grid, 256, 0, s>>>(VI_ARGS);
 #undef VI_ARGS
     LSS_CHECK_LAUNCH();
-    k_plan_scatter<<<grid, 256, 0, s>>>(d, tl, vox, tile_start, cursor, entries);
+    if (lss_launch(k_plan_scatter, dim3(grid), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
     if (sorted) {
         const size_t sort_smem = (size_t)(3 * tl.TY + 1) * sizeof(int);
         if (sort_smem > 24 * 1024 &&
             cudaFuncSetAttribute(k_plan_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess)
             return LSS_ERR_CUDA;
-        k_plan_sort<<<tl.n_tiles, LSS_SORT_THREADS, sort_smem, s>>>(
-            d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
-            (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
-            (int4 *)(w + L->off_mixed_recs), counters, prow);
+        if (lss_launch(k_plan_sort, dim3(tl.n_tiles), dim3(LSS_SORT_THREADS), sort_smem, s, true,
+                       d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
+                       (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
+                       (int4 *)(w + L->off_mixed_recs), counters, prow) != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;

@@ -309,6 +309,7 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
     extern __shared__ __align__(16) float s_col[];       // [fH][C] context rows of the column, [D][fH] softmax weights
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
+    lss_pdl_trigger();                                   // PDL: the store kernel may start its prologue in our tail
     const bool column = (int)blockIdx.x < n_keys;        // else: a CTA of the mixed-voxel queue (group per voxel, all
     const int key = column ? key_lo + (int)blockIdx.x : 0;   // operands from global memory); measured: a warp per mixed
     lss_stamp<true>(blockIdx.x, 0);                      // voxel (16 rows in flight, sum handed on by shuffle) is slower
@@ -465,6 +466,9 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
     const int per_pass = SPLAT_THREADS / c4;              // rows per pass
     const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
     if (blockIdx.y == 0) lss_stamp(tile, 1);
+    // PDL: everything above reads plan data only (written by earlier, completed launches); the compact rows come
+    // from the gather kernel, which may still be running if this kernel was launched programmatically
+    lss_pdl_wait();
     // request the first rows before zero-filling the staging tile
     int col0 = 0;
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -496,6 +500,96 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
     store_tile<VEC4>(t2, smem, bev);
     if (blockIdx.y == 0) lss_stamp(tile, 3);
     if (threadIdx.x == 0 && blockIdx.y == 0 && g_lss_timeline != nullptr) g_lss_timeline[(size_t)tile * 8 + 7] = nseg;
+}
+
+// (2b) k_fwd_store_tma -- the same streaming store as a PERSISTENT kernel: every CTA walks tiles with two staging
+// buffers.  The rows of the staged tile leave through the bulk-copy engine (cp.async.bulk shared -> global, issued by
+// one warp), so the CTA does not wait for its stores: while tile k drains it zero-fills the other buffer and
+// transposes tile k+1 into it; the meta data and the first compact rows of tile k+1 are requested one iteration
+// ahead, which takes the dependent global loads off the critical path.  Needs 16-byte aligned rows (VEC4 shapes).
+__device__ __forceinline__ void bulk_store(float *gdst, const float *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool CL>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__restrict__ tile_start,
+                const int32_t *__restrict__ tile_nseg, const int32_t *__restrict__ tile_row0,
+                const uint32_t *__restrict__ segs, const float *__restrict__ vsum, float *__restrict__ bev) {
+    extern __shared__ __align__(128) float smem[];
+    const int C = d.C, c4 = C >> 2;
+    const int SRS = CL ? C : tl.TY + 4;
+    const int tile_floats = CL ? tl.TY * C : C * SRS;
+    const int per_pass = SPLAT_THREADS / c4;              // compact rows per pass (C = 64: 16)
+    const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
+    const bool loader = r0 < per_pass;
+    // prefetched state of the NEXT tile: meta data and this thread's share of its first 2*per_pass compact rows
+    int n_nseg = 0, n_s = 0, n_row0 = 0, n_col[2] = {0, 0};
+    float4 n_v[2];
+    auto prefetch = [&](int t) {
+        n_nseg = 0;
+        if (t >= n_tiles || tile_nseg == nullptr) return;     // (null: measurement aid, zero tiles only)
+        const int tile = tile_lo + t;
+        n_nseg = __ldg(tile_nseg + tile);
+        if (n_nseg == 0) return;
+        n_s = __ldg(tile_start + tile);
+        n_row0 = __ldg(tile_row0 + tile);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = r0 + u * per_pass;
+            if (loader && r < n_nseg) {
+                n_col[u] = (int)(__ldg(segs + n_s + r) >> LSS_PIDX_BITS);
+                n_v[u] = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(n_row0 + r) * C) + q);
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        float *buf = smem + (it & 1) * tile_floats;
+        const int nseg = n_nseg, s = n_s, row0 = n_row0;
+        const int col[2] = {n_col[0], n_col[1]};
+        const float4 v[2] = {n_v[0], n_v[1]};
+        prefetch(t + gridDim.x);                          // dependent loads of the next tile start now
+        if (threadIdx.x < 32) bulk_wait_read<1>();        // this buffer was handed to the copy engine two tiles ago
+        __syncthreads();
+        zero_smem(buf, tile_floats);
+        __syncthreads();
+        if (loader) {
+            for (int r = r0, u = 0; r < nseg; r += per_pass, ++u) {
+                int cc; float4 vv;
+                if (u < 2) { cc = col[u]; vv = v[u]; }
+                else {
+                    cc = (int)(__ldg(segs + s + r) >> LSS_PIDX_BITS);
+                    vv = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + r) * C) + q);
+                }
+                if (CL) *reinterpret_cast<float4 *>(buf + cc * C + 4 * q) = vv;
+                else {
+                    float *dst = buf + (4 * q) * SRS + cc;
+                    dst[0] = vv.x; dst[SRS] = vv.y; dst[2 * SRS] = vv.z; dst[3 * SRS] = vv.w;
+                }
+            }
+        }
+        fence_async_smem();                               // generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const TileCoord tc = tile_coord(d, tl, tile_lo + t);
+            const Tile2D t2 = tile_2d<CL>(d, tl, tc);
+            float *g = bev + t2.gbase;
+            if (CL && t2.GRS == (size_t)C) {              // the whole tile is one contiguous run
+                if (threadIdx.x == 0) bulk_store(g, buf, (unsigned)(t2.NR * C) * 4u);
+            } else {
+                for (int r = threadIdx.x; r < t2.NR; r += 32) bulk_store(g + (size_t)r * t2.GRS, buf + r * SRS, (unsigned)t2.RL * 4u);
+            }
+            bulk_commit();                                // one group per tile and lane (possibly empty)
+        }
+    }
+    if (threadIdx.x < 32) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -695,10 +789,12 @@ __global__ void __launch_bounds__(SPLAT_THREADS, 4)
 k_bwd_rows_compact(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                    const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs,
                    const float *__restrict__ grad_bev, float *__restrict__ grows) {
+    lss_pdl_trigger();
     const int tile = tile_lo + blockIdx.x;
-    const int nseg = __ldg(tile_nseg + tile);
-    if (nseg == 0) return;
+    const int nseg = __ldg(tile_nseg + tile);      // plan data: older than the previous launch
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
+    lss_pdl_wait();                                // the gradient may come from the kernel right before this one
+    if (nseg == 0) return;
     const TileCoord tc = tile_coord(d, tl, tile);
     const int C = d.C;
     if (CL) {
@@ -784,6 +880,7 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__rest
 #pragma unroll
         for (int a = 0; a < CPL; ++a) dctx[a] = 0.f;
     }
+    lss_pdl_wait();                                       // the gradient rows come from k_bwd_rows_compact
     __syncthreads();
     const int gg = g < npx ? g : 0;                       // idle groups mirror group 0 (shuffles stay warp-uniform)
     const float *my_p = s_p + gg * D;
@@ -981,7 +1078,7 @@ static inline PlanPtrs plan_ptrs(const lss_plan_layout *L, const void *workspace
 
 template <bool CL, bool VEC4>
 static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
-                            cudaStream_t s) {
+                            bool pdl, cudaStream_t s) {
     static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;   // tuning knob
     int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
     if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
@@ -992,7 +1089,32 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     if (st != LSS_OK) return st;
     static int zero_only = getenv("LSS_STORE_ZERO") ? 1 : 0;                                // measurement aid
     const int tps = tl.n_tiles / d.B;                     // tiles per sample
-    kern<<<dim3((b1 - b0) * tps, d.C / CH), SPLAT_THREADS, smem, s>>>(d, tl, b0 * tps, zero_only ? -CH : CH, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
+    if (lss_launch(kern, dim3((b1 - b0) * tps, d.C / CH), dim3(SPLAT_THREADS), smem, s, pdl, d, tl, b0 * tps, zero_only ? -CH : CH,
+                   pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+template <bool CL>
+static int launch_fwd_store_tma(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
+                                cudaStream_t s) {
+    const int tile_floats = CL ? tl.TY * d.C : d.C * (tl.TY + 4);
+    const size_t smem = (size_t)2 * tile_floats * 4;
+    auto kern = k_fwd_store_tma<CL>;
+    static bool configured = false;
+    int st = opt_in_smem(kern, smem, configured);
+    if (st != LSS_OK) return st;
+    static int per_sm = 0;
+    static size_t per_sm_smem = 0;
+    if (per_sm == 0 || per_sm_smem != smem) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SPLAT_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        per_sm = nb; per_sm_smem = smem;
+    }
+    const int tps = tl.n_tiles / d.B, n_tiles = (b1 - b0) * tps;
+    const int grid = min(n_tiles, num_sms() * per_sm);
+    static int zero_only = getenv("LSS_STORE_ZERO") ? 1 : 0;                                // measurement aid
+    kern<<<grid, SPLAT_THREADS, smem, s>>>(d, tl, b0 * tps, n_tiles, pp.tile_start, zero_only ? nullptr : pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -1018,8 +1140,15 @@ static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, co
     LSS_CHECK_LAUNCH();
     if (variant == LSS_VARIANT_GROUP_GATHER) return LSS_OK;
 store:
-    if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, b0, b1, s);
-    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, s);
+    {
+        static int tma_mode = getenv("LSS_STORE_TMA") ? atoi(getenv("LSS_STORE_TMA")) : 0;   // tuning knob (0: LSU stores)
+        const size_t tma_smem = (size_t)2 * (cl ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
+        if (tma_mode && vec4 && tma_smem <= 227 * 1024 && (cl || tl.nty == 1 || tl.TY % 4 == 0))
+            return cl ? launch_fwd_store_tma<true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false>(d, tl, pp, vsum, bev, b0, b1, s);
+    }
+    const bool pdl = variant != LSS_VARIANT_GROUP_STORE;  // only right behind its gather
+    if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
+    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
 }
 
 template <int VW, int KC, bool DENSE>
@@ -1217,8 +1346,12 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
                            int stage, int b0, int b1, cudaStream_t s) {
     const int tps = tl.n_tiles / d.B;                     // tiles per sample
     if (stage != 2) {
-        if (cl) k_bwd_rows_compact<true><<<(b1 - b0) * tps, SPLAT_THREADS, 0, s>>>(d, tl, b0 * tps, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
-        else k_bwd_rows_compact<false><<<(b1 - b0) * tps, SPLAT_THREADS, 0, s>>>(d, tl, b0 * tps, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
+        const cudaError_t e = cl
+            ? lss_launch(k_bwd_rows_compact<true>, dim3((b1 - b0) * tps), dim3(SPLAT_THREADS), 0, s, true, d, tl, b0 * tps,
+                         pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows)
+            : lss_launch(k_bwd_rows_compact<false>, dim3((b1 - b0) * tps), dim3(SPLAT_THREADS), 0, s, true, d, tl, b0 * tps,
+                         pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows);
+        if (e != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
         if (stage == 1) return LSS_OK;
     }
@@ -1234,7 +1367,8 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
         static bool configured = false;                                                                          \
         int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
         if (st != LSS_OK) return st;                                                                             \
-        k_bwd_gather_px<CPL><<<grid, SPLAT_THREADS, smem, s>>>(d, b0 * d.N, WC, stage_rows, prow, prob_col, ctx_t, grows, grad_dn); \
+        if (lss_launch(k_bwd_gather_px<CPL>, grid, dim3(SPLAT_THREADS), smem, s, stage != 2, d, b0 * d.N, WC, stage_rows, prow, prob_col, \
+                       ctx_t, grows, grad_dn) != cudaSuccess) return LSS_ERR_CUDA;                                            \
     } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
 #undef GPX
