@@ -1141,9 +1141,13 @@ static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, co
     if (variant == LSS_VARIANT_GROUP_GATHER) return LSS_OK;
 store:
     {
-        static int tma_mode = getenv("LSS_STORE_TMA") ? atoi(getenv("LSS_STORE_TMA")) : 0;   // tuning knob (0: LSU stores)
+        // persistent bulk-copy variant: measured faster only where a tile is ONE contiguous run (channels_last, nz = 1:
+        // 36.7 vs 38.7 us forward at cfg 2); with one 800-byte bulk copy per channel row (NCHW) it is slower (42.7 us).
+        // LSS_STORE_TMA=1 / 0 forces it on / off.
+        static int tma_mode = getenv("LSS_STORE_TMA") ? atoi(getenv("LSS_STORE_TMA")) : -1;
         const size_t tma_smem = (size_t)2 * (cl ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
-        if (tma_mode && vec4 && tma_smem <= 227 * 1024 && (cl || tl.nty == 1 || tl.TY % 4 == 0))
+        const bool want = tma_mode < 0 ? (cl && d.nz == 1) : tma_mode > 0;
+        if (want && vec4 && tma_smem <= 227 * 1024 && (cl || tl.nty == 1 || tl.TY % 4 == 0))
             return cl ? launch_fwd_store_tma<true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false>(d, tl, pp, vsum, bev, b0, b1, s);
     }
     const bool pdl = variant != LSS_VARIANT_GROUP_STORE;  // only right behind its gather
