@@ -117,14 +117,14 @@ __device__ __forceinline__ Tile2D tile_2d(const Dims &d, const Tiling &tl, const
 // Stream a tile to global memory (src == nullptr: zeros).  A warp walks whole rows (or 32/vpr rows at once when a
 // row has fewer than 32 vector slots), so the inner loop is one shared load, one global store and two pointer
 // increments: the store stream, not index arithmetic, has to be the limit here.
-template <bool VEC4>
+template <bool VEC4, int NT = SPLAT_THREADS>
 __device__ __forceinline__ void store_tile(const Tile2D &t, const float *__restrict__ src, float *__restrict__ bev) {
     float *g = bev + t.gbase;
     if (!VEC4) {
         const int total = t.NR * t.RL;
         int row = threadIdx.x / t.RL, v = threadIdx.x - row * t.RL;
-        const int dr = SPLAT_THREADS / t.RL, dv = SPLAT_THREADS - dr * t.RL;
-        for (int i = threadIdx.x; i < total; i += SPLAT_THREADS) {
+        const int dr = NT / t.RL, dv = NT - dr * t.RL;
+        for (int i = threadIdx.x; i < total; i += NT) {
             g[(size_t)row * t.GRS + v] = src ? src[row * t.SRS + v] : 0.f;
             v += dv; row += dr;
             if (v >= t.RL) { v -= t.RL; ++row; }
@@ -137,7 +137,7 @@ __device__ __forceinline__ void store_tile(const Tile2D &t, const float *__restr
     const int sub = rpw == 1 ? 0 : lane / vpr;
     const int v0 = rpw == 1 ? lane : lane - sub * vpr;
     if (sub >= rpw) return;
-    const int row0 = warp * rpw + sub, rstep = SPLAT_WARPS * rpw;
+    const int row0 = warp * rpw + sub, rstep = (NT / 32) * rpw;
     float4 *gp = reinterpret_cast<float4 *>(g + (size_t)row0 * t.GRS) + v0;
     const size_t gstep = (size_t)rstep * t.GRS / 4;         // GRS % 4 == 0 on the vector path
     if (src == nullptr) {
@@ -264,9 +264,10 @@ __device__ __forceinline__ void walk_bucket(const Dims &d, const SrcArgs &src, i
 #undef LSS_FLUSH
 }
 
+template <int NT = SPLAT_THREADS>
 __device__ __forceinline__ void zero_smem(float *buf, int n_floats) {
     float4 *z = reinterpret_cast<float4 *>(buf);
-    for (int i = threadIdx.x; i < (n_floats >> 2); i += SPLAT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < (n_floats >> 2); i += NT) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // One CTA per tile, LSU stores.  Generic path: any shape / alignment.
@@ -444,8 +445,8 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
 // transposed into a zero-filled shared-memory tile, which is written out with 16-byte stores.  Every BEV
 // element is written exactly once, zeros included.  (A variant without the staging tile -- zeros from
 // registers, non-empty slots looked up through a column map -- was measured slower: 28 us vs 19 us.)
-template <bool CL, bool VEC4>
-__global__ void __launch_bounds__(SPLAT_THREADS)
+template <bool CL, bool VEC4, int NT>
+__global__ void __launch_bounds__(NT)
 k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
             const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
             float *__restrict__ bev) {
@@ -460,10 +461,10 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
       else { t2.NR = ch; t2.gbase += (size_t)c0 * t2.GRS; } }
     const int nseg = CH < 0 ? 0 : __ldg(tile_nseg + tile);      // CH < 0: measurement aid, zero tiles only
     if (CH < 0) CH = -CH;
-    if (nseg == 0) { store_tile<VEC4>(t2, nullptr, bev); if (blockIdx.y == 0) lss_stamp(tile, 3); return; }
+    if (nseg == 0) { store_tile<VEC4, NT>(t2, nullptr, bev); if (blockIdx.y == 0) lss_stamp(tile, 3); return; }
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
     const int C = d.C, c4 = CH >> 2;                      // C % 4 == 0 and CH % 4 == 0 on this path
-    const int per_pass = SPLAT_THREADS / c4;              // rows per pass
+    const int per_pass = NT / c4;              // rows per pass
     const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
     if (blockIdx.y == 0) lss_stamp(tile, 1);
     // PDL: everything above reads plan data only (written by earlier, completed launches); the compact rows come
@@ -477,7 +478,7 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
         col0 = (int)(__ldg(segs + s + r0) >> LSS_PIDX_BITS);
         v0 = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + r0) * C + c0) + q);
     }
-    zero_smem(smem, CL ? tl.TY * CH : CH * t2.SRS);
+    zero_smem<NT>(smem, CL ? tl.TY * CH : CH * t2.SRS);
     __syncthreads();
     if (r0 < per_pass) {
         for (int r = r0; r < nseg; r += per_pass) {
@@ -497,7 +498,7 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
     }
     __syncthreads();
     if (blockIdx.y == 0) lss_stamp(tile, 2);
-    store_tile<VEC4>(t2, smem, bev);
+    store_tile<VEC4, NT>(t2, smem, bev);
     if (blockIdx.y == 0) lss_stamp(tile, 3);
     if (threadIdx.x == 0 && blockIdx.y == 0 && g_lss_timeline != nullptr) g_lss_timeline[(size_t)tile * 8 + 7] = nseg;
 }
@@ -1083,7 +1084,19 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
     if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
     const size_t smem = (size_t)(CL ? tl.TY * CH : CH * (tl.TY + 4)) * 4;
-    auto kern = k_fwd_store<CL, VEC4>;
+    static int nt512 = getenv("LSS_STORE_NT") ? atoi(getenv("LSS_STORE_NT")) == 512 : 0;                 // tuning knob
+    if (nt512) {
+        auto kern5 = k_fwd_store<CL, VEC4, 512>;
+        static bool configured5 = false;
+        int st5 = opt_in_smem(kern5, smem, configured5);
+        if (st5 != LSS_OK) return st5;
+        const int tps5 = tl.n_tiles / d.B;
+        if (lss_launch(kern5, dim3((b1 - b0) * tps5, d.C / CH), dim3(512), smem, s, pdl, d, tl, b0 * tps5, CH,
+                       pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
+        LSS_CHECK_LAUNCH();
+        return LSS_OK;
+    }
+    auto kern = k_fwd_store<CL, VEC4, SPLAT_THREADS>;
     static bool configured = false;
     int st = opt_in_smem(kern, smem, configured);
     if (st != LSS_OK) return st;
