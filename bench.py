@@ -250,7 +250,9 @@ class BufferSet:
 
 STAGES = ("calib", "plan_build", "lift_prepare", "splat_fwd", "splat_bwd")
 NO_OVERLAP = bool(os.environ.get("LSS_BENCH_NO_OVERLAP"))
-NO_FUSED_CALIB = bool(os.environ.get("LSS_BENCH_NO_FUSED_CALIB"))
+# calibration inverses inside k_voxel_index (lss_plan_build_raw) vs k_calib_matrices + programmatic dependent launch of
+# k_voxel_index: measured 2953 vs 2989 Mpoints/s at cfg 2 -> the separate tiny kernel stays the default
+NO_FUSED_CALIB = not bool(os.environ.get("LSS_BENCH_FUSED_CALIB"))
 # sample-range pipelining of gather/store on two streams: measured slower at cfg 2 (2 parts: 2404, 4 parts: 1868 vs 2876
 # Mpoints/s unsplit) -- every kernel already fills the GPU, smaller launches only add tails -- so it stays off
 PARTS = 1 if NO_OVERLAP else int(os.environ.get("LSS_BENCH_PARTS", "1"))

@@ -122,7 +122,10 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
               int32_t *__restrict__ tile_count, int32_t *__restrict__ tile_start, int32_t *__restrict__ cursor,
               int32_t *__restrict__ sync, int32_t *__restrict__ counters, int32_t *__restrict__ key_count,
               int32_t *__restrict__ prow) {
-    if (COUNT) lss_pdl_trigger();                  // the scatter kernel may be scheduled while this grid drains
+    if (COUNT) {
+        lss_pdl_trigger();                         // the scatter kernel may be scheduled while this grid drains
+        if (!RAW && !FROM_GEOM) lss_pdl_wait();    // M1 / M2 may come from k_calib_matrices right before this launch
+    }
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < d.n_points;
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
@@ -599,7 +602,7 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
 #define VI_ARGS d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count, tile_start, cursor, sync, counters, key_count, prow
     if (geom != nullptr) k_voxel_index<true, true><<<grid, 256, 0, s>>>(VI_ARGS);
     else if (raw) k_voxel_index<false, true, true><<<grid, 256, 0, s>>>(VI_ARGS);
-    else k_voxel_index<false, true><<<grid, 256, 0, s>>>(VI_ARGS);
+    else if (lss_launch(k_voxel_index<false, true, false>, dim3(grid), dim3(256), 0, s, true, VI_ARGS) != cudaSuccess) return LSS_ERR_CUDA;
 #undef VI_ARGS
     LSS_CHECK_LAUNCH();
     if (lss_launch(k_plan_scatter, dim3(grid), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess) return LSS_ERR_CUDA;
