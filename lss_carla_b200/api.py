@@ -12,6 +12,8 @@ closed-form inverse kernel (no LAPACK call, graph-capturable).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import models, ops
@@ -20,7 +22,7 @@ from .tools import gen_dx_bx
 
 class LiftSplat:
     def __init__(self, grid_conf, data_aug_conf, C=64, downsample=16, splat_mode="sorted",
-                 inverse_mode="reference", bev_channels_last=False, device="cuda:0", tile_cols=0):
+                 inverse_mode="reference", bev_channels_last=False, device="cuda:0", tile_cols=0, copy_streams=False):
         self.device = torch.device(device)
         dx, bx, nx = gen_dx_bx(grid_conf["xbound"], grid_conf["ybound"], grid_conf["zbound"])
         self.dx, self.bx, self.nx = dx, bx, nx
@@ -35,18 +37,49 @@ class LiftSplat:
         self.D, self.camC = ds.shape[0], C
         self.splat_mode, self.inverse_mode, self.bev_channels_last = splat_mode, inverse_mode, bev_channels_last
         self.tile_cols = tile_cols
+        self._up = self._down = None
+        self.copy_streams = bool(copy_streams or os.environ.get("LSS_API_COPY_STREAMS"))
 
     def _dev(self, t):
         return t if t.is_cuda else t.to(self.device, non_blocking=True)
 
-    upload = _dev
+    _BIG = 1 << 18     # elements: only transfers of this size are worth a second stream (event hand-offs cost host time)
+
+    def upload(self, t):
+        """Device copy of a (pinned) host tensor on the current stream.  With `copy_streams=True` large tensors go
+        through a dedicated copy stream (upload of the next call next to the kernels of the previous one); measured
+        on B200 this is SLOWER for this call sequence (952 vs 1177 Mpoints/s end to end at cfg 2), so it is off."""
+        if t.is_cuda:
+            return t
+        if t.numel() < self._BIG or not self.copy_streams:
+            return t.to(self.device, non_blocking=True)
+        if self._up is None:
+            self._up, self._down = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._up):
+            d = t.to(self.device, non_blocking=True)
+        cur.wait_stream(self._up)
+        d.record_stream(cur)
+        return d
 
     def download(self, t, out):
-        """Stream-ordered copy of a device result into the (pinned) host tensor `out`; synchronise before reading.
-        (Measured on B200: dedicated upload/download streams with event hand-offs make this host-bound call
-        sequence slower -- 695 vs ~850 Mpoints/s end to end at cfg 2 -- so everything stays on the current stream.)"""
-        out.copy_(t, non_blocking=True)
+        """Copy a device result into the (pinned) host tensor `out`; large results leave through a dedicated copy
+        stream that waits for the current one, so the copy overlaps whatever is enqueued next.  Synchronise the
+        device (or `sync_downloads()`) before reading `out`."""
+        if t.numel() < self._BIG or not self.copy_streams:
+            out.copy_(t, non_blocking=True)
+            return out
+        if self._down is None:
+            self._up, self._down = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+        self._down.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._down):
+            out.copy_(t, non_blocking=True)
+        t.record_stream(self._down)
         return out
+
+    def sync_downloads(self):
+        if self._down is not None:
+            self._down.synchronize()
 
     def __call__(self, depthnet_out, rots, trans, intrins, post_rots, post_trans, plan=None):
         B, N = trans.shape[:2]
