@@ -514,7 +514,8 @@ def main():
     step_s = elapsed / args.steps
     if args.mode == "sorted":
         # dominant HBM-bound kernel: k_fwd_store writes every BEV element once (G) and reads the compact voxel rows
-        kname, kbytes, ksec = "k_fwd_store", G + 4 * cfg.C * v_hit, stages["k_fwd_store"]
+        kname = "k_fwd_store_rows" if not channels_last else "k_fwd_store_tma"
+        kbytes, ksec = G + 4 * cfg.C * v_hit, stages["k_fwd_store"]
     else:
         kname = {"atomic": "k_splat_fwd_tile (shared-memory atomics)", "red": "memset + k_splat_fwd_red"}[args.mode]
         kbytes, ksec = fwd_bytes, stages["splat_fwd"]

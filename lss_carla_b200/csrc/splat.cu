@@ -503,6 +503,67 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
     if (threadIdx.x == 0 && blockIdx.y == 0 && g_lss_timeline != nullptr) g_lss_timeline[(size_t)tile * 8 + 7] = nseg;
 }
 
+// (2a) k_fwd_store_rows -- NCHW, 16-byte aligned rows: the same streaming store WITHOUT a staging tile.  All C channel
+// rows of a tile share one hit pattern (the tile's non-empty columns), so every lane resolves its two 16-byte slots
+// ONCE -- which compact row, if any, feeds each of its 8 columns -- and then walks the channels: a slot without a
+// hit is a zero store straight from registers, the others read the tile's compact rows, which are staged in
+// shared memory (a few KB, odd stride).  Shared memory per CTA drops from 52 KB to ~8 KB, so the SM runs its full
+// complement of CTAs, and the 51 KB zero-fill / read-back of the staging tile disappears.
+#define ROWS_CAP 64      // compact rows staged in shared memory (tiles with more non-empty columns read the rest from global)
+#ifndef STORE_ROWS_MINB
+#define STORE_ROWS_MINB 4       // 6 (40 registers, spills) measured no better
+#endif
+__global__ void __launch_bounds__(SPLAT_THREADS, STORE_ROWS_MINB)
+k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
+                 const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
+                 float *__restrict__ bev) {
+    extern __shared__ __align__(16) float s_rows[];               // [ROWS_CAP][C + 1], then short map[TY rounded to 8]
+    const int tile = tile_lo + blockIdx.x;
+    const TileCoord tc = tile_coord(d, tl, tile);
+    const Tile2D t2 = tile_2d<false>(d, tl, tc);
+    const int nseg = __ldg(tile_nseg + tile);
+    if (nseg == 0) { lss_pdl_wait(); store_tile<true>(t2, nullptr, bev); return; }
+    const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
+    const int C = d.C, SR = C + 1, c4 = C >> 2;
+    short *s_map = reinterpret_cast<short *>(s_rows + ROWS_CAP * SR + (ROWS_CAP & 1));
+    for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = threadIdx.x; k < nseg; k += SPLAT_THREADS) s_map[__ldg(segs + s + k) >> LSS_PIDX_BITS] = (short)k;
+    lss_pdl_wait();                                               // the compact rows come from the gather kernel
+    const int nst = min(nseg, ROWS_CAP);
+    for (int i = threadIdx.x; i < nst * c4; i += SPLAT_THREADS) { // coalesced: the tile's rows are one block
+        const int k = i / c4, q = i - k * c4;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + k) * C) + q);
+        float *dst = s_rows + k * SR + 4 * q;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vpr = t2.RL >> 2;                                   // 16-byte slots per channel row (<= 64 handled per lane pair)
+    const float *rows_g = vsum + (size_t)row0 * C;
+    for (int v0 = lane; v0 < vpr; v0 += 32) {                     // usually 2 slots per lane
+        const uint2 m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
+        const int k0 = (short)(m.x & 0xFFFFu), k1 = (short)(m.x >> 16), k2 = (short)(m.y & 0xFFFFu), k3 = (short)(m.y >> 16);
+        float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
+        const size_t gstep = (size_t)SPLAT_WARPS * t2.GRS / 4;
+        if (nseg <= ROWS_CAP) {                                   // CTA-uniform: every compact row is staged
+            // one loop for all lanes (no divergence between lanes with and without hits): predicated shared loads
+            const float *p0 = s_rows + max(k0, 0) * SR, *p1 = s_rows + max(k1, 0) * SR;
+            const float *p2 = s_rows + max(k2, 0) * SR, *p3 = s_rows + max(k3, 0) * SR;
+#pragma unroll 4
+            for (int c = warp; c < C; c += SPLAT_WARPS, gp += gstep) {
+                float4 o;
+                o.x = k0 >= 0 ? p0[c] : 0.f; o.y = k1 >= 0 ? p1[c] : 0.f;
+                o.z = k2 >= 0 ? p2[c] : 0.f; o.w = k3 >= 0 ? p3[c] : 0.f;
+                *gp = o;
+            }
+        } else {
+            auto val = [&](int k, int c) { return k < 0 ? 0.f : (k < ROWS_CAP ? s_rows[k * SR + c] : __ldg(rows_g + (size_t)k * C + c)); };
+            for (int c = warp; c < C; c += SPLAT_WARPS, gp += gstep) *gp = make_float4(val(k0, c), val(k1, c), val(k2, c), val(k3, c));
+        }
+    }
+}
+
 // (2b) k_fwd_store_tma -- the same streaming store as a PERSISTENT kernel: every CTA walks tiles with two staging
 // buffers.  The rows of the staged tile leave through the bulk-copy engine (cp.async.bulk shared -> global, issued by
 // one warp), so the CTA does not wait for its stores: while tile k drains it zero-fills the other buffer and
@@ -517,7 +578,7 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool CL>
+template <bool CL, bool USE_TMA = true>
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__restrict__ tile_start,
                 const int32_t *__restrict__ tile_nseg, const int32_t *__restrict__ tile_row0,
@@ -552,13 +613,13 @@ k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__re
     prefetch(blockIdx.x);
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        float *buf = smem + (it & 1) * tile_floats;
+        float *buf = smem + (USE_TMA ? (it & 1) * tile_floats : 0);
         const int nseg = n_nseg, s = n_s, row0 = n_row0;
         const int col[2] = {n_col[0], n_col[1]};
         const float4 v[2] = {n_v[0], n_v[1]};
         prefetch(t + gridDim.x);                          // dependent loads of the next tile start now
-        if (threadIdx.x < 32) bulk_wait_read<1>();        // this buffer was handed to the copy engine two tiles ago
-        __syncthreads();
+        if (USE_TMA && threadIdx.x < 32) bulk_wait_read<1>();   // this buffer was handed to the copy engine two tiles ago
+        __syncthreads();                                  // (LSU variant: everybody has read the previous tile)
         zero_smem(buf, tile_floats);
         __syncthreads();
         if (loader) {
@@ -576,9 +637,28 @@ k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__re
                 }
             }
         }
-        fence_async_smem();                               // generic-proxy writes -> visible to the async proxy
+        if (USE_TMA) fence_async_smem();                  // generic-proxy writes -> visible to the async proxy
         __syncthreads();
-        if (threadIdx.x < 32) {
+        if (!USE_TMA) {                                   // persistent LSU variant: ordinary 16-byte stores
+            const TileCoord tc = tile_coord(d, tl, tile_lo + t);
+            const Tile2D t2 = tile_2d<CL>(d, tl, tc);
+            if (true) {                                   // store_tile may return early for idle lanes: keep it last
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                const int vpr = t2.RL >> 2;
+                const int rpw = vpr >= 32 ? 1 : 32 / vpr;
+                const int sub = rpw == 1 ? 0 : lane / vpr;
+                const int v0 = rpw == 1 ? lane : lane - sub * vpr;
+                if (sub < rpw) {
+                    const int rowa = warp * rpw + sub, rstep = SPLAT_WARPS * rpw;
+                    float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)rowa * t2.GRS) + v0;
+                    const size_t gstep = (size_t)rstep * t2.GRS / 4;
+                    const float4 *sp = reinterpret_cast<const float4 *>(buf + rowa * SRS) + v0;
+                    const int sstep = rstep * SRS / 4;
+                    for (int row = rowa; row < t2.NR; row += rstep, gp += gstep, sp += sstep)
+                        for (int v = v0; v < vpr; v += 32) gp[v - v0] = sp[v - v0];
+                }
+            }
+        } else if (threadIdx.x < 32) {
             const TileCoord tc = tile_coord(d, tl, tile_lo + t);
             const Tile2D t2 = tile_2d<CL>(d, tl, tc);
             float *g = bev + t2.gbase;
@@ -590,7 +670,7 @@ k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__re
             bulk_commit();                                // one group per tile and lane (possibly empty)
         }
     }
-    if (threadIdx.x < 32) bulk_wait_all();
+    if (USE_TMA && threadIdx.x < 32) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1084,6 +1164,16 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
     if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
     const size_t smem = (size_t)(CL ? tl.TY * CH : CH * (tl.TY + 4)) * 4;
+    // NCHW with 16-byte rows: the staging-free kernel (36.1 vs 37.9 us forward at cfg 2); LSS_STORE_ROWS=0 switches it off
+    static int rows_mode = getenv("LSS_STORE_ROWS") ? atoi(getenv("LSS_STORE_ROWS")) : 1;
+    if (rows_mode && !CL && VEC4 && CH == d.C && getenv("LSS_STORE_ZERO") == nullptr && tl.TY <= 32767) {
+        const size_t rsm = (size_t)(ROWS_CAP * (d.C + 1) + 1) * 4 + (size_t)((tl.TY + 7) / 8) * 16;
+        const int tpsr = tl.n_tiles / d.B;
+        if (lss_launch(k_fwd_store_rows, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
+                       pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
+        LSS_CHECK_LAUNCH();
+        return LSS_OK;
+    }
     static int nt512 = getenv("LSS_STORE_NT") ? atoi(getenv("LSS_STORE_NT")) == 512 : 0;                 // tuning knob
     if (nt512) {
         auto kern5 = k_fwd_store<CL, VEC4, 512>;
@@ -1108,12 +1198,12 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     return LSS_OK;
 }
 
-template <bool CL>
+template <bool CL, bool USE_TMA>
 static int launch_fwd_store_tma(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
                                 cudaStream_t s) {
     const int tile_floats = CL ? tl.TY * d.C : d.C * (tl.TY + 4);
-    const size_t smem = (size_t)2 * tile_floats * 4;
-    auto kern = k_fwd_store_tma<CL>;
+    const size_t smem = (size_t)(USE_TMA ? 2 : 1) * tile_floats * 4;
+    auto kern = k_fwd_store_tma<CL, USE_TMA>;
     static bool configured = false;
     int st = opt_in_smem(kern, smem, configured);
     if (st != LSS_OK) return st;
@@ -1160,8 +1250,11 @@ store:
         static int tma_mode = getenv("LSS_STORE_TMA") ? atoi(getenv("LSS_STORE_TMA")) : -1;
         const size_t tma_smem = (size_t)2 * (cl ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
         const bool want = tma_mode < 0 ? (cl && d.nz == 1) : tma_mode > 0;
-        if (want && vec4 && tma_smem <= 227 * 1024 && (cl || tl.nty == 1 || tl.TY % 4 == 0))
-            return cl ? launch_fwd_store_tma<true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false>(d, tl, pp, vsum, bev, b0, b1, s);
+        if (want && vec4 && tma_smem <= 227 * 1024 && (cl || tl.nty == 1 || tl.TY % 4 == 0)) {
+            if (tma_mode == 2)      // persistent CTAs with prefetch, ordinary stores (experiment)
+                return cl ? launch_fwd_store_tma<true, false>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false, false>(d, tl, pp, vsum, bev, b0, b1, s);
+            return cl ? launch_fwd_store_tma<true, true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false, true>(d, tl, pp, vsum, bev, b0, b1, s);
+        }
     }
     const bool pdl = variant != LSS_VARIANT_GROUP_STORE;  // only right behind its gather
     if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
