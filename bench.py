@@ -351,6 +351,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-inverse", default="device", choices=["device", "reference"])
+    ap.add_argument("--e2e-streams", type=int, default=4)
+    ap.add_argument("--no-e2e-graph", dest="e2e_graph", action="store_false", help="e2e through eager LiftSplat.__call__ instead of StepGraph")
     ap.add_argument("--metric", default="pool", choices=["pool", "train"],
                     help="pool: BEV-pool Mpoints/s fwd+bwd (headline); train: LSS training samples/s")
     ap.add_argument("--splat", default="ours", choices=["ours", "aten"], help="--metric train: lift-splat implementation")
@@ -450,12 +452,40 @@ def main():
         ls.download(x.grad, h["grad_out"])
         ls.download(bev.detach().reshape(-1)[:1024], h["probe"])
 
+    e2e_api = (f"lss_carla_b200.api.LiftSplat.__call__ + autograd backward + LiftSplat.download; inverse_mode={args.e2e_inverse}; "
+               "stream-ordered pinned H2D/D2H copies inside the timed region")
+    if args.e2e_graph and args.e2e_inverse == "device":
+        # the same step as one CUDA graph per pinned buffer set, replayed alternately on two streams: the copies of one
+        # step overlap the kernels of its neighbour; every replay still moves that step's inputs H2D and results D2H
+        streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(args.e2e_streams, len(pinned))))]
+        sgraphs = [api.StepGraph(ls, pinned[i], sets[i].grad_bev, streams[i % len(streams)]) for i in range(len(pinned))]
+        e2e_api = ("lss_carla_b200.api.StepGraph.replay (H2D of the step's pinned inputs + plan + lift-splat fwd/bwd + D2H of the "
+                   f"input gradient and a BEV probe, one CUDA graph per buffer set, round-robin on {len(streams)} streams)")
+
+        def e2e_step(i):       # noqa: F811
+            sgraphs[i % len(sgraphs)].replay()
+
+        def fork():
+            for st in streams:
+                st.wait_stream(torch.cuda.current_stream())
+
+        def join():
+            for st in streams:
+                torch.cuda.current_stream().wait_stream(st)
+    else:
+        def fork():
+            pass
+
+        def join():
+            pass
     for i in range(args.warmup):
         e2e_step(i)
     barrier()
     e0.record()
+    fork()
     for i in range(e2e_steps):
         e2e_step(i)
+    join()
     e1.record()
     barrier()
     e2e_elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
@@ -555,8 +585,7 @@ def main():
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": round(e2e_elapsed / e2e_steps * 1e3, 4),
-                    "api": f"lss_carla_b200.api.LiftSplat.__call__ + autograd backward + LiftSplat.download; inverse_mode={args.e2e_inverse}; "
-                           "stream-ordered pinned H2D/D2H copies inside the timed region"},
+                    "api": e2e_api},
             "gpu_launches": (LAUNCHES_PER_STEP[args.mode] - (1 if (args.inverse == "device" and not NO_FUSED_CALIB) else 0)) * args.steps,
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

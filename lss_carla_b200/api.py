@@ -99,3 +99,57 @@ class LiftSplat:
                 plan = models.plan_from_calibration(self, prob, self._dev(rots), self._dev(trans), self._dev(intrins),
                                                     self._dev(post_rots), self._dev(post_trans))
         return ops.lift_splat(self._dev(depthnet_out), prob, plan, self.splat_mode, self.bev_channels_last)
+
+
+class StepGraph:
+    """One lift-splat forward + backward as a CUDA graph bound to a set of PINNED host buffers.
+
+        g = StepGraph(ls, host, grad_bev, stream)      # host: dict of pinned tensors, see below
+        ...write the next batch into host["depthnet_out"], host["rots"], ... ; g.replay() ; later: stream.synchronize()
+
+    Every replay copies the step's inputs host -> device, builds the plan (device inverse mode), runs lift + splat,
+    the backward against `grad_bev` (a device tensor, e.g. what BevEncode's backward produced) and copies the input
+    gradient and a probe of the BEV back into host["grad_out"] / host["probe"] -- all as nodes of one graph, so the
+    host pays one launch per step and graphs replayed on different streams overlap their copies with each other's
+    kernels.  Keys of `host`: depthnet_out, rots, trans, intrins, post_rots, post_trans, grad_out, probe."""
+
+    def __init__(self, ls: LiftSplat, host: dict, grad_bev, stream=None):
+        if ls.inverse_mode != "device":
+            raise ValueError("StepGraph needs inverse_mode='device' (the LAPACK inverse of the reference mode runs on the host)")
+        self.ls, self.host, self.stream = ls, host, stream or torch.cuda.Stream(device=ls.device)
+        B, N = host["trans"].shape[:2]
+        fH, fW = host["depthnet_out"].shape[-2:]
+        prob = models._problem_for(ls, B, N, fH, fW, host["depthnet_out"].shape[1] - ls.D)
+        ws = ops.Plan(prob, ls.device, ls.tile_cols)       # a workspace of its own: graphs may overlap
+        dev = ls.device
+
+        vsum = torch.empty((ws.layout.n_rows_cap, prob.C), dtype=torch.float32, device=dev)
+        rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=dev)
+        self._keep = (ws, vsum, rows)
+
+        def step():
+            # the kernels are called directly (no autograd graph inside the capture): forward, then the backward
+            # of lift+splat against `grad_bev`, exactly what _LiftSplatFn.forward / backward do
+            x = host["depthnet_out"].to(dev, non_blocking=True)
+            cal = [host[k].to(dev, non_blocking=True) for k in ("rots", "trans", "intrins", "post_rots", "post_trans")]
+            plan = ops.build_plan_raw(prob, ls.frustum, *cal, sorted=(ls.splat_mode == "sorted"), plan=ws)
+            pr, ct = ops.lift_prepare(prob, x)
+            bev = ops.splat_fwd(prob, plan, pr, ct, ls.splat_mode, ls.bev_channels_last, voxel_sums=vsum)
+            grad = ops.splat_bwd(prob, plan, grad_bev, pr, ct, rows)
+            host["grad_out"].copy_(grad, non_blocking=True)
+            host["probe"].copy_(bev.reshape(-1)[: host["probe"].numel()], non_blocking=True)
+
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            for _ in range(3):
+                step()
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.pool = torch.cuda.graph_pool_handle()      # a memory pool of its own: graphs replay concurrently
+        with torch.cuda.graph(self.graph, pool=self.pool, stream=self.stream):
+            step()
+        self.stream.synchronize()
+
+    def replay(self):
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
