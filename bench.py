@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--e2e-inverse", default="device", choices=["device", "reference"])
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--no-e2e-graph", dest="e2e_graph", action="store_false", help="e2e through eager LiftSplat.__call__ instead of StepGraph")

@@ -510,3 +510,36 @@ def test_model_install_style_get_voxels():
     # host LAPACK bits may depend on the box's BLAS code path -> closeness here; bit-exactness given
     # (M1, M2) is covered by test_geometry_and_voxel_index_bit_exact
     np.testing.assert_allclose(geom.cpu().numpy(), g["geom"], rtol=1e-6, atol=1e-5)
+
+
+def test_step_graph_matches_eager_api_and_overlaps_safely():
+    """api.StepGraph (H2D + plan + fwd/bwd + D2H captured per pinned buffer set) == eager LiftSplat + autograd, also when
+    several graphs replay concurrently on different streams."""
+    from lss_carla_b200 import api
+    cfg = CONFIGS["cfg1"]
+    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, inverse_mode="device", device=dev())
+    gb = make_bev_grad(cfg, 0).to(dev())
+
+    def host_set(seed):
+        b = make_batch(cfg, seed, "train")
+        h = {k: b[k].pin_memory() for k in ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans")}
+        h["grad_out"] = torch.empty_like(h["depthnet_out"]).pin_memory()
+        h["probe"] = torch.empty(2048).pin_memory()
+        return h
+
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    hs = [host_set(i) for i in range(3)]
+    gs = [api.StepGraph(ls, hs[i], gb, streams[i % 2]) for i in range(3)]
+    for _ in range(5):
+        for g in gs:
+            g.replay()
+    torch.cuda.synchronize()
+    for h in hs:
+        x = h["depthnet_out"].to(dev()).requires_grad_(True)
+        bev = ls(x, *[h[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans")])
+        bev.backward(gb)
+        torch.cuda.synchronize()
+        assert torch.equal(x.grad.cpu(), h["grad_out"])
+        assert torch.equal(bev.detach().reshape(-1)[:2048].cpu(), h["probe"])
+    with pytest.raises(ValueError):
+        api.StepGraph(api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, device=dev()), hs[0], gb)
