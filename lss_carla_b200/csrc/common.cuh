@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <math.h>
 
 #include "../../include/lss_b200.h"
 
@@ -68,6 +69,7 @@ struct Dims {
     int P;         // points per sample N*D*fH*fW
     int n_points;  // B*P
     float dx[3], lo[3];
+    float inv_dx[3];   // 1/dx where dx is a power of two (x / dx == x * (1/dx) bit for bit), else 0: true division
     unsigned long long mDHW, mHW;   // ceil(2^40 / DHW), ceil(2^40 / HW): exact division of a 20-bit point index
 };
 
@@ -84,7 +86,12 @@ static inline Dims make_dims(const lss_problem *p) {
     d.DHW = p->D * d.HW;
     d.P = p->N * d.DHW;
     d.n_points = p->B * d.P;
-    for (int k = 0; k < 3; ++k) { d.dx[k] = p->dx[k]; d.lo[k] = p->lo[k]; }
+    for (int k = 0; k < 3; ++k) {
+        d.dx[k] = p->dx[k]; d.lo[k] = p->lo[k];
+        int e = 0;
+        const float m = frexpf(p->dx[k], &e);          // dx = m * 2^e, m in [0.5, 1)
+        d.inv_dx[k] = (m == 0.5f && e > -100 && e < 100) ? 1.0f / p->dx[k] : 0.0f;
+    }
     d.mDHW = ((1ull << 40) + (unsigned)d.DHW - 1) / (unsigned)d.DHW;
     d.mHW = ((1ull << 40) + (unsigned)d.HW - 1) / (unsigned)d.HW;
     return d;

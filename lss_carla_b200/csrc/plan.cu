@@ -47,16 +47,18 @@ __device__ __forceinline__ void ego_point(const CalibPtrs &c, int cam, int in_ca
 }
 
 // ((g - lo) / dx).long()  with x86 semantics for values a 64-bit integer cannot hold (models.py:212)
-__device__ __forceinline__ long long quantise(float g, float lo, float dx) {
-    const float u = __fdiv_rn(__fsub_rn(g, lo), dx);
+__device__ __forceinline__ long long quantise(float g, float lo, float dx, float inv_dx) {
+    // a power-of-two voxel size divides exactly like a multiplication by its reciprocal (same bits, no IEEE division)
+    const float t = __fsub_rn(g, lo);
+    const float u = inv_dx != 0.0f ? __fmul_rn(t, inv_dx) : __fdiv_rn(t, dx);
     if (!(fabsf(u) < 9223372036854775808.0f)) return (long long)0x8000000000000000ULL;  // NaN, inf, overflow
     return __float2ll_rz(u);
 }
 
 __device__ __forceinline__ int voxel_of_point(const Dims &d, int b, const float g[3], long long ii[3]) {
-    ii[0] = quantise(g[0], d.lo[0], d.dx[0]);
-    ii[1] = quantise(g[1], d.lo[1], d.dx[1]);
-    ii[2] = quantise(g[2], d.lo[2], d.dx[2]);
+    ii[0] = quantise(g[0], d.lo[0], d.dx[0], d.inv_dx[0]);
+    ii[1] = quantise(g[1], d.lo[1], d.dx[1], d.inv_dx[1]);
+    ii[2] = quantise(g[2], d.lo[2], d.dx[2], d.inv_dx[2]);
     const bool kept = ii[0] >= 0 && ii[0] < d.nx && ii[1] >= 0 && ii[1] < d.ny && ii[2] >= 0 && ii[2] < d.nz;  // :219-221
     if (!kept) return -1;
     return ((b * d.nz + (int)ii[2]) * d.nx + (int)ii[0]) * d.ny + (int)ii[1];
