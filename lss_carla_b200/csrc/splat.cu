@@ -25,6 +25,9 @@
 #define SPLAT_THREADS 256
 #define SPLAT_WARPS (SPLAT_THREADS / 32)
 #define GATHER_THREADS 128
+#ifndef QUEUE_FIRST
+#define QUEUE_FIRST 1
+#endif
 
 // Debug hook (lss_debug_set_timeline): when set, CTAs of the forward kernel stamp %globaltimer at their
 // phase boundaries into this buffer, 8 x u64 per tile.  Null in production: one uniform branch per phase.
@@ -311,8 +314,14 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
     lss_pdl_trigger();                                   // PDL: the store kernel may start its prologue in our tail
-    const bool column = (int)blockIdx.x < n_keys;        // else: a CTA of the mixed-voxel queue (group per voxel, all
-    const int key = column ? key_lo + (int)blockIdx.x : 0;   // operands from global memory); measured: a warp per mixed
+    // The FIRST CTAs of the grid drain the queue of mixed voxels (group per voxel, all operands from global memory):
+    // they start at once, live a few microseconds and hand their slots to the column CTAs that did not fit the first
+    // wave, instead of forming the tail of the kernel.
+    const int n_queue = (int)gridDim.x - n_keys, qfirst = QUEUE_FIRST ? n_queue : 0;
+    const int bid = QUEUE_FIRST ? ((int)blockIdx.x < n_queue ? n_keys + (int)blockIdx.x : (int)blockIdx.x - n_queue) : (int)blockIdx.x;
+    (void)qfirst;
+    const bool column = bid < n_keys;                    // (measured: a warp per mixed voxel -- 16 rows in flight, sum
+    const int key = column ? key_lo + bid : 0;           // handed on by shuffle -- is slower than a group per voxel)
     lss_stamp<true>(blockIdx.x, 0);                      // voxel (16 rows in flight, sum handed on by shuffle) is slower
     const int n_rec = column ? __ldg(key_count + key) : __ldg(counters + 1);
     const int w0 = column ? key % d.fW : -1, bn = key / d.fW;
@@ -339,7 +348,7 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
     const int gl = lane & 7;
     const float *s_ctx = s_col + gl * 4;                 // lane gl: float4 slots gl, gl+8, ...
     const int stride = column ? NG : NG * ((int)gridDim.x - n_keys);
-    int r = (column ? 0 : NG * ((int)blockIdx.x - n_keys)) + (threadIdx.x >> 3);
+    int r = (column ? 0 : NG * (bid - n_keys)) + (threadIdx.x >> 3);
     // software pipeline over the group's records: the record and the first 8 entries of the NEXT voxel are
     // requested before the current one is consumed.  All shuffles use the full mask (a lane-dependent mask
     // costs a MATCH per shuffle), so every loop below is warp-uniform and the groups are predicated.
