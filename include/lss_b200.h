@@ -105,7 +105,9 @@ typedef struct lss_plan_layout {
     size_t off_prow;        /* int32 [B,N,fW,D,fH] sorted plans: compact row of the point's voxel, -1 */
                             /*                    for dropped points, camera-column major (backward) */
     size_t off_counters;    /* int32 [64]         [0] = non-empty voxels of the batch (rows in use), */
-                            /*                    [1] = records in mixed_recs                        */
+                            /*                    [1] = records in mixed_recs, [2] = records of long */
+                            /*                    voxels (>= 64 points), stored from the END of      */
+                            /*                    mixed_recs downwards                               */
     int64_t n_rows_cap;     /* min(n_points, B*nx*ny*nz): capacity of the voxel_sums workspace       */
     size_t off_tile_count;  /* int32 [n_tiles]    scratch, all-zero between calls                    */
     size_t off_cursor;      /* int32 [n_tiles]    scratch                                            */

@@ -13,6 +13,7 @@
 #define LSS_MAX_TILE_COLS 4096               // 12 bits of column per entry
 #define LSS_MAX_DEPTH 256                    // fused backward keeps per-depth state in registers
 #define LSS_MAX_CHANNELS 256
+#define LSS_LONG_VOXEL 64                    // voxels with at least this many points are summed by a whole CTA
 
 #define LSS_CHECK_LAUNCH()                                                \
     do {                                                                  \

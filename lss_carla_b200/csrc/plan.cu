@@ -217,7 +217,7 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
         __syncthreads();
     }
     for (int i = threadIdx.x; i < d.B * d.N * d.fW; i += blockDim.x) key_count[i] = 0;
-    if (threadIdx.x == 0) { tile_start[tl.n_tiles] = s_carry; *sync = 0; counters[0] = 0; counters[1] = 0; }
+    if (threadIdx.x == 0) { tile_start[tl.n_tiles] = s_carry; *sync = 0; counters[0] = 0; counters[1] = 0; counters[2] = 0; }
 }
 
 // Scatter kept points into their tile buckets: entries[tile_start[t] + k] = col << 20 | point-in-sample.
@@ -338,7 +338,11 @@ __device__ __forceinline__ int block_enumerate(int L, int *s_warp, Flag flag, Em
 __device__ __forceinline__ void emit_voxel_record(const Dims &d, int b, uint32_t first_entry, int kind, int e0,
                                                   int len, int row, int4 *__restrict__ seg_recs,
                                                   int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
-                                                  int32_t *__restrict__ counters) {
+                                                  int32_t *__restrict__ counters, long long n_rows_cap) {
+    if (len >= LSS_LONG_VOXEL) {                   // long voxels: their own queue, filled from the END of mixed_recs
+        mixed_recs[n_rows_cap - 1 - atomicAdd(counters + 2, 1)] = make_int4(e0, len, b, row);
+        return;
+    }
     if (kind == 2) {
         mixed_recs[atomicAdd(counters + 1, 1)] = make_int4(e0, len, b, row);
         return;
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(LSS_SORT_THREADS)
 k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries,
             uint32_t *__restrict__ segs, int32_t *__restrict__ tile_nseg, int32_t *__restrict__ tile_row0,
             int4 *__restrict__ seg_recs, int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
-            int32_t *__restrict__ counters, int32_t *__restrict__ prow) {
+            int32_t *__restrict__ counters, int32_t *__restrict__ prow, long long n_rows_cap) {
     extern __shared__ int s_int[];                 // start[TY+1], cursor[TY], mixed[TY]
     __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
     __shared__ int s_warp[LSS_SORT_THREADS / 32];
@@ -386,7 +390,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
             int j = i + 1;                          // segment end: next head (long runs only occur here)
             while (j < n && (g[j] >> LSS_PIDX_BITS) == col) ++j;
             segs[s + k] = (col << LSS_PIDX_BITS) | (uint32_t)i;
-            emit_voxel_record(d, b, g[i], 2, s + i, j - i, row0 + k, seg_recs, key_count, mixed_recs, counters);
+            emit_voxel_record(d, b, g[i], 2, s + i, j - i, row0 + k, seg_recs, key_count, mixed_recs, counters, n_rows_cap);
             for (int q = i; q < j; ++q) prow[(size_t)b * d.P + lss_column_major(d, g[q] & LSS_PIDX_MASK)] = row0 + k;
         });
         return;
@@ -435,7 +439,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
         mixed[c] |= k << 2;                       // the voxel's ordinal in the tile, for the per-point rows below
         segs[s + k] = ((uint32_t)c << LSS_PIDX_BITS) | (uint32_t)start[c];
         emit_voxel_record(d, b, (uint32_t)cursor[c], mixed[c] & 3, s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
-                          mixed_recs, counters);
+                          mixed_recs, counters, n_rows_cap);
     });
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
@@ -617,7 +621,7 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
         if (lss_launch(k_plan_sort, dim3(tl.n_tiles), dim3(LSS_SORT_THREADS), sort_smem, s, true,
                        d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
                        (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
-                       (int4 *)(w + L->off_mixed_recs), counters, prow) != cudaSuccess) return LSS_ERR_CUDA;
+                       (int4 *)(w + L->off_mixed_recs), counters, prow, (long long)L->n_rows_cap) != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;

@@ -307,7 +307,7 @@ k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, cons
 template <int CPL>
 __global__ void __launch_bounds__(GATHER_THREADS, 1024 / GATHER_THREADS)
 k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_count, const int4 *__restrict__ seg_recs,
-             const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs,
+             const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs, long long n_rows_cap,
              const uint32_t *__restrict__ entries, const float *__restrict__ prob, const float *__restrict__ prob_col,
              const float *__restrict__ ctx_t, float *__restrict__ vsum) {
     extern __shared__ __align__(16) float s_col[];       // [fH][C] context rows of the column, [D][fH] softmax weights
@@ -343,9 +343,47 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
             for (int i = threadIdx.x; i < d.D * d.fH; i += GATHER_THREADS) s_prob[i] = __ldg(psrc + (size_t)i * d.fW);
         }
     }
-    const int4 *recs = column ? seg_recs + (size_t)key * (d.D * d.fH) : mixed_recs;
     const int lane = threadIdx.x & 31;
     const int gl = lane & 7;
+    if (!column) {
+        // ---- long voxels (>= LSS_LONG_VOXEL points, e.g. the cells right in front of a camera): one at a time by the
+        // whole CTA.  NG points per pass: every group fetches one point's context row and writes float32(prob*ctx) to
+        // shared memory (all loads in flight together); thread c then adds the NG products of channel c in ascending
+        // point order -- the same sequence of float32 additions as everywhere else, without the serial load chain.
+        const int n_long = __ldg(counters + 2);
+        float *s_prod = s_col;                                // [NG][C]
+        for (int rl = bid - n_keys; rl < n_long; rl += n_queue) {   // CTA-uniform
+            const int4 lrec = __ldg(mixed_recs + (n_rows_cap - 1 - rl));
+            const uint32_t *ent = entries + lrec.x;
+            const float *prob_b = prob + (size_t)lrec.z * d.P;
+            const float *ctx_b = ctx_t + (size_t)lrec.z * d.N * d.HW * C + gl * 4;
+            const int j = threadIdx.x >> 3;                   // this group's point within the pass
+            float accc = 0.f;                                 // running sum of channel threadIdx.x
+            for (int base = 0; base < lrec.y; base += NG) {
+                const int cnt = min(NG, lrec.y - base);
+                if (j < cnt) {
+                    const unsigned pidx = __ldg(ent + base + j) & LSS_PIDX_MASK;
+                    const unsigned cam = lss_div20(pidx, d.mDHW);
+                    const unsigned rr = pidx - cam * d.DHW;
+                    const unsigned hw = rr - lss_div20(rr, d.mHW) * d.HW;
+                    const float w = __ldg(prob_b + pidx);
+                    const float4 *rowp = reinterpret_cast<const float4 *>(ctx_b + (size_t)(cam * d.HW + hw) * C);
+                    float4 *dst = reinterpret_cast<float4 *>(s_prod + j * C) + gl;
+#pragma unroll
+                    for (int q = 0; q < CPL / 4; ++q) {
+                        const float4 v = __ldg(rowp + 8 * q);
+                        dst[8 * q] = make_float4(__fmul_rn(w, v.x), __fmul_rn(w, v.y), __fmul_rn(w, v.z), __fmul_rn(w, v.w));
+                    }
+                }
+                __syncthreads();
+                if ((int)threadIdx.x < C)
+                    for (int jj = 0; jj < cnt; ++jj) accc = __fadd_rn(accc, s_prod[jj * C + threadIdx.x]);
+                __syncthreads();
+            }
+            if ((int)threadIdx.x < C) vsum[(size_t)lrec.w * C + threadIdx.x] = accc;
+        }
+    }
+    const int4 *recs = column ? seg_recs + (size_t)key * (d.D * d.fH) : mixed_recs;
     const float *s_ctx = s_col + gl * 4;                 // lane gl: float4 slots gl, gl+8, ...
     const int stride = column ? NG : NG * ((int)gridDim.x - n_keys);
     int r = (column ? 0 : NG * (bid - n_keys)) + (threadIdx.x >> 3);
@@ -1241,9 +1279,9 @@ static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, co
     const int n_keys = (b1 - b0) * d.N * d.fW;           // one CTA per camera column of the samples [b0, b1) ...
     // ... plus the CTAs that drain the queue of mixed voxels (of ALL samples): they ride with the part that starts at 0
     const int grid = n_keys + (b0 == 0 ? 2 * num_sms() : 0);
-    const size_t gsm = (size_t)(d.fH * d.C + d.D * d.fH) * 4;
+    const size_t gsm = max((size_t)(d.fH * d.C + d.D * d.fH), (size_t)(GATHER_THREADS / 8) * d.C) * 4;   // column operands / long-voxel products
     if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, pp.entries, prob, prob_col, ctx_t, vsum
+#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, L_rows_cap, pp.entries, prob, prob_col, ctx_t, vsum
     if (d.C == 32) k_fwd_gather<4><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else if (d.C == 64) k_fwd_gather<8><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else k_fwd_gather<16><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
