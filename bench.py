@@ -351,7 +351,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--e2e-inverse", default="device", choices=["device", "reference"])
-    ap.add_argument("--e2e-streams", type=int, default=4)
+    ap.add_argument("--e2e-streams", type=int, default=6, help="StepGraph e2e: graphs (pinned buffer sets) and streams in flight")
     ap.add_argument("--no-e2e-graph", dest="e2e_graph", action="store_false", help="e2e through eager LiftSplat.__call__ instead of StepGraph")
     ap.add_argument("--metric", default="pool", choices=["pool", "train"],
                     help="pool: BEV-pool Mpoints/s fwd+bwd (headline); train: LSS training samples/s")
@@ -436,8 +436,10 @@ def main():
     # ---- e2e through the public API: host buffers in, input gradient out, every step
     e2e_steps = max(10, min(args.e2e_steps, args.steps))
     pinned = []
-    for bs in sets:
-        h = {k: bs.host[k].pin_memory() for k in ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans")}
+    n_e2e = max(len(sets), args.e2e_streams) if (args.e2e_graph and args.e2e_inverse == "device") else len(sets)
+    for i in range(n_e2e):        # pinned host batches of the e2e loop (their own seeds beyond the device buffer sets)
+        hb = sets[i].host if i < len(sets) else make_batch(cfg, 100 * rank + i, "train")
+        h = {k: hb[k].pin_memory() for k in ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans")}
         h["grad_out"] = torch.empty_like(h["depthnet_out"]).pin_memory()
         h["probe"] = torch.empty(1024, dtype=torch.float32).pin_memory()
         pinned.append(h)
@@ -458,7 +460,7 @@ def main():
         # the same step as one CUDA graph per pinned buffer set, replayed alternately on two streams: the copies of one
         # step overlap the kernels of its neighbour; every replay still moves that step's inputs H2D and results D2H
         streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(args.e2e_streams, len(pinned))))]
-        sgraphs = [api.StepGraph(ls, pinned[i], sets[i].grad_bev, streams[i % len(streams)]) for i in range(len(pinned))]
+        sgraphs = [api.StepGraph(ls, pinned[i], sets[i % len(sets)].grad_bev, streams[i % len(streams)]) for i in range(len(pinned))]
         e2e_api = ("lss_carla_b200.api.StepGraph.replay (H2D of the step's pinned inputs + plan + lift-splat fwd/bwd + D2H of the "
                    f"input gradient and a BEV probe, one CUDA graph per buffer set, round-robin on {len(streams)} streams)")
 
