@@ -507,11 +507,16 @@ def main():
     # (a) in-step attribution: graphs of the first k stages, T_k - T_(k-1) = cost of stage k inside the step
     #     (its inputs are L2-hot exactly as in the real step); (b) each stage alone (inputs L2-cold)
     instep, prev = {}, 0.0
+    # (the reference inverse mode calls LAPACK on the host inside the step: not capturable, attributed with device inverses)
+    attr_inverse = "device"
     for k, name in enumerate(STAGES, start=1):
-        tk = time_kernel(lambda bs, k=k: one_step(ops, prob, frustum, bs, args.mode, channels_last, args.inverse, upto=k),
+        tk = time_kernel(lambda bs, k=k: one_step(ops, prob, frustum, bs, args.mode, channels_last, attr_inverse, upto=k),
                          sets, kiters, stream)
         instep[name] = tk - prev
         prev = tk
+    if args.inverse != "device":
+        for bs in sets:                                # M1 / M2 for the stage timings below
+            bs.out["M1"], bs.out["M2"] = ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots)
     stages = {}
     stages["calib"] = time_kernel(lambda bs: ops.calib_matrices_device(bs.rots, bs.intrins, bs.post_rots), sets, kiters, stream)
     fused_calib = args.inverse == "device" and not NO_FUSED_CALIB
