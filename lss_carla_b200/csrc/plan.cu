@@ -114,10 +114,13 @@ __global__ void k_geometry(Dims d, CalibPtrs c, float *__restrict__ geom) {
     geom[(size_t)p * 3 + 2] = g[2];
 }
 
-// One thread per frustum point.  COUNT adds the per-tile histogram of kept points and, in the last CTA
-// to finish, the exclusive scan tile_count -> tile_start (and leaves tile_count / cursor zeroed).
-#define LSS_RAW_CAMS 8    // cameras a 256-point CTA may span in the fused (RAW) build
-template <bool FROM_GEOM, bool COUNT, bool RAW = false>
+// PPT points per thread (each round of 256 consecutive points is warp-aggregated on its own).  COUNT adds the
+// per-tile histogram of kept points and, in the last CTA to finish, the exclusive scan tile_count -> tile_start
+// (and leaves tile_count / cursor zeroed).  The plan build uses PPT = 2: the grid then fits the GPU in ONE wave (the
+// kernel is a chain of latencies -- calibration loads, histogram atomics, fence, ticket -- so a second, nearly empty
+// wave doubled its run time).
+#define LSS_RAW_CAMS 8    // cameras a CTA (PPT * 256 points) may span in the fused (RAW) build
+template <bool FROM_GEOM, bool COUNT, bool RAW = false, int PPT = 1>
 __global__ void __launch_bounds__(256)
 k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, int32_t *__restrict__ vox,
               long long *__restrict__ idx, uint8_t *__restrict__ kept, long long *__restrict__ rank,
@@ -128,49 +131,51 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
         lss_pdl_trigger();                         // the scatter kernel may be scheduled while this grid drains
         if (!RAW && !FROM_GEOM) lss_pdl_wait();    // M1 / M2 may come from k_calib_matrices right before this launch
     }
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = p < d.n_points;
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
-    const int cam0 = (int)((blockIdx.x * blockDim.x) / (unsigned)d.DHW);
+    const int cam0 = (int)((blockIdx.x * (PPT * 256u)) / (unsigned)d.DHW);
     if (RAW) {      // the calibration matrices of the few cameras this CTA touches, made on the fly (no extra launch)
         const int cam = cam0 + (int)threadIdx.x;
         if (threadIdx.x < LSS_RAW_CAMS && cam < d.B * d.N) calib_matrices_of(c.rots, c.intrins, c.post_rots, cam, s_m[threadIdx.x], s_m[threadIdx.x] + 9);
         __syncthreads();
     }
-    int v = -1;
-    if (live) {
-        const int b = p / d.P;
-        float g[3];
-        if (FROM_GEOM) {
-            g[0] = __ldg(geom + (size_t)p * 3 + 0);
-            g[1] = __ldg(geom + (size_t)p * 3 + 1);
-            g[2] = __ldg(geom + (size_t)p * 3 + 2);
-        } else {
-            const int cam = p / d.DHW;
-            if (RAW) ego_point(c, cam, p - cam * d.DHW, g, s_m[cam - cam0], s_m[cam - cam0] + 9);
-            else ego_point(c, cam, p - cam * d.DHW, g);
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const int p = (blockIdx.x * PPT + u) * 256 + threadIdx.x;
+        int v = -1;
+        if (p < d.n_points) {
+            const int b = p / d.P;
+            float g[3];
+            if (FROM_GEOM) {
+                g[0] = __ldg(geom + (size_t)p * 3 + 0);
+                g[1] = __ldg(geom + (size_t)p * 3 + 1);
+                g[2] = __ldg(geom + (size_t)p * 3 + 2);
+            } else {
+                const int cam = p / d.DHW;
+                if (RAW) ego_point(c, cam, p - cam * d.DHW, g, s_m[cam - cam0], s_m[cam - cam0] + 9);
+                else ego_point(c, cam, p - cam * d.DHW, g);
+            }
+            long long ii[3];
+            v = voxel_of_point(d, b, g, ii);
+            if (vox) vox[p] = v;
+            if (COUNT && v < 0)                      // kept points get their compact row from k_plan_sort
+                prow[(size_t)b * d.P + lss_column_major(d, (unsigned)(p - b * d.P))] = -1;
+            if (idx) { idx[(size_t)p * 3 + 0] = ii[0]; idx[(size_t)p * 3 + 1] = ii[1]; idx[(size_t)p * 3 + 2] = ii[2]; }
+            if (kept) kept[p] = v >= 0;
+            if (rank)   // models.py:226-229, int64
+                rank[p] = v >= 0 ? ii[0] * ((long long)d.ny * d.nz * d.B) + ii[1] * ((long long)d.nz * d.B) + ii[2] * d.B + b : -1;
         }
-        long long ii[3];
-        v = voxel_of_point(d, b, g, ii);
-        if (vox) vox[p] = v;
-        if (COUNT && v < 0)                      // kept points get their compact row from k_plan_sort
-            prow[(size_t)b * d.P + lss_column_major(d, (unsigned)(p - b * d.P))] = -1;
-        if (idx) { idx[(size_t)p * 3 + 0] = ii[0]; idx[(size_t)p * 3 + 1] = ii[1]; idx[(size_t)p * 3 + 2] = ii[2]; }
-        if (kept) kept[p] = v >= 0;
-        if (rank)   // models.py:226-229, int64
-            rank[p] = v >= 0 ? ii[0] * ((long long)d.ny * d.nz * d.B) + ii[1] * ((long long)d.nz * d.B) + ii[2] * d.B + b : -1;
+        if (COUNT) {    // ---- per-tile histogram, warp-aggregated
+            int tile = -1 - lane;   // unique negative key for dropped points: singleton groups
+            if (v >= 0) {
+                const int iy = v % d.ny;
+                tile = (v / d.ny) * tl.nty + iy / tl.TY;
+            }
+            const unsigned peers = __match_any_sync(LSS_FULL_MASK, tile);
+            if (v >= 0 && lane == __ffs(peers) - 1) atomicAdd(tile_count + tile, __popc(peers));
+        }
     }
     if (!COUNT) return;
-
-    // ---- per-tile histogram, warp-aggregated
-    const int lane = threadIdx.x & 31;
-    int tile = -1 - lane;   // unique negative key for dropped points: singleton groups
-    if (v >= 0) {
-        const int iy = v % d.ny;
-        tile = (v / d.ny) * tl.nty + iy / tl.TY;
-    }
-    const unsigned peers = __match_any_sync(LSS_FULL_MASK, tile);
-    if (v >= 0 && lane == __ffs(peers) - 1) atomicAdd(tile_count + tile, __popc(peers));
 
     // ---- last CTA scans the histogram
     __shared__ int s_last;
@@ -221,30 +226,46 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
 }
 
 // Scatter kept points into their tile buckets: entries[tile_start[t] + k] = col << 20 | point-in-sample.
+// PPT points per thread (256 consecutive points per warp-aggregation round): with PPT = 2 the grid is a single wave and
+// both cursor atomics of a thread are in flight together (the kernel waits for atomic round trips, nothing else).
+template <int PPT>
 __global__ void __launch_bounds__(256)
 k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, const int32_t *__restrict__ tile_start,
                int32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
     lss_pdl_trigger();
     lss_pdl_wait();                                // voxel ids and tile_start come from k_voxel_index
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int v = -1;
-    if (p < d.n_points) v = __ldg(vox + p);
-    int tile = -1 - lane, col = 0;
-    if (v >= 0) {
-        const int iy = v % d.ny;
-        const int ty = iy / tl.TY;
-        tile = (v / d.ny) * tl.nty + ty;
-        col = iy - ty * tl.TY;
+    int v[PPT], tile[PPT], col[PPT], base[PPT], ts[PPT];
+    unsigned peers[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const int p = (blockIdx.x * PPT + u) * 256 + threadIdx.x;
+        v[u] = p < d.n_points ? __ldg(vox + p) : -1;
     }
-    const unsigned peers = __match_any_sync(LSS_FULL_MASK, tile);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (v >= 0 && lane == leader) base = atomicAdd(cursor + tile, __popc(peers));
-    base = __shfl_sync(LSS_FULL_MASK, base, leader);
-    if (v >= 0) {
-        const int slot = __ldg(tile_start + tile) + base + __popc(peers & ((1u << lane) - 1u));
-        entries[slot] = ((uint32_t)col << LSS_PIDX_BITS) | (uint32_t)(p % d.P);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        tile[u] = -1 - lane; col[u] = 0; ts[u] = 0;
+        if (v[u] >= 0) {
+            const int iy = v[u] % d.ny;
+            const int ty = iy / tl.TY;
+            tile[u] = (v[u] / d.ny) * tl.nty + ty;
+            col[u] = iy - ty * tl.TY;
+        }
+        peers[u] = __match_any_sync(LSS_FULL_MASK, tile[u]);
+        base[u] = 0;
+        if (v[u] >= 0) {
+            if (lane == __ffs(peers[u]) - 1) base[u] = atomicAdd(cursor + tile[u], __popc(peers[u]));
+            ts[u] = __ldg(tile_start + tile[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const int p = (blockIdx.x * PPT + u) * 256 + threadIdx.x;
+        const int b0 = __shfl_sync(LSS_FULL_MASK, base[u], __ffs(peers[u]) - 1);
+        if (v[u] >= 0) {
+            const int slot = ts[u] + b0 + __popc(peers[u] & ((1u << lane) - 1u));
+            entries[slot] = ((uint32_t)col[u] << LSS_PIDX_BITS) | (uint32_t)(p % d.P);
+        }
     }
 }
 
@@ -277,11 +298,12 @@ __device__ __forceinline__ void bitonic_sort_block(Keys a, int n) {
 }
 
 #define LSS_SORT_SMEM_CAP 4096   // entries grouped in shared memory (16 KB); larger buckets sort in global memory
-#define LSS_SORT_THREADS 256
+#define LSS_SORT_THREADS 256          // default CTA size of k_plan_sort (LSS_SORT_NT=128 selects the 128-thread build)
 
 // Exclusive scan of a[0..L) in shared memory by the whole CTA (L <= LSS_MAX_TILE_COLS); a[L] = total.
+template <int NT>
 __device__ __forceinline__ void block_scan_excl(int *a, int L, int *s_warp) {
-    const int per = (L + LSS_SORT_THREADS - 1) / LSS_SORT_THREADS;
+    const int per = (L + NT - 1) / NT;
     const int lo = threadIdx.x * per, hi = min(L, lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int sum = 0;
@@ -294,17 +316,17 @@ __device__ __forceinline__ void block_scan_excl(int *a, int L, int *s_warp) {
     int run = inc - sum;
     for (int w = 0; w < warp; ++w) run += s_warp[w];
     for (int i = lo; i < hi; ++i) { const int x = a[i]; a[i] = run; run += x; }
-    if (threadIdx.x == LSS_SORT_THREADS - 1) a[L] = run;
+    if (threadIdx.x == NT - 1) a[L] = run;
     __syncthreads();
 }
 
 // Ordered enumeration by the whole CTA: calls emit(k, i) for every i in [0, L) with flag(i), k ascending
 // in i starting at 0.  COUNT_ONLY skips the calls.  Returns the number of flagged items (uniform).
-template <bool COUNT_ONLY, typename Flag, typename Emit>
+template <int NT, bool COUNT_ONLY, typename Flag, typename Emit>
 __device__ __forceinline__ int block_enumerate(int L, int *s_warp, Flag flag, Emit emit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int base = 0;
-    for (int i0 = 0; i0 < L; i0 += LSS_SORT_THREADS) {
+    for (int i0 = 0; i0 < L; i0 += NT) {
         const int i = i0 + threadIdx.x;
         const bool f = i < L && flag(i);
         const unsigned hb = __ballot_sync(LSS_FULL_MASK, f);
@@ -312,7 +334,7 @@ __device__ __forceinline__ int block_enumerate(int L, int *s_warp, Flag flag, Em
         __syncthreads();
         int off = base, total = 0;
 #pragma unroll
-        for (int w = 0; w < LSS_SORT_THREADS / 32; ++w) { const int c = s_warp[w]; if (w < warp) off += c; total += c; }
+        for (int w = 0; w < NT / 32; ++w) { const int c = s_warp[w]; if (w < warp) off += c; total += c; }
         if (!COUNT_ONLY && f) emit(off + __popc(hb & ((1u << lane) - 1u)), i);
         base += total;
         __syncthreads();
@@ -359,14 +381,15 @@ __device__ __forceinline__ void emit_voxel_record(const Dims &d, int b, uint32_t
     seg_recs[(size_t)key * (d.D * d.fH) + slot] = make_int4(e0, pure ? -(int)(dd + 1) : len, b, row);
 }
 
-__global__ void __launch_bounds__(LSS_SORT_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries,
             uint32_t *__restrict__ segs, int32_t *__restrict__ tile_nseg, int32_t *__restrict__ tile_row0,
             int4 *__restrict__ seg_recs, int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
             int32_t *__restrict__ counters, int32_t *__restrict__ prow, long long n_rows_cap) {
     extern __shared__ int s_int[];                 // start[TY+1], cursor[TY], mixed[TY]
     __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
-    __shared__ int s_warp[LSS_SORT_THREADS / 32];
+    __shared__ int s_warp[NT / 32];
     __shared__ int s_row0;
     lss_pdl_wait();                                // the buckets come from k_plan_scatter
     const int t = blockIdx.x;
@@ -383,9 +406,9 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
         bitonic_sort_block((volatile uint32_t *)g, n);
         __syncthreads();
         auto head = [&](int i) { return i == 0 || (g[i] >> LSS_PIDX_BITS) != (g[i - 1] >> LSS_PIDX_BITS); };
-        const int ns = block_enumerate<true>(n, s_warp, head, [](int, int) {});
+        const int ns = block_enumerate<NT, true>(n, s_warp, head, [](int, int) {});
         const int row0 = reserve(ns);
-        block_enumerate<false>(n, s_warp, head, [&](int k, int i) {
+        block_enumerate<NT, false>(n, s_warp, head, [&](int k, int i) {
             const uint32_t col = g[i] >> LSS_PIDX_BITS;
             int j = i + 1;                          // segment end: next head (long runs only occur here)
             while (j < n && (g[j] >> LSS_PIDX_BITS) == col) ++j;
@@ -397,19 +420,19 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     }
     const int TY = tl.TY;
     int *start = s_int, *cursor = s_int + TY + 1, *mixed = cursor + TY;
-    for (int i = threadIdx.x; i <= TY; i += LSS_SORT_THREADS) start[i] = 0;
-    for (int i = threadIdx.x; i < TY; i += LSS_SORT_THREADS) { cursor[i] = 0; mixed[i] = 0; }
+    for (int i = threadIdx.x; i <= TY; i += NT) start[i] = 0;
+    for (int i = threadIdx.x; i < TY; i += NT) { cursor[i] = 0; mixed[i] = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) atomicAdd(start + (g[i] >> LSS_PIDX_BITS), 1);
+    for (int i = threadIdx.x; i < n; i += NT) atomicAdd(start + (g[i] >> LSS_PIDX_BITS), 1);
     __syncthreads();
-    block_scan_excl(start, TY, s_warp);
-    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+    block_scan_excl<NT>(start, TY, s_warp);
+    for (int i = threadIdx.x; i < n; i += NT) {
         const uint32_t e = g[i];
         const int col = (int)(e >> LSS_PIDX_BITS);
         s_grp[start[col] + atomicAdd(cursor + col, 1)] = e;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+    for (int i = threadIdx.x; i < n; i += NT) {
         const uint32_t e = s_grp[i];
         const int col = (int)(e >> LSS_PIDX_BITS);
         const int a = start[col], bb = start[col + 1];
@@ -421,7 +444,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     __syncthreads();
     {   // classify every voxel against its first point: same (camera column, depth) / same column / foreign points
         const unsigned span = (unsigned)d.fH * d.fW;
-        for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+        for (int i = threadIdx.x; i < n; i += NT) {
             const uint32_t e = s_grp[i];
             const int col = (int)(e >> LSS_PIDX_BITS);
             const unsigned p = e & LSS_PIDX_MASK, p0 = (uint32_t)cursor[col] & LSS_PIDX_MASK;
@@ -433,16 +456,16 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     }
     __syncthreads();
     auto hit = [&](int c) { return start[c + 1] > start[c]; };
-    const int ns = block_enumerate<true>(TY, s_warp, hit, [](int, int) {});
+    const int ns = block_enumerate<NT, true>(TY, s_warp, hit, [](int, int) {});
     const int row0 = reserve(ns);
-    block_enumerate<false>(TY, s_warp, hit, [&](int k, int c) {
+    block_enumerate<NT, false>(TY, s_warp, hit, [&](int k, int c) {
         mixed[c] |= k << 2;                       // the voxel's ordinal in the tile, for the per-point rows below
         segs[s + k] = ((uint32_t)c << LSS_PIDX_BITS) | (uint32_t)start[c];
         emit_voxel_record(d, b, (uint32_t)cursor[c], mixed[c] & 3, s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
                           mixed_recs, counters, n_rows_cap);
     });
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += LSS_SORT_THREADS) {
+    for (int i = threadIdx.x; i < n; i += NT) {
         const uint32_t e = s_grp[i];
         prow[(size_t)b * d.P + lss_column_major(d, e & LSS_PIDX_MASK)] = row0 + (mixed[e >> LSS_PIDX_BITS] >> 2);
     }
@@ -605,20 +628,32 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
     int32_t *key_count = (int32_t *)(w + L->off_key_count);
     int32_t *prow = (int32_t *)(w + L->off_prow);
     const int grid = (d.n_points + 255) / 256;
+    static const int vi_ppt = getenv("LSS_VOXEL_PPT") ? atoi(getenv("LSS_VOXEL_PPT")) : 2;   // tuning knob
+    const int grid_vi = vi_ppt == 2 ? (grid + 1) / 2 : grid;
 #define VI_ARGS d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count, tile_start, cursor, sync, counters, key_count, prow
-    if (geom != nullptr) k_voxel_index<true, true><<<grid, 256, 0, s>>>(VI_ARGS);
-    else if (raw) k_voxel_index<false, true, true><<<grid, 256, 0, s>>>(VI_ARGS);
-    else if (lss_launch(k_voxel_index<false, true, false>, dim3(grid), dim3(256), 0, s, true, VI_ARGS) != cudaSuccess) return LSS_ERR_CUDA;
+    if (geom != nullptr) {
+        if (vi_ppt == 2) k_voxel_index<true, true, false, 2><<<grid_vi, 256, 0, s>>>(VI_ARGS);
+        else k_voxel_index<true, true><<<grid, 256, 0, s>>>(VI_ARGS);
+    } else if (raw) {
+        if (vi_ppt == 2) k_voxel_index<false, true, true, 2><<<grid_vi, 256, 0, s>>>(VI_ARGS);
+        else k_voxel_index<false, true, true><<<grid, 256, 0, s>>>(VI_ARGS);
+    } else if ((vi_ppt == 2 ? lss_launch(k_voxel_index<false, true, false, 2>, dim3(grid_vi), dim3(256), 0, s, true, VI_ARGS)
+                            : lss_launch(k_voxel_index<false, true, false, 1>, dim3(grid), dim3(256), 0, s, true, VI_ARGS)) != cudaSuccess) return LSS_ERR_CUDA;
 #undef VI_ARGS
     LSS_CHECK_LAUNCH();
-    if (lss_launch(k_plan_scatter, dim3(grid), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess) return LSS_ERR_CUDA;
+    static const int scatter_ppt = getenv("LSS_SCATTER_PPT") ? atoi(getenv("LSS_SCATTER_PPT")) : 2;   // tuning knob
+    if (scatter_ppt == 2
+            ? lss_launch(k_plan_scatter<2>, dim3((grid + 1) / 2), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess
+            : lss_launch(k_plan_scatter<1>, dim3(grid), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
     if (sorted) {
         const size_t sort_smem = (size_t)(3 * tl.TY + 1) * sizeof(int);
         if (sort_smem > 24 * 1024 &&
-            cudaFuncSetAttribute(k_plan_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess)
+            (cudaFuncSetAttribute(k_plan_sort<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess ||
+             cudaFuncSetAttribute(k_plan_sort<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess))
             return LSS_ERR_CUDA;
-        if (lss_launch(k_plan_sort, dim3(tl.n_tiles), dim3(LSS_SORT_THREADS), sort_smem, s, true,
+        static const int sort_nt = getenv("LSS_SORT_NT") ? atoi(getenv("LSS_SORT_NT")) : LSS_SORT_THREADS;   // tuning knob
+        if (lss_launch(sort_nt == 128 ? k_plan_sort<128> : k_plan_sort<256>, dim3(tl.n_tiles), dim3(sort_nt == 128 ? 128 : 256), sort_smem, s, true,
                        d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
                        (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
                        (int4 *)(w + L->off_mixed_recs), counters, prow, (long long)L->n_rows_cap) != cudaSuccess) return LSS_ERR_CUDA;
@@ -646,7 +681,7 @@ extern "C" int lss_plan_build_raw(const lss_problem *p, const lss_plan_layout *L
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
     LSS_REQUIRE(frustum && rots && trans && intrins && post_rots && post_trans, LSS_ERR_BAD_ARG);
     const long long dhw = (long long)p->D * p->fH * p->fW;
-    LSS_REQUIRE(256 / dhw + 2 <= LSS_RAW_CAMS, LSS_ERR_UNSUPPORTED);   // cameras one 256-point CTA may span
+    LSS_REQUIRE(512 / dhw + 2 <= LSS_RAW_CAMS, LSS_ERR_UNSUPPORTED);   // cameras one CTA (up to 512 points) may span
     CalibPtrs c{frustum, post_trans, nullptr, nullptr, trans, rots, intrins, post_rots};
     return plan_build_impl(p, L, workspace, nullptr, c, true, sorted, (cudaStream_t)stream);
 }

@@ -560,31 +560,76 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
 #ifndef STORE_ROWS_MINB
 #define STORE_ROWS_MINB 4       // 6 (40 registers, spills) measured no better
 #endif
+// LEAN (default; LSS_STORE_LEAN=0 selects the first version): the prologue is two global round trips instead of
+// four -- the three words of tile meta data are requested together, and the tile's compact rows are requested
+// (into registers) together with its column list, before the column map is built; rows and map then go to shared
+// memory behind one barrier.  A CTA lives ~6 us of which ~2 us are stores, so the dependent loads in front of the
+// store stream are what keeps the kernel away from the write floor.
+template <bool LEAN>
 __global__ void __launch_bounds__(SPLAT_THREADS, STORE_ROWS_MINB)
 k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                  const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
                  float *__restrict__ bev) {
     extern __shared__ __align__(16) float s_rows[];               // [ROWS_CAP][C + 1], then short map[TY rounded to 8]
     const int tile = tile_lo + blockIdx.x;
-    const TileCoord tc = tile_coord(d, tl, tile);
-    const Tile2D t2 = tile_2d<false>(d, tl, tc);
-    const int nseg = __ldg(tile_nseg + tile);
-    if (nseg == 0) { lss_pdl_wait(); store_tile<true>(t2, nullptr, bev); return; }
-    const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
     const int C = d.C, SR = C + 1, c4 = C >> 2;
     short *s_map = reinterpret_cast<short *>(s_rows + ROWS_CAP * SR + (ROWS_CAP & 1));
-    for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
-    __syncthreads();
-    for (int k = threadIdx.x; k < nseg; k += SPLAT_THREADS) s_map[__ldg(segs + s + k) >> LSS_PIDX_BITS] = (short)k;
-    lss_pdl_wait();                                               // the compact rows come from the gather kernel
-    const int nst = min(nseg, ROWS_CAP);
-    for (int i = threadIdx.x; i < nst * c4; i += SPLAT_THREADS) { // coalesced: the tile's rows are one block
-        const int k = i / c4, q = i - k * c4;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + k) * C) + q);
-        float *dst = s_rows + k * SR + 4 * q;
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    int nseg, s, row0;
+    if (LEAN) {
+        nseg = __ldg(tile_nseg + tile); s = __ldg(tile_start + tile); row0 = __ldg(tile_row0 + tile);   // one round trip
+        for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
+    } else {
+        nseg = __ldg(tile_nseg + tile);
     }
-    __syncthreads();
+    const TileCoord tc = tile_coord(d, tl, tile);
+    const Tile2D t2 = tile_2d<false>(d, tl, tc);
+    if (nseg == 0) { lss_pdl_wait(); store_tile<true>(t2, nullptr, bev); return; }
+    const int nst = min(nseg, ROWS_CAP);
+    if (LEAN) {
+        // the column list is plan data (older than the gather): request it before waiting for the gather
+        const uint32_t e0 = threadIdx.x < nseg ? __ldg(segs + s + threadIdx.x) : 0u;
+        lss_pdl_wait();                                           // the compact rows come from the gather kernel
+        float4 r[4];                                              // this thread's share of the first 4 * 256 row quads
+        const float4 *rsrc = reinterpret_cast<const float4 *>(vsum + (size_t)row0 * C);   // the tile's rows are one block
+        const int nq = nst * c4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + j * SPLAT_THREADS;
+            r[j] = i < nq ? __ldg(rsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();                                          // the map is initialised
+        if (threadIdx.x < nseg) s_map[e0 >> LSS_PIDX_BITS] = (short)threadIdx.x;
+        for (int k = threadIdx.x + SPLAT_THREADS; k < nseg; k += SPLAT_THREADS) s_map[__ldg(segs + s + k) >> LSS_PIDX_BITS] = (short)k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + j * SPLAT_THREADS;
+            if (i < nq) {
+                const int k = i / c4, q = i - k * c4;
+                float *dst = s_rows + k * SR + 4 * q;
+                dst[0] = r[j].x; dst[1] = r[j].y; dst[2] = r[j].z; dst[3] = r[j].w;
+            }
+        }
+        for (int i = threadIdx.x + 4 * SPLAT_THREADS; i < nq; i += SPLAT_THREADS) {     // C > 64 only
+            const int k = i / c4, q = i - k * c4;
+            const float4 v = __ldg(rsrc + i);
+            float *dst = s_rows + k * SR + 4 * q;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        __syncthreads();
+    } else {
+        s = __ldg(tile_start + tile); row0 = __ldg(tile_row0 + tile);
+        for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = threadIdx.x; k < nseg; k += SPLAT_THREADS) s_map[__ldg(segs + s + k) >> LSS_PIDX_BITS] = (short)k;
+        lss_pdl_wait();                                           // the compact rows come from the gather kernel
+        for (int i = threadIdx.x; i < nst * c4; i += SPLAT_THREADS) { // coalesced: the tile's rows are one block
+            const int k = i / c4, q = i - k * c4;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + k) * C) + q);
+            float *dst = s_rows + k * SR + 4 * q;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = t2.RL >> 2;                                   // 16-byte slots per channel row (<= 64 handled per lane pair)
     const float *rows_g = vsum + (size_t)row0 * C;
@@ -966,15 +1011,17 @@ k_bwd_rows_compact(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ t
 // the CTA's points are staged in shared memory first (one round of coalesced loads); the depth loop then
 // reads shared memory, keeps LF gradient rows in flight and needs no control flow (dropped points read
 // row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
+struct GpxMagic { unsigned long long per, fH, npx, WC; };   // ceil(2^40 / x) of D*fH, fH, fH*WC, WC (lss_div20)
 template <int CPL>
 __global__ void __launch_bounds__(SPLAT_THREADS)
-k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
+k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
                 const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
     extern __shared__ __align__(16) float smem[];
     constexpr int LF = CPL <= 8 ? 4 : 2;
     constexpr int NT = SPLAT_THREADS;
+    constexpr int C = 8 * CPL;                            // the dispatch guarantees d.C == 8 * CPL
     const int bn = bn_lo + blockIdx.y, w0 = blockIdx.x * WC;
-    const int D = d.D, C = d.C, fH = d.fH, DC = D + C;
+    const int D = d.D, fH = d.fH, DC = D + C;
     const int npx = fH * WC;                              // pixels of the CTA (<= 32), group g <-> pixel (h, wl)
     float *s_p = smem;                                    // [32][D] softmax weight
     int *s_row = reinterpret_cast<int *>(smem + 32 * D);  // [32][D] compact row or -1
@@ -985,8 +1032,8 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__rest
         const int ncol = min(WC, d.fW - w0), per = D * fH;
         const size_t base = ((size_t)bn * d.fW + w0) * per;
         for (int i = threadIdx.x; i < WC * per; i += NT) {
-            const int wl = i / per, r = i - wl * per;
-            const int dd = r / fH, h = r - dd * fH;
+            const int wl = (int)lss_div20((unsigned)i, mg.per), r = i - wl * per;
+            const int dd = (int)lss_div20((unsigned)r, mg.fH), h = r - dd * fH;
             const bool ok = wl < ncol;
             s_p[(h * WC + wl) * D + dd] = ok ? __ldg(prob_col + base + i) : 0.f;
             s_row[(h * WC + wl) * D + dd] = ok ? __ldg(prow + base + i) : -1;
@@ -994,7 +1041,7 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__rest
     }
     const int lane = threadIdx.x & 31, gl = lane & 7;
     const int g = threadIdx.x >> 3;
-    const int h = g / WC, wl = g - h * WC;
+    const int h = (int)lss_div20((unsigned)g, mg.WC), wl = g - h * WC;
     const bool active = g < npx && w0 + wl < d.fW;
     const size_t my_ctx = ((size_t)bn * d.HW + (active ? h * d.fW + w0 + wl : 0)) * C;
     float ctx[CPL], dctx[CPL];
@@ -1014,17 +1061,22 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__rest
     const float *my_p = s_p + gg * D;
     const int *my_row = s_row + gg * D;
     const float4 *rows4 = reinterpret_cast<const float4 *>(grows) + gl;
-    const int c4 = C >> 2;
+    constexpr int c4 = C >> 2;
     if (stage_rows) {
         // Almost always the fH pixels of a column hit the same voxel at a given depth.  Fetch that "primary" row
         // (the one of pixel h = 0) ONCE per (column, depth), all of them in flight together, zeros where there is
         // none; the depth loop then reads shared memory only and has no control flow.
+        // (cp.async, global -> shared without a register round trip: ALL the CTA's rows are in flight together; a
+        // source size of 0 zero-fills the slot of a dropped point)
+        const unsigned s_g_addr = (unsigned)__cvta_generic_to_shared(s_g);
         for (int i = threadIdx.x; i < WC * D * c4; i += NT) {
             const int cd = i / c4, q = i - cd * c4;       // cd = wl * D + dd; pixel (h = 0, wl) has index wl
             const int r = s_row[cd];
-            reinterpret_cast<float4 *>(s_g)[i] = r >= 0 ? __ldg(reinterpret_cast<const float4 *>(grows) + (size_t)r * c4 + q)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 *src = reinterpret_cast<const float4 *>(grows) + (size_t)max(r, 0) * c4 + q;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s_g_addr + 16u * (unsigned)i), "l"(src), "r"(r >= 0 ? 16 : 0) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const int *col_row = s_row + (g < npx ? wl : 0) * D;
         const float4 *my_sg = reinterpret_cast<const float4 *>(s_g + (size_t)(g < npx ? wl : 0) * D * C) + gl;
@@ -1125,8 +1177,8 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, const int32_t *__rest
     __syncthreads();
     float *out = grad_dn + (size_t)bn * DC * d.HW + w0;
     for (int i = threadIdx.x; i < DC * npx; i += NT) {
-        const int c = i / npx, px = i - c * npx;
-        const int hh = px / WC, ww = px - hh * WC;
+        const int c = (int)lss_div20((unsigned)i, mg.npx), px = i - c * npx;
+        const int hh = (int)lss_div20((unsigned)px, mg.WC), ww = px - hh * WC;
         if (w0 + ww < d.fW) out[(size_t)c * d.HW + hh * d.fW + ww] = s_out[i];
     }
 }
@@ -1216,7 +1268,8 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     if (rows_mode && !CL && VEC4 && CH == d.C && getenv("LSS_STORE_ZERO") == nullptr && tl.TY <= 32767) {
         const size_t rsm = (size_t)(ROWS_CAP * (d.C + 1) + 1) * 4 + (size_t)((tl.TY + 7) / 8) * 16;
         const int tpsr = tl.n_tiles / d.B;
-        if (lss_launch(k_fwd_store_rows, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
+        static int lean = getenv("LSS_STORE_LEAN") ? atoi(getenv("LSS_STORE_LEAN")) : 1;
+        if (lss_launch(lean ? k_fwd_store_rows<true> : k_fwd_store_rows<false>, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
                        pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
         return LSS_OK;
@@ -1514,6 +1567,8 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
     }
     const int WC = max(1, 32 / d.fH);
     const dim3 grid((d.fW + WC - 1) / WC, (b1 - b0) * d.N);
+    auto magic = [](unsigned x) { return ((1ull << 40) + x - 1) / x; };
+    const GpxMagic mg{magic((unsigned)(d.D * d.fH)), magic((unsigned)d.fH), magic((unsigned)(d.fH * WC)), magic((unsigned)WC)};
     size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
     const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16;  // staged gradient rows (+ alignment), if they fit next to a second CTA
@@ -1524,7 +1579,7 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
         static bool configured = false;                                                                          \
         int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
         if (st != LSS_OK) return st;                                                                             \
-        if (lss_launch(k_bwd_gather_px<CPL>, grid, dim3(SPLAT_THREADS), smem, s, stage != 2, d, b0 * d.N, WC, stage_rows, prow, prob_col, \
+        if (lss_launch(k_bwd_gather_px<CPL>, grid, dim3(SPLAT_THREADS), smem, s, stage != 2, d, b0 * d.N, WC, stage_rows, mg, prow, prob_col, \
                        ctx_t, grows, grad_dn) != cudaSuccess) return LSS_ERR_CUDA;                                            \
     } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
