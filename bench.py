@@ -238,7 +238,7 @@ class BufferSet:
         fmt = torch.channels_last if channels_last else torch.contiguous_format
         self.grad_bev = make_bev_grad(cfg, seed).to(dev).contiguous(memory_format=fmt)
         self.plan = ops.Plan(prob, dev, tile_cols)
-        self.rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=dev)
+        self.rows = torch.empty((max(prob.n_voxels, self.plan.layout.n_rows_cap), prob.C), dtype=torch.float32, device=dev)
         self.vsum = torch.empty((self.plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=dev)
         self.lift_out = (torch.empty((2, prob.B * prob.N, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=dev),
                          torch.empty((prob.B * prob.N, prob.fH * prob.fW, prob.C), dtype=torch.float32, device=dev))

@@ -108,7 +108,7 @@ typedef struct lss_plan_layout {
                             /*                    [1] = records in mixed_recs, [2] = records of long */
                             /*                    voxels (>= 64 points), stored from the END of      */
                             /*                    mixed_recs downwards                               */
-    int64_t n_rows_cap;     /* min(n_points, B*nx*ny*nz): capacity of the voxel_sums workspace       */
+    int64_t n_rows_cap;     /* n_points: capacity (rows) of the voxel_sums / grad_rows workspaces     */
     size_t off_tile_count;  /* int32 [n_tiles]    scratch, all-zero between calls                    */
     size_t off_cursor;      /* int32 [n_tiles]    scratch                                            */
     size_t off_sync;        /* int32 [64]         scratch counters, all-zero between calls           */
@@ -208,7 +208,7 @@ int lss_bev_clear(const lss_problem *p, float *bev, void *stream);
  * `b0, b1`: sample range [b0, b1) to process ((0, 0) = all).  Samples are independent, so a caller can issue the
  * GROUP variant in parts on two streams and let the store of one part overlap the gather of the next (the part
  * that starts at sample 0 also sums the voxels shared between camera columns of ALL samples: issue it first).
- * `voxel_sums`: caller workspace f32[min(n_points, B*nx*ny*nz), C] for the GROUP variant (may be null:
+ * `voxel_sums`: caller workspace f32[n_rows_cap, C] (n_rows_cap = n_points) for the GROUP variant (may be null:
  * the WARP variant is used).  bev f32[B, nz*C, nx, ny] in `layout`. */
 int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,
                   const float *prob, const float *ctx_t, const float *prob_col, float *voxel_sums, float *bev,
@@ -217,7 +217,7 @@ int lss_splat_fwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
 /* Backward of lift+splat to the depthnet output (replaces QuickCumsum.backward tools.py:212-219 and the
  * autograd backward of models.py:58-59,:199-200,:240-244):
  *   grad_depthnet f32[B*N, D+C, fH, fW]  (first D channels: logits through the softmax; last C: context)
- * `grad_rows` is a caller workspace f32[B*nz*nx*ny, C]: the gradient rows of the non-empty voxels are
+ * `grad_rows` is a caller workspace f32[max(B*nz*nx*ny, n_rows_cap), C]: the gradient rows of the non-empty voxels are
  * gathered into it, channel-contiguous (compact row order for sorted plans, voxel order otherwise); it may
  * be null only for channels_last gradients.  `plan_sorted` != 0 promises that the plan was built with
  * sorted=1, which (together with `prob_col` from lss_lift_prepare) enables the compact-row kernels

@@ -124,7 +124,7 @@ class StepGraph:
         dev = ls.device
 
         vsum = torch.empty((ws.layout.n_rows_cap, prob.C), dtype=torch.float32, device=dev)
-        rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=dev)
+        rows = torch.empty((max(prob.n_voxels, ws.layout.n_rows_cap), prob.C), dtype=torch.float32, device=dev)
         self._keep = (ws, vsum, rows)
 
         def step():

@@ -120,7 +120,7 @@ __global__ void k_geometry(Dims d, CalibPtrs c, float *__restrict__ geom) {
 // kernel is a chain of latencies -- calibration loads, histogram atomics, fence, ticket -- so a second, nearly empty
 // wave doubled its run time).
 #define LSS_RAW_CAMS 8    // cameras a CTA (PPT * 256 points) may span in the fused (RAW) build
-template <bool FROM_GEOM, bool COUNT, bool RAW = false, int PPT = 1>
+template <bool FROM_GEOM, bool COUNT, bool RAW = false, int PPT = 1, bool TAIL = true>
 __global__ void __launch_bounds__(256)
 k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, int32_t *__restrict__ vox,
               long long *__restrict__ idx, uint8_t *__restrict__ kept, long long *__restrict__ rank,
@@ -175,7 +175,7 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
             if (v >= 0 && lane == __ffs(peers) - 1) atomicAdd(tile_count + tile, __popc(peers));
         }
     }
-    if (!COUNT) return;
+    if (!COUNT || !TAIL) return;                   // !TAIL: k_plan_scatter<PPT, true> scans the histogram itself
 
     // ---- last CTA scans the histogram
     __shared__ int s_last;
@@ -228,13 +228,56 @@ k_voxel_index(Dims d, Tiling tl, const float *__restrict__ geom, CalibPtrs c, in
 // Scatter kept points into their tile buckets: entries[tile_start[t] + k] = col << 20 | point-in-sample.
 // PPT points per thread (256 consecutive points per warp-aggregation round): with PPT = 2 the grid is a single wave and
 // both cursor atomics of a thread are in flight together (the kernel waits for atomic round trips, nothing else).
-template <int PPT>
+// SCAN: the exclusive scan tile_count -> tile_start is done HERE, redundantly by every CTA into shared memory (a few
+// thousand counters from L2), instead of by the last CTA of k_voxel_index behind a fence and a ticket: that kernel then
+// ends with its histogram atomics.  CTA 0 publishes tile_start and clears the per-build counters; tile_count / cursor
+// are cleared by k_plan_sort (sorted plans) or a memset (unsorted plans).
+template <int PPT, bool SCAN>
 __global__ void __launch_bounds__(256)
-k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, const int32_t *__restrict__ tile_start,
-               int32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, int32_t *__restrict__ tile_start,
+               int32_t *__restrict__ cursor, uint32_t *__restrict__ entries, const int32_t *__restrict__ tile_count,
+               int32_t *__restrict__ key_count, int32_t *__restrict__ counters) {
+    extern __shared__ int s_start[];               // SCAN: [n_tiles + 1]
     lss_pdl_trigger();
-    lss_pdl_wait();                                // voxel ids and tile_start come from k_voxel_index
+    lss_pdl_wait();                                // voxel ids and the histogram (or tile_start) come from k_voxel_index
     const int lane = threadIdx.x & 31;
+    if (SCAN) {
+        __shared__ int s_warp[8];
+        __shared__ int s_carry;
+        const int warp = threadIdx.x >> 5, nt = tl.n_tiles;
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < nt; base += 1024) {
+            const int i0 = base + threadIdx.x * 4;       // (tile_count is padded to 256 bytes, the padding is zero)
+            const int4 a = i0 < nt ? __ldcg(reinterpret_cast<const int4 *>(tile_count + i0)) : make_int4(0, 0, 0, 0);
+            const int tsum = a.x + a.y + a.z + a.w;
+            int inc = tsum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(LSS_FULL_MASK, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            int run = s_carry + inc - tsum;
+            for (int w = 0; w < warp; ++w) run += s_warp[w];
+            if (i0 < nt) {                                // s_start has n_tiles + 1 slots; slots beyond hold the total
+                s_start[i0] = run; run += a.x;
+                if (i0 + 1 <= nt) s_start[i0 + 1] = run; run += a.y;
+                if (i0 + 2 <= nt) s_start[i0 + 2] = run; run += a.z;
+                if (i0 + 3 <= nt) s_start[i0 + 3] = run; run += a.w;
+                if (i0 + 4 == nt) s_start[nt] = run;
+            }
+            __syncthreads();
+            if (threadIdx.x == 255) s_carry = run;
+            __syncthreads();
+        }
+        if (blockIdx.x == 0) {
+            for (int i = threadIdx.x; i <= nt; i += 256) tile_start[i] = s_start[i];
+            for (int i = threadIdx.x; i < d.B * d.N * d.fW; i += 256) key_count[i] = 0;
+            if (threadIdx.x < 3) counters[threadIdx.x] = 0;
+        }
+    }
     int v[PPT], tile[PPT], col[PPT], base[PPT], ts[PPT];
     unsigned peers[PPT];
 #pragma unroll
@@ -255,7 +298,7 @@ k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, const int32_t
         base[u] = 0;
         if (v[u] >= 0) {
             if (lane == __ffs(peers[u]) - 1) base[u] = atomicAdd(cursor + tile[u], __popc(peers[u]));
-            ts[u] = __ldg(tile_start + tile[u]);
+            ts[u] = SCAN ? s_start[tile[u]] : __ldg(tile_start + tile[u]);
         }
     }
 #pragma unroll
@@ -386,29 +429,28 @@ __global__ void __launch_bounds__(NT)
 k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t *__restrict__ entries,
             uint32_t *__restrict__ segs, int32_t *__restrict__ tile_nseg, int32_t *__restrict__ tile_row0,
             int4 *__restrict__ seg_recs, int32_t *__restrict__ key_count, int4 *__restrict__ mixed_recs,
-            int32_t *__restrict__ counters, int32_t *__restrict__ prow, long long n_rows_cap) {
+            int32_t *__restrict__ counters, int32_t *__restrict__ prow, long long n_rows_cap,
+            int32_t *__restrict__ clear_count, int32_t *__restrict__ clear_cursor) {
     extern __shared__ int s_int[];                 // start[TY+1], cursor[TY], mixed[TY]
     __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
     __shared__ int s_warp[NT / 32];
-    __shared__ int s_row0;
     lss_pdl_wait();                                // the buckets come from k_plan_scatter
     const int t = blockIdx.x;
+    if (clear_count != nullptr && threadIdx.x == 0) { clear_count[t] = 0; clear_cursor[t] = 0; }   // scratch of the next build
     const int s = tile_start[t], n = tile_start[t + 1] - s;
     const int b = t / (tl.nty * d.nx * d.nz);
     uint32_t *g = entries + s;
     if (n == 0) { if (threadIdx.x == 0) { tile_nseg[t] = 0; tile_row0[t] = 0; } return; }
-    auto reserve = [&](int ns) {                   // uniform call; returns the tile's first compact row
-        if (threadIdx.x == 0) { s_row0 = atomicAdd(counters, ns); tile_nseg[t] = ns; tile_row0[t] = s_row0; }
-        __syncthreads();
-        return s_row0;
-    };
+    // Compact rows: the tile's k-th non-empty voxel owns row s + k (s = the tile's first bucket slot; a voxel has at
+    // least one entry, so the rows of different tiles never collide and stay below the number of kept points).  No
+    // reservation, hence no atomic round trip in the middle of the CTA; the row space is sparse but tile-contiguous.
+    const int row0 = s;
+    auto publish = [&](int ns) { if (threadIdx.x == 0) { tile_nseg[t] = ns; tile_row0[t] = s; atomicAdd(counters, ns); } };
     if (n > LSS_SORT_SMEM_CAP) {                   // rare: correctness fallback, sorts in global memory (L2)
         bitonic_sort_block((volatile uint32_t *)g, n);
         __syncthreads();
         auto head = [&](int i) { return i == 0 || (g[i] >> LSS_PIDX_BITS) != (g[i - 1] >> LSS_PIDX_BITS); };
-        const int ns = block_enumerate<NT, true>(n, s_warp, head, [](int, int) {});
-        const int row0 = reserve(ns);
-        block_enumerate<NT, false>(n, s_warp, head, [&](int k, int i) {
+        const int ns = block_enumerate<NT, false>(n, s_warp, head, [&](int k, int i) {
             const uint32_t col = g[i] >> LSS_PIDX_BITS;
             int j = i + 1;                          // segment end: next head (long runs only occur here)
             while (j < n && (g[j] >> LSS_PIDX_BITS) == col) ++j;
@@ -416,6 +458,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
             emit_voxel_record(d, b, g[i], 2, s + i, j - i, row0 + k, seg_recs, key_count, mixed_recs, counters, n_rows_cap);
             for (int q = i; q < j; ++q) prow[(size_t)b * d.P + lss_column_major(d, g[q] & LSS_PIDX_MASK)] = row0 + k;
         });
+        publish(ns);
         return;
     }
     const int TY = tl.TY;
@@ -432,38 +475,36 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
         s_grp[start[col] + atomicAdd(cursor + col, 1)] = e;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += NT) {
-        const uint32_t e = s_grp[i];
-        const int col = (int)(e >> LSS_PIDX_BITS);
-        const int a = start[col], bb = start[col + 1];
-        int rank = 0;
-        for (int j = a; j < bb; ++j) rank += s_grp[j] < e;
-        g[a + rank] = e;
-        if (rank == 0) cursor[col] = (int)e;       // the voxel's first point (cursor is free again)
-    }
-    __syncthreads();
-    {   // classify every voxel against its first point: same (camera column, depth) / same column / foreign points
+    {   // rank inside the voxel, and in the same walk the voxel's first point (its smallest key): every entry is
+        // classified against it -- same (camera column, depth) / same column / foreign points
         const unsigned span = (unsigned)d.fH * d.fW;
         for (int i = threadIdx.x; i < n; i += NT) {
             const uint32_t e = s_grp[i];
             const int col = (int)(e >> LSS_PIDX_BITS);
-            const unsigned p = e & LSS_PIDX_MASK, p0 = (uint32_t)cursor[col] & LSS_PIDX_MASK;
+            const int a = start[col], bb = start[col + 1];
+            int rank = 0;
+            uint32_t first = e;
+            for (int j = a; j < bb; ++j) { const uint32_t x = s_grp[j]; rank += x < e; first = min(first, x); }
+            g[a + rank] = e;
+            if (rank == 0) { cursor[col] = (int)e; continue; }       // the first point itself is kind 0 (cursor is free again)
+            const unsigned p = e & LSS_PIDX_MASK, p0 = first & LSS_PIDX_MASK;
             const unsigned delta = p - p0;
-            if (delta < span && delta % (unsigned)d.fW == 0u) continue;                      // kind 0
-            const bool same_col = lss_div20(p, d.mDHW) == lss_div20(p0, d.mDHW) && delta % (unsigned)d.fW == 0u;
+            const bool col_aligned = delta % (unsigned)d.fW == 0u;
+            if (delta < span && col_aligned) continue;                                       // kind 0
+            const bool same_col = col_aligned && lss_div20(p, d.mDHW) == lss_div20(p0, d.mDHW);
             atomicMax(mixed + col, same_col ? 1 : 2);
         }
     }
     __syncthreads();
     auto hit = [&](int c) { return start[c + 1] > start[c]; };
-    const int ns = block_enumerate<NT, true>(TY, s_warp, hit, [](int, int) {});
-    const int row0 = reserve(ns);
-    block_enumerate<NT, false>(TY, s_warp, hit, [&](int k, int c) {
-        mixed[c] |= k << 2;                       // the voxel's ordinal in the tile, for the per-point rows below
+    const int ns = block_enumerate<NT, false>(TY, s_warp, hit, [&](int k, int c) {
+        const int kind = mixed[c] & 3;
+        mixed[c] = kind | (k << 2);               // the voxel's ordinal in the tile, for the per-point rows below
         segs[s + k] = ((uint32_t)c << LSS_PIDX_BITS) | (uint32_t)start[c];
-        emit_voxel_record(d, b, (uint32_t)cursor[c], mixed[c] & 3, s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
+        emit_voxel_record(d, b, (uint32_t)cursor[c], kind, s + start[c], start[c + 1] - start[c], row0 + k, seg_recs, key_count,
                           mixed_recs, counters, n_rows_cap);
     });
+    publish(ns);
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += NT) {
         const uint32_t e = s_grp[i];
@@ -548,7 +589,8 @@ extern "C" int lss_plan_layout_init(const lss_problem *p, int tile_cols, lss_pla
     out->off_tile_nseg = off;  off += up((size_t)nt * 4);
     out->off_tile_row0 = off;  off += up((size_t)nt * 4);
     const int64_t nvox = (int64_t)p->B * p->nx * p->ny * p->nz;
-    out->n_rows_cap = nvox < (int64_t)d.n_points ? nvox : (int64_t)d.n_points;
+    (void)nvox;
+    out->n_rows_cap = (int64_t)d.n_points;         // compact rows are indexed by bucket slot (k_plan_sort): below the number of kept points
     out->off_seg_recs = off;   off += up((size_t)d.n_points * 16);
     out->off_key_count = off;  off += up((size_t)p->B * p->N * p->fW * 4);
     out->off_mixed_recs = off; off += up((size_t)out->n_rows_cap * 16);
@@ -628,23 +670,35 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
     int32_t *key_count = (int32_t *)(w + L->off_key_count);
     int32_t *prow = (int32_t *)(w + L->off_prow);
     const int grid = (d.n_points + 255) / 256;
-    static const int vi_ppt = getenv("LSS_VOXEL_PPT") ? atoi(getenv("LSS_VOXEL_PPT")) : 2;   // tuning knob
-    const int grid_vi = vi_ppt == 2 ? (grid + 1) / 2 : grid;
+    // the histogram scan rides in the scatter kernel when its table fits shared memory (LSS_SCAN_IN_SCATTER=0: old path)
+    static const int scan_knob = getenv("LSS_SCAN_IN_SCATTER") ? atoi(getenv("LSS_SCAN_IN_SCATTER")) : 1;
+    const size_t scan_smem = ((size_t)tl.n_tiles + 1) * sizeof(int);
+    const bool scan_in_scatter = scan_knob && scan_smem <= 64 * 1024;
+    const int grid_vi = (grid + 1) / 2;
 #define VI_ARGS d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count, tile_start, cursor, sync, counters, key_count, prow
     if (geom != nullptr) {
-        if (vi_ppt == 2) k_voxel_index<true, true, false, 2><<<grid_vi, 256, 0, s>>>(VI_ARGS);
-        else k_voxel_index<true, true><<<grid, 256, 0, s>>>(VI_ARGS);
+        if (scan_in_scatter) k_voxel_index<true, true, false, 2, false><<<grid_vi, 256, 0, s>>>(VI_ARGS);
+        else k_voxel_index<true, true, false, 2, true><<<grid_vi, 256, 0, s>>>(VI_ARGS);
     } else if (raw) {
-        if (vi_ppt == 2) k_voxel_index<false, true, true, 2><<<grid_vi, 256, 0, s>>>(VI_ARGS);
-        else k_voxel_index<false, true, true><<<grid, 256, 0, s>>>(VI_ARGS);
-    } else if ((vi_ppt == 2 ? lss_launch(k_voxel_index<false, true, false, 2>, dim3(grid_vi), dim3(256), 0, s, true, VI_ARGS)
-                            : lss_launch(k_voxel_index<false, true, false, 1>, dim3(grid), dim3(256), 0, s, true, VI_ARGS)) != cudaSuccess) return LSS_ERR_CUDA;
+        if (scan_in_scatter) k_voxel_index<false, true, true, 2, false><<<grid_vi, 256, 0, s>>>(VI_ARGS);
+        else k_voxel_index<false, true, true, 2, true><<<grid_vi, 256, 0, s>>>(VI_ARGS);
+    } else if ((scan_in_scatter ? lss_launch(k_voxel_index<false, true, false, 2, false>, dim3(grid_vi), dim3(256), 0, s, true, VI_ARGS)
+                                : lss_launch(k_voxel_index<false, true, false, 2, true>, dim3(grid_vi), dim3(256), 0, s, true, VI_ARGS)) != cudaSuccess) return LSS_ERR_CUDA;
 #undef VI_ARGS
     LSS_CHECK_LAUNCH();
-    static const int scatter_ppt = getenv("LSS_SCATTER_PPT") ? atoi(getenv("LSS_SCATTER_PPT")) : 2;   // tuning knob
-    if (scatter_ppt == 2
-            ? lss_launch(k_plan_scatter<2>, dim3((grid + 1) / 2), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess
-            : lss_launch(k_plan_scatter<1>, dim3(grid), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries) != cudaSuccess) return LSS_ERR_CUDA;
+    if (scan_in_scatter) {
+        static bool configured = false;
+        if (scan_smem > 40 * 1024 && !configured) {
+            if (cudaFuncSetAttribute(k_plan_scatter<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
+            configured = true;
+        }
+        if (lss_launch(k_plan_scatter<2, true>, dim3(grid_vi), dim3(256), scan_smem, s, true, d, tl, vox, tile_start, cursor, entries,
+                       tile_count, key_count, counters) != cudaSuccess) return LSS_ERR_CUDA;
+        if (!sorted) {      // no sort kernel to clear the scratch counters of the next build: tile_count and cursor are contiguous
+            if (cudaMemsetAsync(tile_count, 0, (size_t)((char *)sync - (char *)tile_count), s) != cudaSuccess) return LSS_ERR_CUDA;
+        }
+    } else if (lss_launch(k_plan_scatter<2, false>, dim3(grid_vi), dim3(256), 0, s, true, d, tl, vox, tile_start, cursor, entries,
+                          tile_count, key_count, counters) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
     if (sorted) {
         const size_t sort_smem = (size_t)(3 * tl.TY + 1) * sizeof(int);
@@ -656,7 +710,8 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
         if (lss_launch(sort_nt == 128 ? k_plan_sort<128> : k_plan_sort<256>, dim3(tl.n_tiles), dim3(sort_nt == 128 ? 128 : 256), sort_smem, s, true,
                        d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
                        (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
-                       (int4 *)(w + L->off_mixed_recs), counters, prow, (long long)L->n_rows_cap) != cudaSuccess) return LSS_ERR_CUDA;
+                       (int4 *)(w + L->off_mixed_recs), counters, prow, (long long)L->n_rows_cap,
+                       scan_in_scatter ? tile_count : (int32_t *)nullptr, cursor) != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
     }
     return LSS_OK;

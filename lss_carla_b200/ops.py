@@ -283,7 +283,7 @@ def bev_clear(prob: Problem, device, channels_last=False):
 def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False, variant="auto", out=None,
               voxel_sums=None, batch_range=(0, 0), precleared=None):
     """`out`: optional output tensor (pre-zeroed, from bev_clear, for mode 'red').  `voxel_sums`: optional
-    workspace f32[min(n_points, n_voxels), C] of the two-kernel GROUP variant (allocated when omitted).
+    workspace f32[plan.layout.n_rows_cap, C] of the two-kernel GROUP variant (allocated when omitted).
     `batch_range` = (b0, b1): only these samples (GROUP variant; see splat_fwd_pipelined)."""
     if mode == "sorted" and not plan.sorted:
         raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
@@ -302,7 +302,7 @@ def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_
               batch_range=(0, 0)):
     g, layout = _bev_layout(_f32c_keep(grad_bev))
     if grad_rows is None and (layout == LAYOUT_NCHW or plan.sorted):
-        grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
+        grad_rows = torch.empty((max(prob.n_voxels, plan.layout.n_rows_cap), prob.C), dtype=torch.float32, device=g.device)
     if out is None:
         out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
     if prob_col is None:
@@ -349,7 +349,7 @@ def splat_bwd_pipelined(prob: Problem, plan: Plan, grad_bev, pr, ct, side, parts
         return splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out)
     cur = torch.cuda.current_stream()
     if grad_rows is None:
-        grad_rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
+        grad_rows = torch.empty((max(prob.n_voxels, plan.layout.n_rows_cap), prob.C), dtype=torch.float32, device=g.device)
     if out is None:
         out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
     for t in (g, grad_rows, out, pr, ct):
@@ -417,7 +417,7 @@ class _VoxelPoolingFn(torch.autograd.Function):
         g, layout = _bev_layout(_f32c_keep(grad_bev))
         rows = None
         if layout == LAYOUT_NCHW:
-            rows = torch.empty((prob.n_voxels, prob.C), dtype=torch.float32, device=g.device)
+            rows = torch.empty((max(prob.n_voxels, plan.layout.n_rows_cap), prob.C), dtype=torch.float32, device=g.device)
         gx = torch.empty(ctx.xshape, dtype=torch.float32, device=g.device)
         check(lib().lss_voxel_pooling_bwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), layout,
                                           _ptr(rows), _ptr(gx), _stream()), "lss_voxel_pooling_bwd")

@@ -72,7 +72,7 @@ def test_plan_layout_host_only(L):
     assert lay.tile_cols == 200 and lay.tiles_per_row == 1 and lay.n_tiles == 8 * 200
     assert lay.n_points == cfg.points == 346368
     assert lay.bytes >= 2 * 4 * cfg.points
-    assert lay.n_rows_cap == min(cfg.points, 8 * 200 * 200)
+    assert lay.n_rows_cap == cfg.points      # compact rows are indexed by bucket slot: below the number of kept points
     offs = [getattr(lay, f[0]) for f in _lib.LssPlanLayout._fields_ if f[0].startswith("off_")]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and offs[-1] < lay.bytes
     assert L.lss_plan_layout_init(C.byref(p.c), 56, C.byref(lay)) == 0

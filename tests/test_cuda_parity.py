@@ -100,10 +100,10 @@ def test_plan_and_reference_sort_order(case, tile_cols):
     n_hit = np.unique(vox[vox >= 0]).size
     r0, tn = plan.tile_row0.cpu().numpy().astype(np.int64), plan.tile_nseg.cpu().numpy().astype(np.int64)
     assert int(plan.n_rows.item()) == n_hit == tn.sum()
-    used = np.zeros(n_hit + 1, np.int64)                     # the tiles' row ranges tile [0, n_hit) exactly
-    np.add.at(used, r0[tn > 0], 1)
-    np.add.at(used, (r0 + tn)[tn > 0], -1)
-    assert np.all(np.cumsum(used)[:-1] == 1)
+    # compact rows: tile t owns rows [tile_start[t], tile_start[t] + nseg[t]) -- inside its own bucket range, hence
+    # disjoint between tiles and below the number of kept points (the capacity of the row workspaces)
+    assert np.array_equal(r0[tn > 0], ts[:-1][tn > 0]) and np.all(tn <= np.diff(ts))
+    assert int((r0 + tn).max()) <= int(g["n_kept"]) <= plan.layout.n_rows_cap
     # reference order: flat index of x[kept][sorts]
     order = ops.reference_order(plan).cpu().numpy()
     rs = O.ranks_and_sort(idx, kept, cfg.B, g["nx"])
