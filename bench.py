@@ -251,8 +251,10 @@ class BufferSet:
 STAGES = ("calib", "plan_build", "lift_prepare", "splat_fwd", "splat_bwd")
 NO_OVERLAP = bool(os.environ.get("LSS_BENCH_NO_OVERLAP"))
 # calibration inverses inside k_voxel_index (lss_plan_build_raw) vs k_calib_matrices + programmatic dependent launch of
-# k_voxel_index: measured 2953 vs 2989 Mpoints/s at cfg 2 -> the separate tiny kernel stays the default
-NO_FUSED_CALIB = not bool(os.environ.get("LSS_BENCH_FUSED_CALIB"))
+# k_voxel_index: with the single-wave voxel-index kernel the fused build is ahead (3467 vs 3426 Mpoints/s at cfg 2; it
+# was 2953 vs 2989 with the two-wave kernel) and is the default -- the same entry point the e2e API path uses.
+# LSS_BENCH_FUSED_CALIB=0 selects the separate kernel.
+NO_FUSED_CALIB = os.environ.get("LSS_BENCH_FUSED_CALIB", "1") == "0"
 # sample-range pipelining of gather/store on two streams: measured slower at cfg 2 (2 parts: 2404, 4 parts: 1868 vs 2876
 # Mpoints/s unsplit) -- every kernel already fills the GPU, smaller launches only add tails -- so it stays off
 PARTS = 1 if NO_OVERLAP else int(os.environ.get("LSS_BENCH_PARTS", "1"))
@@ -351,8 +353,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--e2e-inverse", default="device", choices=["device", "reference"])
-    ap.add_argument("--e2e-streams", type=int, default=6, help="StepGraph e2e: graphs (pinned buffer sets) and streams in flight")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="e2e: steps (pinned buffer sets + device buffers) in flight")
     ap.add_argument("--no-e2e-graph", dest="e2e_graph", action="store_false", help="e2e through eager LiftSplat.__call__ instead of StepGraph")
+    ap.add_argument("--e2e-mode", default="pipeline", choices=["pipeline", "graphs"],
+                    help="pipeline: api.StepPipeline (copy-in / compute / copy-out streams); graphs: api.StepGraph per stream")
     ap.add_argument("--metric", default="pool", choices=["pool", "train"],
                     help="pool: BEV-pool Mpoints/s fwd+bwd (headline); train: LSS training samples/s")
     ap.add_argument("--splat", default="ours", choices=["ours", "aten"], help="--metric train: lift-splat implementation")
@@ -456,7 +460,33 @@ def main():
 
     e2e_api = (f"lss_carla_b200.api.LiftSplat.__call__ + autograd backward + LiftSplat.download; inverse_mode={args.e2e_inverse}; "
                "stream-ordered pinned H2D/D2H copies inside the timed region")
-    if args.e2e_graph and args.e2e_inverse == "device":
+    if args.e2e_graph and args.e2e_inverse == "device" and args.e2e_mode == "pipeline":
+        # three-stage pipeline (api.StepPipeline): copy-in stream, ONE compute stream replaying the step's kernel graph,
+        # copy-out stream; `--e2e-streams` steps (pinned buffer sets + device buffers) in flight
+        pstreams = api.PipelineStreams(dev)
+        fH, fW = cfg.fHW
+        psteps = []
+        for i in range(len(pinned)):
+            hb = api.pinned_step_buffers(cfg.B, cfg.N, cfg.D + cfg.C, fH, fW)
+            for k in ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans"):
+                hb[k].copy_(pinned[i][k].reshape(hb[k].shape))
+            psteps.append(api.StepPipeline(ls, hb, sets[i % len(sets)].grad_bev, pstreams))
+        d2h = psteps[0].host["grad_out"].numel() * 4 + psteps[0].host["probe"].numel() * 4
+        e2e_api = ("lss_carla_b200.api.StepPipeline.run (H2D of the step's pinned depthnet output + calibration block on a "
+                   "copy-in stream, plan + lift-splat fwd/bwd as one CUDA graph on the shared compute stream, D2H of the input "
+                   f"gradient and a BEV probe on a copy-out stream; {len(psteps)} steps in flight)")
+
+        def e2e_step(i):       # noqa: F811
+            psteps[i % len(psteps)].run()
+
+        def fork():
+            for st in pstreams.all():
+                st.wait_stream(torch.cuda.current_stream())
+
+        def join():
+            for st in pstreams.all():
+                torch.cuda.current_stream().wait_stream(st)
+    elif args.e2e_graph and args.e2e_inverse == "device":
         # the same step as one CUDA graph per pinned buffer set, replayed alternately on two streams: the copies of one
         # step overlap the kernels of its neighbour; every replay still moves that step's inputs H2D and results D2H
         streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(args.e2e_streams, len(pinned))))]

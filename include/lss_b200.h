@@ -269,6 +269,21 @@ int lss_quickcumsum_fwd(int64_t n, int32_t C, const float *x, int64_t x_row_stri
 int lss_quickcumsum_bwd(int64_t n, int32_t C, const float *grad_sums, const int32_t *run_id,
                         float *grad_x, void *stream);
 
+/* ---------------------------------------------------------------------------------------------- */
+/* Host-buffer pipeline helpers (used by lss_carla_b200.api.StepPipeline; the reference has no        */
+/* counterpart: its loader hands CUDA tensors to LiftSplatShoot.forward, train_simbev.py:232-239)     */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Events without timing, for stream-to-stream ordering.  lss_pipe_event_create returns NULL on failure. */
+void *lss_pipe_event_create(void);
+int lss_pipe_event_destroy(void *event);
+int lss_pipe_event_synchronize(void *event);
+/* One pipeline stage, enqueued with a single call: `stream` waits for wait_a and wait_b (each may be NULL), runs
+ * n_copies (<= 4) cudaMemcpyAsync(dst[i], src[i], bytes[i], default kind: pinned host <-> device), then records
+ * `record` (may be NULL).  Returns LSS_OK or LSS_ERR_CUDA. */
+int lss_pipe_stage(void *stream, void *wait_a, void *wait_b, int32_t n_copies, void *const *dst,
+                   const void *const *src, const size_t *bytes, void *record);
+
 #ifdef __cplusplus
 }
 #endif

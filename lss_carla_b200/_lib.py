@@ -66,6 +66,11 @@ SIGNATURES = {
     "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
     "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),
+    "lss_pipe_event_create": (C.c_void_p, []),
+    "lss_pipe_event_destroy": (C.c_int, [_P]),
+    "lss_pipe_event_synchronize": (C.c_int, [_P]),
+    "lss_pipe_stage": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_size_t), _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -153,3 +153,155 @@ class StepGraph:
     def replay(self):
         with torch.cuda.stream(self.stream):
             self.graph.replay()
+
+
+CALIB_KEYS = ("rots", "trans", "intrins", "post_rots", "post_trans")
+_CALIB_FLOATS = {"rots": 9, "trans": 3, "intrins": 9, "post_rots": 9, "post_trans": 3}
+
+
+def pinned_step_buffers(B, N, channels, fH, fW, probe=1024):
+    """Pinned host buffers of one step for `StepPipeline`: ONE input block (`in_block`: the depthnet output followed by
+    the five calibration tensors, 33 floats per camera) and ONE output block (`out_block`: input gradient, BEV probe); the
+    named entries are views, so a step is one copy host -> device and one back."""
+    n_x = B * N * channels * fH * fW
+    blk = torch.empty(n_x + B * N * 33, dtype=torch.float32).pin_memory()
+    h = {"in_block": blk, "depthnet_out": blk[:n_x].view(B * N, channels, fH, fW)}
+    off = n_x
+    for k in CALIB_KEYS:
+        n = _CALIB_FLOATS[k]
+        h[k] = blk[off:off + B * N * n].view((B, N, 3, 3) if n == 9 else (B, N, 3))
+        off += B * N * n
+    out = torch.empty(n_x + probe, dtype=torch.float32).pin_memory()
+    h["out_block"] = out
+    h["grad_out"] = out[:n_x].view(B * N, channels, fH, fW)
+    h["probe"] = out[n_x:]
+    return h
+
+
+class PipelineStreams:
+    """The three streams a group of `StepPipeline`s shares: copy-in, compute, copy-out."""
+
+    def __init__(self, device):
+        self.h2d, self.compute, self.d2h = (torch.cuda.Stream(device=device) for _ in range(3))
+
+    def all(self):
+        return (self.h2d, self.compute, self.d2h)
+
+
+class _Event:
+    """cudaEvent (no timing) owned by the C library: recorded / waited for inside lss_pipe_stage."""
+
+    def __init__(self):
+        from ._lib import lib
+        self.h = lib().lss_pipe_event_create()
+        if not self.h:
+            raise RuntimeError("liblss_b200: lss_pipe_event_create failed")
+
+    def synchronize(self):
+        from ._lib import check, lib
+        check(lib().lss_pipe_event_synchronize(self.h), "lss_pipe_event_synchronize")
+
+    def __del__(self):
+        try:
+            from ._lib import lib
+            lib().lss_pipe_event_destroy(self.h)
+        except Exception:
+            pass
+
+
+class StepPipeline:
+    """One lift-splat forward + backward step between PINNED host buffers, as a three-stage pipeline.
+
+        streams = PipelineStreams(dev)
+        steps = [StepPipeline(ls, pinned_step_buffers(...), grad_bev, streams) for _ in range(depth)]
+        ... s = steps[i % depth]; s.done.synchronize(); write batch i into s.host[...]; s.run(); later read s.host["grad_out"]
+
+    `run()` enqueues (1) the host -> device copy of this step's input block (depthnet output + calibration) on the copy-in
+    stream, (2) ONE CUDA graph with the step's kernels (plan build with the device inverse, lift next to it on a forked
+    branch, splat forward, backward against `grad_bev`) on the compute stream and (3) the device -> host copy of the output
+    block (input gradient, BEV probe) on the copy-out stream, chained by events.  All instances of a group run their
+    kernels on the SAME compute stream -- the kernels of different steps never interleave (co-scheduled steps were
+    measured ~20 % slower per step than back-to-back ones) -- while the copies of the neighbouring steps overlap them on
+    the two copy engines.  The host side of a step is four foreign-function calls (lss_pipe_stage) and one graph launch.
+    Every instance owns its device buffers and plan workspace; it may be re-run once its previous results have been
+    consumed (`done.synchronize()`).  `host` comes from `pinned_step_buffers`."""
+
+    def __init__(self, ls: LiftSplat, host: dict, grad_bev, streams: PipelineStreams):
+        import ctypes as C
+        from ._lib import check, lib
+        if ls.inverse_mode != "device":
+            raise ValueError("StepPipeline needs inverse_mode='device' (the LAPACK inverse of the reference mode runs on the host)")
+        if "in_block" not in host or "out_block" not in host:
+            raise ValueError("StepPipeline needs the buffers of api.pinned_step_buffers (one pinned block per direction)")
+        self.ls, self.host, self.streams = ls, host, streams
+        self._lib, self._check = lib(), check
+        dev = ls.device
+        B, N = host["trans"].shape[:2]
+        fH, fW = host["depthnet_out"].shape[-2:]
+        prob = models._problem_for(ls, B, N, fH, fW, host["depthnet_out"].shape[1] - ls.D)
+        ws = ops.Plan(prob, dev, ls.tile_cols)
+        n_x = host["depthnet_out"].numel()
+        self.in_dev = torch.empty(host["in_block"].shape, dtype=torch.float32, device=dev)
+        self.out_dev = torch.empty(host["out_block"].shape, dtype=torch.float32, device=dev)
+        x = self.in_dev[:n_x].view(host["depthnet_out"].shape)
+        cal, off = [], n_x
+        for k in CALIB_KEYS:
+            n = host[k].numel()
+            cal.append(self.in_dev[off:off + n].view(host[k].shape))
+            off += n
+        grad_out = self.out_dev[:n_x].view(host["depthnet_out"].shape)
+        probe_out = self.out_dev[n_x:]
+        vsum = torch.empty((ws.layout.n_rows_cap, prob.C), dtype=torch.float32, device=dev)
+        rows = torch.empty((max(prob.n_voxels, ws.layout.n_rows_cap), prob.C), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)           # lift_prepare next to the plan build, inside the graph
+        self._keep = (ws, vsum, rows, side, x, cal)
+
+        def compute():
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                pr, ct = ops.lift_prepare(prob, x)
+            plan = ops.build_plan_raw(prob, ls.frustum, *cal, sorted=(ls.splat_mode == "sorted"), plan=ws)
+            cur.wait_stream(side)
+            bev = ops.splat_fwd(prob, plan, pr, ct, ls.splat_mode, ls.bev_channels_last, voxel_sums=vsum)
+            ops.splat_bwd(prob, plan, grad_bev, pr, ct, rows, out=grad_out)
+            probe_out.copy_(bev.reshape(-1)[:probe_out.numel()])
+
+        self.ev_in, self.ev_c, self.done = _Event(), _Event(), _Event()
+        P = C.c_void_p
+        self._in_args = ((P * 1)(self.in_dev.data_ptr()), (P * 1)(host["in_block"].data_ptr()),
+                         (C.c_size_t * 1)(host["in_block"].numel() * 4))
+        self._out_args = ((P * 1)(host["out_block"].data_ptr()), (P * 1)(self.out_dev.data_ptr()),
+                          (C.c_size_t * 1)(host["out_block"].numel() * 4))
+        self._s = tuple(C.c_void_p(st.cuda_stream) for st in streams.all())
+        cs = streams.compute
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):
+            self.in_dev.copy_(host["in_block"], non_blocking=True)
+            for _ in range(3):
+                compute()
+        cs.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=cs):
+            compute()
+        cs.synchronize()
+        for ev in (self.ev_c, self.done):              # "recorded and complete": the first run() must not wait
+            check(self._lib.lss_pipe_stage(self._s[1], None, None, 0, None, None, None, ev.h), "lss_pipe_stage")
+        cs.synchronize()
+
+    def run(self):
+        L, s = self._lib, self._s
+        # copy-in: after the previous run of this instance has read its inputs
+        st = L.lss_pipe_stage(s[0], self.ev_c.h, None, 1, *self._in_args, self.ev_in.h)
+        # compute: after the inputs have arrived and the previous results have left the device
+        st |= L.lss_pipe_stage(s[1], self.ev_in.h, self.done.h, 0, None, None, None, None)
+        if torch.cuda.current_stream(self.ls.device) == self.streams.compute:
+            self.graph.replay()
+        else:
+            with torch.cuda.stream(self.streams.compute):
+                self.graph.replay()
+        st |= L.lss_pipe_stage(s[1], None, None, 0, None, None, None, self.ev_c.h)
+        # copy-out
+        st |= L.lss_pipe_stage(s[2], self.ev_c.h, None, 1, *self._out_args, self.done.h)
+        if st:
+            self._check(st, "lss_pipe_stage")

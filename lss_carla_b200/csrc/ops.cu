@@ -156,3 +156,35 @@ extern "C" void lss_get_limits(lss_limits *out) {
     out->max_depth_bins = LSS_MAX_DEPTH;
     out->max_channels = LSS_MAX_CHANNELS;
 }
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer pipeline helpers (api.StepPipeline): a whole stage -- waits, copies, record -- per call, so that the
+// host side of a step is a handful of foreign-function calls instead of a dozen framework calls
+// ------------------------------------------------------------------------------------------------
+
+extern "C" void *lss_pipe_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return (void *)e;
+}
+
+extern "C" int lss_pipe_event_destroy(void *event) {
+    return (event == nullptr || cudaEventDestroy((cudaEvent_t)event) == cudaSuccess) ? LSS_OK : LSS_ERR_CUDA;
+}
+
+extern "C" int lss_pipe_event_synchronize(void *event) {
+    LSS_REQUIRE(event != nullptr, LSS_ERR_BAD_ARG);
+    return cudaEventSynchronize((cudaEvent_t)event) == cudaSuccess ? LSS_OK : LSS_ERR_CUDA;
+}
+
+extern "C" int lss_pipe_stage(void *stream, void *wait_a, void *wait_b, int32_t n_copies, void *const *dst,
+                              const void *const *src, const size_t *bytes, void *record) {
+    LSS_REQUIRE(n_copies >= 0 && n_copies <= 4 && (n_copies == 0 || (dst && src && bytes)), LSS_ERR_BAD_ARG);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (wait_a && cudaStreamWaitEvent(s, (cudaEvent_t)wait_a, 0) != cudaSuccess) return LSS_ERR_CUDA;
+    if (wait_b && cudaStreamWaitEvent(s, (cudaEvent_t)wait_b, 0) != cudaSuccess) return LSS_ERR_CUDA;
+    for (int i = 0; i < n_copies; ++i)
+        if (cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, s) != cudaSuccess) return LSS_ERR_CUDA;
+    if (record && cudaEventRecord((cudaEvent_t)record, s) != cudaSuccess) return LSS_ERR_CUDA;
+    return LSS_OK;
+}

@@ -241,16 +241,30 @@ k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, int32_t *__re
     lss_pdl_trigger();
     lss_pdl_wait();                                // voxel ids and the histogram (or tile_start) come from k_voxel_index
     const int lane = threadIdx.x & 31;
+    int v[PPT], tile[PPT], col[PPT], base[PPT], ts[PPT];
+    unsigned peers[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {                // requested before the scan: in flight while it runs
+        const int p = (blockIdx.x * PPT + u) * 256 + threadIdx.x;
+        v[u] = p < d.n_points ? __ldg(vox + p) : -1;
+    }
     if (SCAN) {
         __shared__ int s_warp[8];
         __shared__ int s_carry;
         const int warp = threadIdx.x >> 5, nt = tl.n_tiles;
         if (threadIdx.x == 0) s_carry = 0;
         __syncthreads();
-        for (int base = 0; base < nt; base += 1024) {
-            const int i0 = base + threadIdx.x * 4;       // (tile_count is padded to 256 bytes, the padding is zero)
-            const int4 a = i0 < nt ? __ldcg(reinterpret_cast<const int4 *>(tile_count + i0)) : make_int4(0, 0, 0, 0);
-            const int tsum = a.x + a.y + a.z + a.w;
+        for (int base0 = 0; base0 < nt; base0 += 2048) {  // 8 counters per thread and step
+            const int i0 = base0 + threadIdx.x * 8;      // (tile_count is padded to 256 bytes, the padding is zero)
+            int a[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int4 q = i0 + 4 * h < nt ? __ldcg(reinterpret_cast<const int4 *>(tile_count + i0 + 4 * h)) : make_int4(0, 0, 0, 0);
+                a[4 * h] = q.x; a[4 * h + 1] = q.y; a[4 * h + 2] = q.z; a[4 * h + 3] = q.w;
+            }
+            int tsum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tsum += a[k];
             int inc = tsum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -261,13 +275,12 @@ k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, int32_t *__re
             __syncthreads();
             int run = s_carry + inc - tsum;
             for (int w = 0; w < warp; ++w) run += s_warp[w];
-            if (i0 < nt) {                                // s_start has n_tiles + 1 slots; slots beyond hold the total
-                s_start[i0] = run; run += a.x;
-                if (i0 + 1 <= nt) s_start[i0 + 1] = run; run += a.y;
-                if (i0 + 2 <= nt) s_start[i0 + 2] = run; run += a.z;
-                if (i0 + 3 <= nt) s_start[i0 + 3] = run; run += a.w;
-                if (i0 + 4 == nt) s_start[nt] = run;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                // s_start has n_tiles + 1 slots: slot nt receives the total
+                if (i0 + k <= nt) s_start[i0 + k] = run;
+                run += a[k];
             }
+            if (i0 + 8 == nt) s_start[nt] = run;
             __syncthreads();
             if (threadIdx.x == 255) s_carry = run;
             __syncthreads();
@@ -277,13 +290,6 @@ k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, int32_t *__re
             for (int i = threadIdx.x; i < d.B * d.N * d.fW; i += 256) key_count[i] = 0;
             if (threadIdx.x < 3) counters[threadIdx.x] = 0;
         }
-    }
-    int v[PPT], tile[PPT], col[PPT], base[PPT], ts[PPT];
-    unsigned peers[PPT];
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        const int p = (blockIdx.x * PPT + u) * 256 + threadIdx.x;
-        v[u] = p < d.n_points ? __ldg(vox + p) : -1;
     }
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {

@@ -304,20 +304,52 @@ k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, cons
 // takes its row and weight from global memory.  Groups look 8 entries ahead (lane gl resolves entry
 // base+gl) and add float32(prob*ctx) in ascending point order.  The sum goes to the voxel's compact row
 // of vsum (L2-resident, 4*C*V_hit bytes).
+// Zero role (ZeroArgs::n_tiles > 0, NCHW with 16-byte rows): the LAST n_tiles CTAs of the grid do not gather.  CTA j
+// zero-fills, in every channel row of BEV tile tile_lo + j, the 32-byte sectors that hold no non-empty column (known
+// from the plan alone).  They are scheduled after all gather CTAs, i.e. into the SMs that idle while the queue of
+// mixed voxels drains, so about a third of the BEV bytes are written before the store kernel starts; that kernel
+// (k_fwd_store_rows<.., SKIPZ>) then skips exactly these sectors.
+struct ZeroArgs { float *bev; const int32_t *tile_start, *tile_nseg; const uint32_t *segs; Tiling tl; int tile_lo, n_tiles; };
+
+__device__ __forceinline__ void zero_empty_sectors(const Dims &d, const ZeroArgs &z, int tile) {
+    __shared__ unsigned s_hit;                           // bit j: sector j (columns 8j .. 8j+7 of the tile) has a voxel
+    const int nseg = __ldg(z.tile_nseg + tile), s = __ldg(z.tile_start + tile);
+    if (threadIdx.x == 0) s_hit = 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < nseg; k += GATHER_THREADS) atomicOr(&s_hit, 1u << ((__ldg(z.segs + s + k) >> LSS_PIDX_BITS) >> 3));
+    __syncthreads();
+    const unsigned hit = s_hit;
+    const TileCoord tc = tile_coord(d, z.tl, tile);
+    const Tile2D t2 = tile_2d<false>(d, z.tl, tc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vpr = t2.RL >> 2;                          // 16-byte slots per channel row; slots 2j, 2j+1 = sector j
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v0 = lane; v0 < vpr; v0 += 32) {
+        if ((hit >> (v0 >> 1)) & 1u) continue;
+        float4 *gp = reinterpret_cast<float4 *>(z.bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
+        const size_t gstep = (size_t)(GATHER_THREADS / 32) * t2.GRS / 4;
+        for (int c = warp; c < d.C; c += GATHER_THREADS / 32, gp += gstep) *gp = zero;
+    }
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(GATHER_THREADS, 1024 / GATHER_THREADS)
 k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_count, const int4 *__restrict__ seg_recs,
              const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs, long long n_rows_cap,
              const uint32_t *__restrict__ entries, const float *__restrict__ prob, const float *__restrict__ prob_col,
-             const float *__restrict__ ctx_t, float *__restrict__ vsum) {
+             const float *__restrict__ ctx_t, float *__restrict__ vsum, ZeroArgs z) {
     extern __shared__ __align__(16) float s_col[];       // [fH][C] context rows of the column, [D][fH] softmax weights
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
     lss_pdl_trigger();                                   // PDL: the store kernel may start its prologue in our tail
+    if ((int)blockIdx.x >= (int)gridDim.x - z.n_tiles) {  // zero role
+        zero_empty_sectors(d, z, z.tile_lo + (int)blockIdx.x - ((int)gridDim.x - z.n_tiles));
+        return;
+    }
     // The FIRST CTAs of the grid drain the queue of mixed voxels (group per voxel, all operands from global memory):
     // they start at once, live a few microseconds and hand their slots to the column CTAs that did not fit the first
     // wave, instead of forming the tail of the kernel.
-    const int n_queue = (int)gridDim.x - n_keys, qfirst = QUEUE_FIRST ? n_queue : 0;
+    const int n_queue = (int)gridDim.x - z.n_tiles - n_keys, qfirst = QUEUE_FIRST ? n_queue : 0;
     const int bid = QUEUE_FIRST ? ((int)blockIdx.x < n_queue ? n_keys + (int)blockIdx.x : (int)blockIdx.x - n_queue) : (int)blockIdx.x;
     (void)qfirst;
     const bool column = bid < n_keys;                    // (measured: a warp per mixed voxel -- 16 rows in flight, sum
@@ -385,7 +417,7 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
     }
     const int4 *recs = column ? seg_recs + (size_t)key * (d.D * d.fH) : mixed_recs;
     const float *s_ctx = s_col + gl * 4;                 // lane gl: float4 slots gl, gl+8, ...
-    const int stride = column ? NG : NG * ((int)gridDim.x - n_keys);
+    const int stride = column ? NG : NG * n_queue;
     int r = (column ? 0 : NG * (bid - n_keys)) + (threadIdx.x >> 3);
     // software pipeline over the group's records: the record and the first 8 entries of the NEXT voxel are
     // requested before the current one is consumed.  All shuffles use the full mask (a lane-dependent mask
@@ -565,7 +597,11 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
 // (into registers) together with its column list, before the column map is built; rows and map then go to shared
 // memory behind one barrier.  A CTA lives ~6 us of which ~2 us are stores, so the dependent loads in front of the
 // store stream are what keeps the kernel away from the write floor.
-template <bool LEAN>
+// SKIPZ: the 32-byte sectors of the tile that hold no non-empty column (about a third of the grid at cfg 2) were
+// already zero-filled by the zero-role CTAs that ride at the end of the gather grid (k_fwd_gather, ZeroArgs), in the
+// shadow of the gather's tail; this kernel then writes the remaining sectors only (a sector is always written whole
+// and by one kernel).  Both sides derive "empty sector" from the tile's column list in the same way.
+template <bool LEAN, bool SKIPZ>
 __global__ void __launch_bounds__(SPLAT_THREADS, STORE_ROWS_MINB)
 k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                  const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
@@ -583,7 +619,7 @@ k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ til
     }
     const TileCoord tc = tile_coord(d, tl, tile);
     const Tile2D t2 = tile_2d<false>(d, tl, tc);
-    if (nseg == 0) { lss_pdl_wait(); store_tile<true>(t2, nullptr, bev); return; }
+    if (nseg == 0) { if (!SKIPZ) { lss_pdl_wait(); store_tile<true>(t2, nullptr, bev); } return; }
     const int nst = min(nseg, ROWS_CAP);
     if (LEAN) {
         // the column list is plan data (older than the gather): request it before waiting for the gather
@@ -633,9 +669,17 @@ k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ til
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = t2.RL >> 2;                                   // 16-byte slots per channel row (<= 64 handled per lane pair)
     const float *rows_g = vsum + (size_t)row0 * C;
-    for (int v0 = lane; v0 < vpr; v0 += 32) {                     // usually 2 slots per lane
-        const uint2 m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
+    for (int vb = 0; vb < vpr; vb += 32) {                        // usually 2 slots per lane (warp-uniform loop)
+        const int v0 = vb + lane;
+        const bool valid = v0 < vpr;
+        uint2 m = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (valid) m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
         const int k0 = (short)(m.x & 0xFFFFu), k1 = (short)(m.x >> 16), k2 = (short)(m.y & 0xFFFFu), k3 = (short)(m.y >> 16);
+        if (SKIPZ) {                                              // slots 2j, 2j+1 = lanes 2j, 2j+1 form a sector
+            const bool empty = (m.x & m.y & 0x80008000u) == 0x80008000u;     // all four columns without a voxel
+            const bool pair_empty = __shfl_xor_sync(LSS_FULL_MASK, empty ? 1 : 0, 1) != 0;
+            if (!valid || (empty && pair_empty)) continue;
+        } else if (!valid) continue;
         float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
         const size_t gstep = (size_t)SPLAT_WARPS * t2.GRS / 4;
         if (nseg <= ROWS_CAP) {                                   // CTA-uniform: every compact row is staged
@@ -1256,9 +1300,17 @@ static inline PlanPtrs plan_ptrs(const lss_plan_layout *L, const void *workspace
     return pp;
 }
 
+// does the NCHW forward go through k_fwd_store_rows (16-byte rows, whole channel range per CTA)?
+static bool store_rows_path(const Dims &d, const Tiling &tl, bool cl, bool vec4) {
+    static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;
+    static int rows_mode = getenv("LSS_STORE_ROWS") ? atoi(getenv("LSS_STORE_ROWS")) : 1;
+    static bool zero_only = getenv("LSS_STORE_ZERO") != nullptr;
+    return rows_mode && !cl && vec4 && (ch_override <= 0 || ch_override == d.C) && !zero_only && tl.TY <= 32767;
+}
+
 template <bool CL, bool VEC4>
 static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
-                            bool pdl, cudaStream_t s) {
+                            bool pdl, cudaStream_t s, bool skipz = false) {
     static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;   // tuning knob
     int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
     if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
@@ -1269,7 +1321,8 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
         const size_t rsm = (size_t)(ROWS_CAP * (d.C + 1) + 1) * 4 + (size_t)((tl.TY + 7) / 8) * 16;
         const int tpsr = tl.n_tiles / d.B;
         static int lean = getenv("LSS_STORE_LEAN") ? atoi(getenv("LSS_STORE_LEAN")) : 1;
-        if (lss_launch(lean ? k_fwd_store_rows<true> : k_fwd_store_rows<false>, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
+        auto kern = skipz ? k_fwd_store_rows<true, true> : (lean ? k_fwd_store_rows<true, false> : k_fwd_store_rows<false, false>);
+        if (lss_launch(kern, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
                        pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
         return LSS_OK;
@@ -1326,15 +1379,23 @@ static int launch_fwd_store_tma(const Dims &d, const Tiling &tl, const PlanPtrs 
 static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, const PlanPtrs &pp, long long L_rows_cap,
                          const float *prob, const float *prob_col, const float *ctx_t, float *vsum, float *bev,
                          int variant, int b0, int b1, cudaStream_t s) {
+    bool zsplit = false;                                  // empty sectors zero-filled by the gather grid, skipped by the store
     if (variant == LSS_VARIANT_GROUP_STORE) goto store;
     {
     const int key_lo = b0 * d.N * d.fW;
     const int n_keys = (b1 - b0) * d.N * d.fW;           // one CTA per camera column of the samples [b0, b1) ...
     // ... plus the CTAs that drain the queue of mixed voxels (of ALL samples): they ride with the part that starts at 0
-    const int grid = n_keys + (b0 == 0 ? 2 * num_sms() : 0);
+    // zero-role CTAs (see ZeroArgs): only when the NCHW row store follows in this call (experiment, LSS_FWD_ZSPLIT=1)
+    // Measured at cfg 2: the store kernel writes a third fewer bytes but shrinks only from 20.7 to 18.1 us (it is bound by
+    // its per-CTA latency chain, not by bytes), while the gather grows from 13.7 to 18.1 us -> forward 36.5 vs 31.6 us: OFF.
+    static int zsplit_knob = getenv("LSS_FWD_ZSPLIT") ? atoi(getenv("LSS_FWD_ZSPLIT")) : 0;
+    const int tps_z = tl.n_tiles / d.B;
+    zsplit = zsplit_knob && variant != LSS_VARIANT_GROUP_GATHER && store_rows_path(d, tl, cl, vec4) && d.ny % 8 == 0 && tl.TY <= 256;
+    const ZeroArgs za{zsplit ? bev : nullptr, pp.tile_start, pp.tile_nseg, pp.segs, tl, b0 * tps_z, zsplit ? (b1 - b0) * tps_z : 0};
+    const int grid = n_keys + (b0 == 0 ? 2 * num_sms() : 0) + za.n_tiles;
     const size_t gsm = max((size_t)(d.fH * d.C + d.D * d.fH), (size_t)(GATHER_THREADS / 8) * d.C) * 4;   // column operands / long-voxel products
     if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, L_rows_cap, pp.entries, prob, prob_col, ctx_t, vsum
+#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, L_rows_cap, pp.entries, prob, prob_col, ctx_t, vsum, za
     if (d.C == 32) k_fwd_gather<4><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else if (d.C == 64) k_fwd_gather<8><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
     else k_fwd_gather<16><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
@@ -1358,7 +1419,7 @@ store:
     }
     const bool pdl = variant != LSS_VARIANT_GROUP_STORE;  // only right behind its gather
     if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
-    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
+    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s, zsplit) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
 }
 
 template <int VW, int KC, bool DENSE>

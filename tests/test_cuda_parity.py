@@ -545,6 +545,37 @@ def test_step_graph_matches_eager_api_and_overlaps_safely():
         api.StepGraph(api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, device=dev()), hs[0], gb)
 
 
+def test_step_pipeline_matches_eager_api():
+    """api.StepPipeline (copy-in stream, kernel graph on one compute stream, copy-out stream; several steps in flight,
+    buffers re-used across rounds) == eager LiftSplat + autograd, bit for bit."""
+    from lss_carla_b200 import api
+    cfg = CONFIGS["cfg1"]
+    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, inverse_mode="device", device=dev())
+    gb = make_bev_grad(cfg, 0).to(dev())
+    fH, fW = cfg.fHW
+    streams = api.PipelineStreams(dev())
+    steps = [api.StepPipeline(ls, api.pinned_step_buffers(cfg.B, cfg.N, cfg.D + cfg.C, fH, fW, probe=2048), gb, streams)
+             for _ in range(3)]
+    keys = ("depthnet_out", "rots", "trans", "intrins", "post_rots", "post_trans")
+    for rnd in range(3):                                  # every round writes NEW batches into the same pinned buffers
+        batches = [make_batch(cfg, 10 * rnd + i, "train") for i in range(3)]
+        for st, b in zip(steps, batches):
+            st.done.synchronize()                         # the previous results of this instance have been consumed
+            for k in keys:
+                st.host[k].copy_(b[k].reshape(st.host[k].shape))
+            st.run()
+        for st, b in zip(steps, batches):
+            st.done.synchronize()
+            x = b["depthnet_out"].to(dev()).requires_grad_(True)
+            bev = ls(x, *[b[k] for k in keys[1:]])
+            bev.backward(gb)
+            torch.cuda.synchronize()
+            assert torch.equal(x.grad.cpu(), st.host["grad_out"])
+            assert torch.equal(bev.detach().reshape(-1)[:2048].cpu(), st.host["probe"])
+    with pytest.raises(ValueError):
+        api.StepPipeline(api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, device=dev()), steps[0].host, gb, streams)
+
+
 def test_model_level_cumsum_check_style():
     """The reference's only in-repo sanity check (src/explore.py:119-191 `cumsum_check`) made into an assertion: the
     same model evaluated with the CUDA lift-splat and with the reference's ATen op chain (QuickCumsum) gives the same
