@@ -1055,8 +1055,16 @@ k_bwd_rows_compact(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ t
 // the CTA's points are staged in shared memory first (one round of coalesced loads); the depth loop then
 // reads shared memory, keeps LF gradient rows in flight and needs no control flow (dropped points read
 // row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
+//
+// DIRECT (NCHW gradients; experiment, off by default -- see run_bwd_compact): no k_bwd_rows_compact launch and no compact gradient rows.  `prow` is
+// then the plan's voxel id per point (point-major), and the CTA stages the gradient rows of its columns' primary voxels
+// straight from the NCHW tensor: one 4-byte cp.async per (voxel, channel), a warp covering 32 voxels along the CTA's
+// rays for one channel (neighbouring voxels share 32-byte sectors), ALL of the CTA's ~10 k requests in flight together.
+// The sector-bound DRAM read (63 MB at cfg 2) that was a kernel of its own now overlaps this kernel's other phases and
+// the compact rows' round trip through L2 disappears.  Shared-memory rows are XOR-swizzled at 16-byte granularity
+// (chunk ^= voxel & 7) so that the 4-byte writes of a warp spread over the banks; a group still reads one 128-byte line.
 struct GpxMagic { unsigned long long per, fH, npx, WC; };   // ceil(2^40 / x) of D*fH, fH, fH*WC, WC (lss_div20)
-template <int CPL>
+template <int CPL, bool DIRECT>
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
                 const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
@@ -1071,7 +1079,9 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
     int *s_row = reinterpret_cast<int *>(smem + 32 * D);  // [32][D] compact row or -1
     float *s_gp = smem + 64 * D;                          // [32][D] <grad row, ctx>
     float *s_out = smem + 96 * D;                         // [D + C][npx] staged outputs
-    float *s_g = smem + ((96 * D + DC * npx + 3) & ~3);   // [WC][D][C] rows of the columns' primary voxels (16-byte aligned)
+    int *s_off = reinterpret_cast<int *>(smem + 96 * D + DC * npx);   // DIRECT: [WC][D] NCHW element offset of the primary voxel, or -1
+    float *s_g = smem + ((96 * D + DC * npx + (DIRECT ? WC * D : 0) + 3) & ~3);   // [WC][D][C] rows of the columns' primary voxels (16-byte aligned)
+    const int plane = d.nx * d.ny;                        // DIRECT: elements per channel plane of the NCHW gradient
     {   // the CTA's columns are one contiguous block [wl][D][fH] in the column-major arrays
         const int ncol = min(WC, d.fW - w0), per = D * fH;
         const size_t base = ((size_t)bn * d.fW + w0) * per;
@@ -1080,7 +1090,16 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
             const int dd = (int)lss_div20((unsigned)r, mg.fH), h = r - dd * fH;
             const bool ok = wl < ncol;
             s_p[(h * WC + wl) * D + dd] = ok ? __ldg(prob_col + base + i) : 0.f;
-            s_row[(h * WC + wl) * D + dd] = ok ? __ldg(prow + base + i) : -1;
+            if (DIRECT) {       // voxel id of the point, point-major: ((bn*D + dd)*fH + h)*fW + w
+                const int v = ok ? __ldg(prow + ((size_t)(bn * D + dd) * fH + h) * d.fW + w0 + wl) : -1;
+                s_row[(h * WC + wl) * D + dd] = v;
+                if (h == 0) {
+                    const int qz = v >= 0 ? v / plane : 0;                      // b*nz + iz
+                    s_off[wl * D + dd] = v >= 0 ? (qz * C) * plane + (v - qz * plane) : -1;
+                }
+            } else {
+                s_row[(h * WC + wl) * D + dd] = ok ? __ldg(prow + base + i) : -1;
+            }
         }
     }
     const int lane = threadIdx.x & 31, gl = lane & 7;
@@ -1113,6 +1132,20 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
         // (cp.async, global -> shared without a register round trip: ALL the CTA's rows are in flight together; a
         // source size of 0 zero-fills the slot of a dropped point)
         const unsigned s_g_addr = (unsigned)__cvta_generic_to_shared(s_g);
+        if (DIRECT) {
+            const int nv = WC * D, warp_i = threadIdx.x >> 5;
+            for (int cd = lane; cd < nv; cd += 32) {
+                const int off = s_off[cd];
+                const float *src = grows + (off >= 0 ? off : 0);                 // grows = the NCHW gradient tensor here
+                const unsigned row_addr = s_g_addr + 4u * (unsigned)(cd * C);
+                const int sw = cd & 7;
+#pragma unroll 4
+                for (int c = warp_i; c < C; c += NT / 32) {
+                    const unsigned dst = row_addr + 4u * (unsigned)(((((c >> 2) ^ sw)) << 2) | (c & 3));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src + (size_t)c * plane), "r"(off >= 0 ? 4 : 0) : "memory");
+                }
+            }
+        } else
         for (int i = threadIdx.x; i < WC * D * c4; i += NT) {
             const int cd = i / c4, q = i - cd * c4;       // cd = wl * D + dd; pixel (h = 0, wl) has index wl
             const int r = s_row[cd];
@@ -1125,6 +1158,7 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
         const int *col_row = s_row + (g < npx ? wl : 0) * D;
         const float4 *my_sg = reinterpret_cast<const float4 *>(s_g + (size_t)(g < npx ? wl : 0) * D * C) + gl;
         unsigned exc = 0;                                 // does this pixel hit other voxels than the primary ones?
+        const int cd0 = (g < npx ? wl : 0) * D;              // DIRECT: swizzle key of voxel (wl, dd) is (cd0 + dd) & 7
 #pragma unroll 4
         for (int dd = 0; dd < D; ++dd) {
             const int rj = my_row[dd];
@@ -1132,9 +1166,10 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
             exc |= (active && rj >= 0 && !same) ? 1u : 0u;
             const float pj = (active && same) ? my_p[dd] : 0.f;       // dropped: the staged row is zero anyway
             float dot = 0.f;
+            const int swz = DIRECT ? ((gl ^ ((cd0 + dd) & 7)) - gl) : 0;        // my_sg already points at chunk gl
 #pragma unroll
             for (int q = 0; q < CPL / 4; ++q) {
-                const float4 v = my_sg[dd * c4 + 8 * q];
+                const float4 v = my_sg[dd * c4 + 8 * q + swz];
                 dot = fmaf(v.x, ctx[4 * q], dot); dot = fmaf(v.y, ctx[4 * q + 1], dot);
                 dot = fmaf(v.z, ctx[4 * q + 2], dot); dot = fmaf(v.w, ctx[4 * q + 3], dot);
                 dctx[4 * q] = fmaf(pj, v.x, dctx[4 * q]); dctx[4 * q + 1] = fmaf(pj, v.y, dctx[4 * q + 1]);
@@ -1154,9 +1189,17 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
                 const float pj = mine ? my_p[dd] : 0.f;
                 float dot = 0.f;
                 if (mine) {
+                    const int qz = DIRECT ? rj / plane : 0;
+                    const float *gsrc = grows + (size_t)(qz * C) * plane + (rj - qz * plane);   // DIRECT: voxel rj in the NCHW tensor
 #pragma unroll
                     for (int q = 0; q < CPL / 4; ++q) {
-                        const float4 v = __ldg(rows4 + (size_t)rj * c4 + 8 * q);
+                        float4 v;
+                        if (DIRECT) {
+                            const float *gp4 = gsrc + (size_t)(4 * (gl + 8 * q)) * plane;
+                            v = make_float4(__ldg(gp4), __ldg(gp4 + plane), __ldg(gp4 + 2 * (size_t)plane), __ldg(gp4 + 3 * (size_t)plane));
+                        } else {
+                            v = __ldg(rows4 + (size_t)rj * c4 + 8 * q);
+                        }
                         dot = fmaf(v.x, ctx[4 * q], dot); dot = fmaf(v.y, ctx[4 * q + 1], dot);
                         dot = fmaf(v.z, ctx[4 * q + 2], dot); dot = fmaf(v.w, ctx[4 * q + 3], dot);
                         dctx[4 * q] = fmaf(pj, v.x, dctx[4 * q]); dctx[4 * q + 1] = fmaf(pj, v.y, dctx[4 * q + 1]);
@@ -1616,7 +1659,23 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
                            const float *grad_bev, const float *prob_col, const float *ctx_t, float *grows, float *grad_dn,
                            int stage, int b0, int b1, cudaStream_t s) {
     const int tps = tl.n_tiles / d.B;                     // tiles per sample
-    if (stage != 2) {
+    const int WC = max(1, 32 / d.fH);
+    const dim3 grid((d.fW + WC - 1) / WC, (b1 - b0) * d.N);
+    auto magic = [](unsigned x) { return ((1ull << 40) + x - 1) / x; };
+    const GpxMagic mg{magic((unsigned)(d.D * d.fH)), magic((unsigned)d.fH), magic((unsigned)(d.fH * WC)), magic((unsigned)WC)};
+    size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16 + (size_t)WC * d.D * 4;  // staged gradient rows (+ alignment, + offsets), if they fit next to a second CTA
+    const int stage_rows = smem + rows_smem <= 100 * 1024;
+    if (stage_rows) smem += rows_smem;
+    // Experiment (LSS_BWD_DIRECT=1): gradient rows straight from the NCHW tensor inside the gather, no rows kernel.
+    // Measured at cfg 2: 83 us for the fused kernel against 16 + 16 us for the two kernels -- 288 CTAs issuing ~10 k
+    // 4-byte cp.async each have far less memory-level parallelism than the tile-owner rows kernel (1600 CTAs, 8
+    // independent loads per lane): OFF.
+    static int direct_knob = getenv("LSS_BWD_DIRECT") ? atoi(getenv("LSS_BWD_DIRECT")) : 0;
+    const bool direct = direct_knob && !cl && stage_rows && (size_t)d.B * d.nz * d.C * d.nx * d.ny < ((size_t)1 << 31);
+    if (direct && stage == 1) return LSS_OK;              // (stage 1 = the rows kernel alone: nothing to do)
+    if (!direct && stage != 2) {
         const cudaError_t e = cl
             ? lss_launch(k_bwd_rows_compact<true>, dim3((b1 - b0) * tps), dim3(SPLAT_THREADS), 0, s, true, d, tl, b0 * tps,
                          pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows)
@@ -1626,22 +1685,18 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
         LSS_CHECK_LAUNCH();
         if (stage == 1) return LSS_OK;
     }
-    const int WC = max(1, 32 / d.fH);
-    const dim3 grid((d.fW + WC - 1) / WC, (b1 - b0) * d.N);
-    auto magic = [](unsigned x) { return ((1ull << 40) + x - 1) / x; };
-    const GpxMagic mg{magic((unsigned)(d.D * d.fH)), magic((unsigned)d.fH), magic((unsigned)(d.fH * WC)), magic((unsigned)WC)};
-    size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
-    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-    const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16;  // staged gradient rows (+ alignment), if they fit next to a second CTA
-    const int stage_rows = smem + rows_smem <= 100 * 1024;
-    if (stage_rows) smem += rows_smem;
 #define GPX(CPL)                                                                                                 \
     do {                                                                                                         \
-        static bool configured = false;                                                                          \
-        int st = opt_in_smem(k_bwd_gather_px<CPL>, smem, configured);                                            \
+        static bool configured = false, configured_d = false;                                                    \
+        int st = direct ? opt_in_smem(k_bwd_gather_px<CPL, true>, smem, configured_d)                            \
+                        : opt_in_smem(k_bwd_gather_px<CPL, false>, smem, configured);                            \
         if (st != LSS_OK) return st;                                                                             \
-        if (lss_launch(k_bwd_gather_px<CPL>, grid, dim3(SPLAT_THREADS), smem, s, stage != 2, d, b0 * d.N, WC, stage_rows, mg, prow, prob_col, \
-                       ctx_t, grows, grad_dn) != cudaSuccess) return LSS_ERR_CUDA;                                            \
+        const cudaError_t e = direct                                                                             \
+            ? lss_launch(k_bwd_gather_px<CPL, true>, grid, dim3(SPLAT_THREADS), smem, s, true, d, b0 * d.N, WC, stage_rows, mg, \
+                         pp.vox, prob_col, ctx_t, grad_bev, grad_dn)                                             \
+            : lss_launch(k_bwd_gather_px<CPL, false>, grid, dim3(SPLAT_THREADS), smem, s, stage != 2, d, b0 * d.N, WC, stage_rows, mg, \
+                         prow, prob_col, ctx_t, (const float *)grows, grad_dn);                                  \
+        if (e != cudaSuccess) return LSS_ERR_CUDA;                                                               \
     } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
 #undef GPX
