@@ -679,7 +679,9 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
     // the histogram scan rides in the scatter kernel when its table fits shared memory (LSS_SCAN_IN_SCATTER=0: old path)
     static const int scan_knob = getenv("LSS_SCAN_IN_SCATTER") ? atoi(getenv("LSS_SCAN_IN_SCATTER")) : 1;
     const size_t scan_smem = ((size_t)tl.n_tiles + 1) * sizeof(int);
-    const bool scan_in_scatter = scan_knob && scan_smem <= 64 * 1024;
+    // ... and is one 2048-counter step: every scatter CTA repeats the scan, which stops paying with many tiles AND many
+    // CTAs (cfg 4, 6400 tiles x 3895 CTAs: plan 138.7 us with the scan in the scatter kernel, 122.6 us with the ticket path)
+    const bool scan_in_scatter = scan_knob && tl.n_tiles <= 2048 && scan_smem <= 64 * 1024;
     const int grid_vi = (grid + 1) / 2;
 #define VI_ARGS d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count, tile_start, cursor, sync, counters, key_count, prow
     if (geom != nullptr) {
