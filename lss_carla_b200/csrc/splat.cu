@@ -700,6 +700,94 @@ k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ til
     }
 }
 
+// (2a') k_fwd_store_rows_persist (experiment, off: see launch_fwd_store) -- the same row store as a PERSISTENT,
+// software-pipelined kernel: a CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... with two shared-memory stages.  While tile i streams out, the column list and the
+// compact rows of tile i+1 are already on their way into the other stage (cp.async, no registers), and the meta words of
+// tile i+2 are in flight into registers: after a CTA's first tile the dependent loads in front of the store stream are
+// hidden, so the SM keeps storing.  Rows are staged with a stride of C + 4 floats (16-byte aligned for cp.async; the
+// lanes of a warp read one channel of different rows, 8 distinct bank groups).
+__global__ void __launch_bounds__(SPLAT_THREADS, STORE_ROWS_MINB)
+k_fwd_store_rows_persist(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__restrict__ tile_start,
+                         const int32_t *__restrict__ tile_nseg, const int32_t *__restrict__ tile_row0,
+                         const uint32_t *__restrict__ segs, const float *__restrict__ vsum, float *__restrict__ bev) {
+    extern __shared__ __align__(16) float sm_p[];
+    const int C = d.C, SR = C + 4, c4 = C >> 2;
+    const int stage_floats = ROWS_CAP * SR;
+    const int TYp = (tl.TY + 7) & ~7;
+    uint32_t *s_segs = reinterpret_cast<uint32_t *>(sm_p + 2 * stage_floats);      // [2][TYp]
+    short *s_map = reinterpret_cast<short *>(s_segs + 2 * TYp);                    // [TYp]
+    const unsigned rows_addr = (unsigned)__cvta_generic_to_shared(sm_p);
+    const unsigned segs_addr = (unsigned)__cvta_generic_to_shared(s_segs);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    int tn = t + gridDim.x;
+    int c_nseg = __ldg(tile_nseg + tile_lo + t), c_s = __ldg(tile_start + tile_lo + t), c_row0 = __ldg(tile_row0 + tile_lo + t);
+    int n_nseg = 0, n_s = 0, n_row0 = 0;
+    if (tn < n_tiles) { n_nseg = __ldg(tile_nseg + tile_lo + tn); n_s = __ldg(tile_start + tile_lo + tn); n_row0 = __ldg(tile_row0 + tile_lo + tn); }
+    auto issue = [&](int nseg, int s, int row0, int b) {      // column list + compact rows of one tile -> stage b
+        if (nseg > 0) {
+            for (int k = threadIdx.x; k < nseg; k += SPLAT_THREADS)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(segs_addr + 4u * (unsigned)(b * TYp + k)), "l"(segs + s + k) : "memory");
+            const int nq = min(nseg, ROWS_CAP) * c4;
+            const float4 *rsrc = reinterpret_cast<const float4 *>(vsum + (size_t)row0 * C);    // the tile's rows are one block
+            for (int i = threadIdx.x; i < nq; i += SPLAT_THREADS) {
+                const int k = i / c4, q = i - k * c4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rows_addr + 4u * (unsigned)(b * stage_floats + k * SR + 4 * q)), "l"(rsrc + i) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    lss_pdl_wait();                                               // the compact rows come from the gather kernel
+    issue(c_nseg, c_s, c_row0, 0);
+    for (int b = 0; t < n_tiles; b ^= 1) {
+        const int tnn = tn + gridDim.x;
+        int nn_nseg = 0, nn_s = 0, nn_row0 = 0;
+        if (tnn < n_tiles) { nn_nseg = __ldg(tile_nseg + tile_lo + tnn); nn_s = __ldg(tile_start + tile_lo + tnn); nn_row0 = __ldg(tile_row0 + tile_lo + tnn); }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                          // stage b has landed; everybody is done with the previous tile
+        const TileCoord tc = tile_coord(d, tl, tile_lo + t);
+        const Tile2D t2 = tile_2d<false>(d, tl, tc);
+        if (c_nseg == 0) {                                        // CTA-uniform
+            issue(n_nseg, n_s, n_row0, b ^ 1);
+            store_tile<true>(t2, nullptr, bev);
+        } else {
+            for (int i = threadIdx.x; i < TYp / 2; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
+            __syncthreads();
+            for (int k = threadIdx.x; k < c_nseg; k += SPLAT_THREADS) s_map[s_segs[b * TYp + k] >> LSS_PIDX_BITS] = (short)k;
+            issue(n_nseg, n_s, n_row0, b ^ 1);                    // next tile on its way while this one is stored
+            __syncthreads();
+            const float *s_rows = sm_p + b * stage_floats;
+            const float *rows_g = vsum + (size_t)c_row0 * C;
+            const int vpr = t2.RL >> 2;
+            for (int v0 = lane; v0 < vpr; v0 += 32) {
+                const uint2 m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
+                const int k0 = (short)(m.x & 0xFFFFu), k1 = (short)(m.x >> 16), k2 = (short)(m.y & 0xFFFFu), k3 = (short)(m.y >> 16);
+                float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
+                const size_t gstep = (size_t)SPLAT_WARPS * t2.GRS / 4;
+                if (c_nseg <= ROWS_CAP) {
+                    const float *p0 = s_rows + max(k0, 0) * SR, *p1 = s_rows + max(k1, 0) * SR;
+                    const float *p2 = s_rows + max(k2, 0) * SR, *p3 = s_rows + max(k3, 0) * SR;
+#pragma unroll 4
+                    for (int c = warp; c < C; c += SPLAT_WARPS, gp += gstep) {
+                        float4 o;
+                        o.x = k0 >= 0 ? p0[c] : 0.f; o.y = k1 >= 0 ? p1[c] : 0.f;
+                        o.z = k2 >= 0 ? p2[c] : 0.f; o.w = k3 >= 0 ? p3[c] : 0.f;
+                        *gp = o;
+                    }
+                } else {
+                    auto val = [&](int k, int c) { return k < 0 ? 0.f : (k < ROWS_CAP ? s_rows[k * SR + c] : __ldg(rows_g + (size_t)k * C + c)); };
+                    for (int c = warp; c < C; c += SPLAT_WARPS, gp += gstep) *gp = make_float4(val(k0, c), val(k1, c), val(k2, c), val(k3, c));
+                }
+            }
+        }
+        t = tn; tn = tnn;
+        c_nseg = n_nseg; c_s = n_s; c_row0 = n_row0;
+        n_nseg = nn_nseg; n_s = nn_s; n_row0 = nn_row0;
+    }
+}
+
 // (2b) k_fwd_store_tma -- the same streaming store as a PERSISTENT kernel: every CTA walks tiles with two staging
 // buffers.  The rows of the staged tile leave through the bulk-copy engine (cp.async.bulk shared -> global, issued by
 // one warp), so the CTA does not wait for its stores: while tile k drains it zero-fills the other buffer and
@@ -1363,6 +1451,30 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
     if (rows_mode && !CL && VEC4 && CH == d.C && getenv("LSS_STORE_ZERO") == nullptr && tl.TY <= 32767) {
         const size_t rsm = (size_t)(ROWS_CAP * (d.C + 1) + 1) * 4 + (size_t)((tl.TY + 7) / 8) * 16;
         const int tpsr = tl.n_tiles / d.B;
+        // persistent, software-pipelined variant (experiment, LSS_STORE_PERSIST=1).  Measured at cfg 2: 23.2 us against
+        // 20.5 us for one CTA per tile (forward 37.4 vs 33.1 us) -- like the earlier persistent stores, the statically
+        // strided CTAs lose more to their lock-step start and uneven tile counts than the hidden prologues win: OFF.
+        static int persist = getenv("LSS_STORE_PERSIST") ? atoi(getenv("LSS_STORE_PERSIST")) : 0;
+        const int TYp = (tl.TY + 7) & ~7;
+        const size_t psm = (size_t)2 * ROWS_CAP * (d.C + 4) * 4 + (size_t)2 * TYp * 4 + (size_t)TYp * 2;
+        if (persist && !skipz && psm <= 100 * 1024) {
+            static bool configured_p = false;
+            int stp = opt_in_smem(k_fwd_store_rows_persist, psm, configured_p);
+            if (stp != LSS_OK) return stp;
+            static int per_sm_p = 0;
+            static size_t per_sm_p_smem = 0;
+            if (per_sm_p == 0 || per_sm_p_smem != psm) {
+                int nb = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fwd_store_rows_persist, SPLAT_THREADS, psm) != cudaSuccess || nb < 1) nb = 1;
+                per_sm_p = nb; per_sm_p_smem = psm;
+            }
+            const int n_t = (b1 - b0) * tpsr;
+            const int grid_p = min(n_t, num_sms() * per_sm_p);
+            if (lss_launch(k_fwd_store_rows_persist, dim3(grid_p), dim3(SPLAT_THREADS), psm, s, pdl, d, tl, b0 * tpsr, n_t,
+                           pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
+            LSS_CHECK_LAUNCH();
+            return LSS_OK;
+        }
         static int lean = getenv("LSS_STORE_LEAN") ? atoi(getenv("LSS_STORE_LEAN")) : 1;
         auto kern = skipz ? k_fwd_store_rows<true, true> : (lean ? k_fwd_store_rows<true, false> : k_fwd_store_rows<false, false>);
         if (lss_launch(kern, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
