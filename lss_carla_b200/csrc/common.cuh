@@ -71,7 +71,7 @@ struct Dims {
     int n_points;  // B*P
     float dx[3], lo[3];
     float inv_dx[3];   // 1/dx where dx is a power of two (x / dx == x * (1/dx) bit for bit), else 0: true division
-    unsigned long long mDHW, mHW;   // ceil(2^40 / DHW), ceil(2^40 / HW): exact division of a 20-bit point index
+    unsigned long long mDHW, mHW, mfW;   // ceil(2^40 / DHW), ceil(2^40 / HW), ceil(2^40 / fW): exact division of a 20-bit point index
 };
 
 // x / divisor for x < 2^20, divisor < 2^20, with m = ceil(2^40 / divisor)
@@ -95,6 +95,7 @@ static inline Dims make_dims(const lss_problem *p) {
     }
     d.mDHW = ((1ull << 40) + (unsigned)d.DHW - 1) / (unsigned)d.DHW;
     d.mHW = ((1ull << 40) + (unsigned)d.HW - 1) / (unsigned)d.HW;
+    d.mfW = ((1ull << 40) + (unsigned)d.fW - 1) / (unsigned)d.fW;
     return d;
 }
 
@@ -114,7 +115,7 @@ __device__ __forceinline__ unsigned lss_column_major(const Dims &d, unsigned pid
     const unsigned r = pidx - cam * d.DHW;
     const unsigned dd = lss_div20(r, d.mHW);
     const unsigned hw = r - dd * d.HW;
-    const unsigned h = hw / (unsigned)d.fW, w = hw - h * d.fW;
+    const unsigned h = lss_div20(hw, d.mfW), w = hw - h * d.fW;
     return ((cam * d.fW + w) * d.D + dd) * d.fH + h;
 }
 

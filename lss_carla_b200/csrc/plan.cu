@@ -423,7 +423,7 @@ __device__ __forceinline__ void emit_voxel_record(const Dims &d, int b, uint32_t
     const unsigned r = pidx - cam * d.DHW;
     const unsigned dd = lss_div20(r, d.mHW);
     const unsigned hw = r - dd * d.HW;
-    const unsigned h = hw / (unsigned)d.fW, w = hw - h * d.fW;
+    const unsigned h = lss_div20(hw, d.mfW), w = hw - h * d.fW;
     const int key = (b * d.N + (int)cam) * d.fW + (int)w;
     const int slot = atomicAdd(key_count + key, 1);
     const bool pure = kind == 0 && len == d.fH && h == 0;
@@ -495,7 +495,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
             if (rank == 0) { cursor[col] = (int)e; continue; }       // the first point itself is kind 0 (cursor is free again)
             const unsigned p = e & LSS_PIDX_MASK, p0 = first & LSS_PIDX_MASK;
             const unsigned delta = p - p0;
-            const bool col_aligned = delta % (unsigned)d.fW == 0u;
+            const bool col_aligned = delta - lss_div20(delta, d.mfW) * (unsigned)d.fW == 0u;   // delta < 2^20
             if (delta < span && col_aligned) continue;                                       // kind 0
             const bool same_col = col_aligned && lss_div20(p, d.mDHW) == lss_div20(p0, d.mDHW);
             atomicMax(mixed + col, same_col ? 1 : 2);

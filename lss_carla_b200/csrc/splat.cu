@@ -468,7 +468,7 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
                 const unsigned rr = pidx - cam * d.DHW;
                 const unsigned dd = lss_div20(rr, d.mHW);
                 const unsigned hw = rr - dd * d.HW;
-                const unsigned h = hw / (unsigned)d.fW, ww = hw - h * d.fW;
+                const unsigned h = lss_div20(hw, d.mfW), ww = hw - h * d.fW;
                 if ((int)cam == n0 && (int)ww == w0) { ro = ~(int)(h * C); w = s_prob[dd * d.fH + h]; }
                 else { ro = (int)((cam * d.HW + hw) * C); w = __ldg(prob_b + pidx); }
             }
