@@ -601,8 +601,8 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
 // already zero-filled by the zero-role CTAs that ride at the end of the gather grid (k_fwd_gather, ZeroArgs), in the
 // shadow of the gather's tail; this kernel then writes the remaining sectors only (a sector is always written whole
 // and by one kernel).  Both sides derive "empty sector" from the tile's column list in the same way.
-template <bool LEAN, bool SKIPZ>
-__global__ void __launch_bounds__(SPLAT_THREADS, STORE_ROWS_MINB)
+template <bool LEAN, bool SKIPZ, int MINB = STORE_ROWS_MINB>
+__global__ void __launch_bounds__(SPLAT_THREADS, MINB)
 k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                  const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
                  float *__restrict__ bev) {
@@ -1476,7 +1476,8 @@ static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp,
             return LSS_OK;
         }
         static int lean = getenv("LSS_STORE_LEAN") ? atoi(getenv("LSS_STORE_LEAN")) : 1;
-        auto kern = skipz ? k_fwd_store_rows<true, true> : (lean ? k_fwd_store_rows<true, false> : k_fwd_store_rows<false, false>);
+        static int minb = getenv("LSS_STORE_MINB") ? atoi(getenv("LSS_STORE_MINB")) : 4;      // tuning knob: CTAs per SM the registers allow
+        auto kern = skipz ? k_fwd_store_rows<true, true> : (lean ? (minb == 5 ? k_fwd_store_rows<true, false, 5> : k_fwd_store_rows<true, false>) : k_fwd_store_rows<false, false>);
         if (lss_launch(kern, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
                        pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
         LSS_CHECK_LAUNCH();
