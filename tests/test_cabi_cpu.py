@@ -112,3 +112,15 @@ def test_no_cpu_fallback():
     import lss_carla_b200.ops as ops_src
     src = open(ops_src.__file__).read()
     assert "oracle" not in src.replace("# oracle", ""), "product code must not import the oracle"
+
+
+def test_pipe_stage_rejects_bad_arguments_without_touching_cuda():
+    """lss_pipe_stage validates its arguments before any CUDA call (more than 4 copies, copies without arrays)."""
+    import ctypes as C
+    from lss_carla_b200 import _lib
+    L = _lib.lib()
+    assert L.lss_pipe_stage(None, None, None, 5, None, None, None, None) != 0
+    assert L.lss_pipe_stage(None, None, None, 1, None, None, None, None) != 0
+    assert L.lss_pipe_stage(None, None, None, -1, None, None, None, None) != 0
+    assert L.lss_pipe_event_synchronize(None) != 0
+    assert L.lss_pipe_event_destroy(None) == 0
