@@ -65,6 +65,7 @@ SIGNATURES = {
     "lss_plan_build_raw": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
     "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
+    "lss_lift_prepare_bf16": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
     "lss_debug_set_timeline": (C.c_int, [_P, _P]),
     "lss_pipe_event_create": (C.c_void_p, []),
     "lss_pipe_event_destroy": (C.c_int, [_P]),

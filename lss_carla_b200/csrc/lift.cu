@@ -10,14 +10,22 @@
 // One CTA owns 32 consecutive pixels of one camera: all D+C channel rows of those pixels are read ONCE
 // (128-byte lines) into shared memory, the softmax runs out of shared memory, and the context tile is
 // written back transposed.
+// The depthnet output may also arrive as bfloat16 (autocast training): it is widened on load, everything after the
+// load -- softmax, the splat, the accumulation -- is the float32 path bit for bit (lss_lift_prepare_bf16).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 #define LIFT_PX 32        // pixels per CTA (one 128-byte line of every channel row)
 #define LIFT_THREADS 256  // 8 warps: warp w owns depth bins / channels w, w+8, ...
 #define LIFT_WARPS 8
 
+__device__ __forceinline__ float lift_load(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float lift_load(const __nv_bfloat16 *p) { return __bfloat162float(__ldg(p)); }
+
+template <typename T>
 __global__ void __launch_bounds__(LIFT_THREADS)
-k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, float *__restrict__ ctx_t,
+k_lift_prepare(Dims d, const T *__restrict__ dn, float *__restrict__ prob, float *__restrict__ ctx_t,
                float *__restrict__ prob_col) {
     extern __shared__ float smem[];                 // [D+C][33]
     __shared__ float s_red[LIFT_WARPS][LIFT_PX];
@@ -28,10 +36,10 @@ k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, f
     const int hw = hw0 + lane;
     const bool live = hw < d.HW;
     const int DC = d.D + d.C;
-    const float *src = dn + (size_t)bn * DC * d.HW + hw;
+    const T *src = dn + (size_t)bn * DC * d.HW + hw;
     constexpr int S = LIFT_PX + 1;
 
-    for (int r = warp; r < DC; r += LIFT_WARPS) smem[r * S + lane] = live ? __ldg(src + (size_t)r * d.HW) : 0.f;
+    for (int r = warp; r < DC; r += LIFT_WARPS) smem[r * S + lane] = live ? lift_load(src + (size_t)r * d.HW) : 0.f;
     __syncthreads();
 
     // ---- softmax over depth (models.py:50,58): max, exp, sum, normalise -- one exp per element
@@ -73,8 +81,8 @@ k_lift_prepare(Dims d, const float *__restrict__ dn, float *__restrict__ prob, f
         for (int c = lane; c < d.C; c += 32) cdst[(size_t)px * d.C + c] = ct[c * S + px];
 }
 
-extern "C" int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
-                                float *prob_col, void *stream) {
+template <typename T>
+static int lift_prepare_impl(const lss_problem *p, const T *depthnet_out, float *prob, float *ctx_t, float *prob_col, void *stream) {
     int st = lss_check_problem(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(depthnet_out && prob && ctx_t, LSS_ERR_BAD_ARG);
@@ -83,9 +91,19 @@ extern "C" int lss_lift_prepare(const lss_problem *p, const float *depthnet_out,
     const size_t smem = (size_t)(d.D + d.C) * (LIFT_PX + 1) * sizeof(float);
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
     if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(k_lift_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(k_lift_prepare<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return LSS_ERR_CUDA;
-    k_lift_prepare<<<d.B * d.N * chunks, LIFT_THREADS, smem, (cudaStream_t)stream>>>(d, depthnet_out, prob, ctx_t, prob_col);
+    k_lift_prepare<T><<<d.B * d.N * chunks, LIFT_THREADS, smem, (cudaStream_t)stream>>>(d, depthnet_out, prob, ctx_t, prob_col);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
+}
+
+extern "C" int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *prob, float *ctx_t,
+                                float *prob_col, void *stream) {
+    return lift_prepare_impl<float>(p, depthnet_out, prob, ctx_t, prob_col, stream);
+}
+
+extern "C" int lss_lift_prepare_bf16(const lss_problem *p, const void *depthnet_out_bf16, float *prob, float *ctx_t,
+                                     float *prob_col, void *stream) {
+    return lift_prepare_impl<__nv_bfloat16>(p, (const __nv_bfloat16 *)depthnet_out_bf16, prob, ctx_t, prob_col, stream);
 }

@@ -237,7 +237,13 @@ def reference_order(plan: Plan):
 def lift_prepare(prob: Problem, depthnet_out, out=None):
     """softmax over depth + pixel-major context (models.py:49-61) -> (prob [BN,D,fH,fW], ctx_t [BN,HW,C]).
     `out`: optional preallocated (f32[2,BN,D,fH,fW], f32[BN,HW,C]) pair, e.g. when the call runs on a side stream."""
-    x = _f32c(depthnet_out, "depthnet_out")
+    bf16 = depthnet_out.dtype == torch.bfloat16     # autocast: widened on load, float32 from there on (lss_lift_prepare_bf16)
+    if bf16:
+        if not depthnet_out.is_cuda:
+            raise RuntimeError("depthnet_out must be a CUDA tensor: the lift-splat path has no CPU implementation")
+        x = depthnet_out.contiguous()
+    else:
+        x = _f32c(depthnet_out, "depthnet_out")
     BN, HW = prob.B * prob.N, prob.fH * prob.fW
     if tuple(x.shape) != (BN, prob.D + prob.C, prob.fH, prob.fW):
         raise ValueError(f"depthnet_out has shape {tuple(x.shape)}, expected {(BN, prob.D + prob.C, prob.fH, prob.fW)}")
@@ -247,7 +253,8 @@ def lift_prepare(prob: Problem, depthnet_out, out=None):
         both = torch.empty((2, BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device)
         ct = torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device)
     pr = both[0]                                   # [BN, D, fH, fW]; both[1] holds the column-major copy [BN, fW, D, fH]
-    check(lib().lss_lift_prepare(C.byref(prob.c), _ptr(x), _ptr(pr), _ptr(ct), _ptr(both[1]), _stream()), "lss_lift_prepare")
+    fn = lib().lss_lift_prepare_bf16 if bf16 else lib().lss_lift_prepare
+    check(fn(C.byref(prob.c), _ptr(x), _ptr(pr), _ptr(ct), _ptr(both[1]), _stream()), "lss_lift_prepare")
     return pr, ct
 
 
@@ -376,7 +383,7 @@ class _LiftSplatFn(torch.autograd.Function):
     def forward(ctx, depthnet_out, prob, plan, mode, channels_last):
         pr, ct = lift_prepare(prob, depthnet_out)
         bev = splat_fwd(prob, plan, pr, ct, mode, channels_last)
-        ctx.prob, ctx.plan = prob, plan
+        ctx.prob, ctx.plan, ctx.in_dtype = prob, plan, depthnet_out.dtype
         ctx.save_for_backward(pr, ct, _prob_col(pr))
         plan.busy = bool(ctx.needs_input_grad[0])
         return bev
@@ -384,8 +391,10 @@ class _LiftSplatFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_bev):
         pr, ct, pc = ctx.saved_tensors
-        out = splat_bwd(ctx.prob, ctx.plan, grad_bev, pr, ct, prob_col=pc)
+        out = splat_bwd(ctx.prob, ctx.plan, grad_bev.float(), pr, ct, prob_col=pc)
         ctx.plan.busy = False
+        if ctx.in_dtype != torch.float32:          # bfloat16 input: the float32 gradient is rounded once, at the very end
+            out = out.to(ctx.in_dtype)
         return out, None, None, None, None
 
 

@@ -545,6 +545,32 @@ def test_step_graph_matches_eager_api_and_overlaps_safely():
         api.StepGraph(api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, device=dev()), hs[0], gb)
 
 
+def test_bf16_depthnet_output_is_the_f32_path_on_widened_inputs():
+    """bfloat16 depthnet output (autocast): lss_lift_prepare_bf16 widens on load, everything else is the float32 path --
+    BEV bit-identical to the float32 path on x.float(), gradient = that path's gradient rounded once to bfloat16.
+    Stated tolerance of the bf16 path against the float32 result on the UNROUNDED inputs: rtol 3e-2 / atol 3e-2."""
+    from lss_carla_b200 import api
+    cfg = CONFIGS["cfg1"]
+    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, inverse_mode="device", device=dev())
+    b = make_batch(cfg, 3, "train")
+    gb = make_bev_grad(cfg, 3).to(dev())
+    cal = [b[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans")]
+    x32 = b["depthnet_out"].to(dev())
+    outs = {}
+    for name, x in (("bf16", x32.bfloat16()), ("widened", x32.bfloat16().float()), ("f32", x32)):
+        x = x.clone().requires_grad_(True)
+        bev = ls(x, *cal)
+        bev.backward(gb)
+        outs[name] = (bev.detach(), x.grad)
+    assert outs["bf16"][0].dtype == torch.float32 and outs["bf16"][1].dtype == torch.bfloat16
+    assert torch.equal(outs["bf16"][0], outs["widened"][0])
+    assert torch.equal(outs["bf16"][1], outs["widened"][1].bfloat16())
+    torch.testing.assert_close(outs["bf16"][0], outs["f32"][0], rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(outs["bf16"][1].float(), outs["f32"][1], rtol=3e-2, atol=3e-2)
+    with pytest.raises(TypeError):
+        ls(x32.half(), *cal)
+
+
 def test_step_pipeline_matches_eager_api():
     """api.StepPipeline (copy-in stream, kernel graph on one compute stream, copy-out stream; several steps in flight,
     buffers re-used across rounds) == eager LiftSplat + autograd, bit for bit."""
