@@ -440,6 +440,7 @@ k_plan_sort(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, uint32_t 
     extern __shared__ int s_int[];                 // start[TY+1], cursor[TY], mixed[TY]
     __shared__ uint32_t s_grp[LSS_SORT_SMEM_CAP];
     __shared__ int s_warp[NT / 32];
+    lss_pdl_trigger();                             // the forward gather may be scheduled while this grid drains (it waits at its top)
     lss_pdl_wait();                                // the buckets come from k_plan_scatter
     const int t = blockIdx.x;
     if (clear_count != nullptr && threadIdx.x == 0) { clear_count[t] = 0; clear_cursor[t] = 0; }   // scratch of the next build

@@ -342,6 +342,8 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
     lss_pdl_trigger();                                   // PDL: the store kernel may start its prologue in our tail
+    lss_pdl_wait();                                      // launched programmatically behind the plan build (or lift_prepare):
+                                                         // everything below reads what those kernels wrote
     if ((int)blockIdx.x >= (int)gridDim.x - z.n_tiles) {  // zero role
         zero_empty_sectors(d, z, z.tile_lo + (int)blockIdx.x - ((int)gridDim.x - z.n_tiles));
         return;
@@ -607,6 +609,7 @@ k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ til
                  const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
                  float *__restrict__ bev) {
     extern __shared__ __align__(16) float s_rows[];               // [ROWS_CAP][C + 1], then short map[TY rounded to 8]
+    lss_pdl_trigger();                                            // a dependent launch (the backward's row gather) may be scheduled in our tail
     const int tile = tile_lo + blockIdx.x;
     const int C = d.C, SR = C + 1, c4 = C >> 2;
     short *s_map = reinterpret_cast<short *>(s_rows + ROWS_CAP * SR + (ROWS_CAP & 1));
@@ -1552,9 +1555,12 @@ static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, co
     const size_t gsm = max((size_t)(d.fH * d.C + d.D * d.fH), (size_t)(GATHER_THREADS / 8) * d.C) * 4;   // column operands / long-voxel products
     if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
 #define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, L_rows_cap, pp.entries, prob, prob_col, ctx_t, vsum, za
-    if (d.C == 32) k_fwd_gather<4><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
-    else if (d.C == 64) k_fwd_gather<8><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
-    else k_fwd_gather<16><<<grid, GATHER_THREADS, gsm, s>>>(GATHER_ARGS);
+    // programmatic launch: the grid is scheduled while its predecessor drains and waits at its top (launch latency only)
+    cudaError_t ge;
+    if (d.C == 32) ge = lss_launch(k_fwd_gather<4>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
+    else if (d.C == 64) ge = lss_launch(k_fwd_gather<8>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
+    else ge = lss_launch(k_fwd_gather<16>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
+    if (ge != cudaSuccess) return LSS_ERR_CUDA;
 #undef GATHER_ARGS
     }
     LSS_CHECK_LAUNCH();
