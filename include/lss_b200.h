@@ -284,6 +284,10 @@ int lss_quickcumsum_bwd(int64_t n, int32_t C, const float *grad_sums, const int3
 void *lss_pipe_event_create(void);
 int lss_pipe_event_destroy(void *event);
 int lss_pipe_event_synchronize(void *event);
+/* Pinned host memory for the blocks of a step.  write_combined != 0 allocates with cudaHostAllocWriteCombined (faster
+ * for the device to read over PCIe, slow for the CPU to read back: input blocks only).  NULL on failure. */
+void *lss_pipe_host_alloc(size_t bytes, int write_combined);
+int lss_pipe_host_free(void *ptr);
 /* One pipeline stage, enqueued with a single call: `stream` waits for wait_a and wait_b (each may be NULL), runs
  * n_copies (<= 4) cudaMemcpyAsync(dst[i], src[i], bytes[i], default kind: pinned host <-> device), then records
  * `record` (may be NULL).  Returns LSS_OK or LSS_ERR_CUDA. */

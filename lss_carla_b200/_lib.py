@@ -70,6 +70,8 @@ SIGNATURES = {
     "lss_pipe_event_create": (C.c_void_p, []),
     "lss_pipe_event_destroy": (C.c_int, [_P]),
     "lss_pipe_event_synchronize": (C.c_int, [_P]),
+    "lss_pipe_host_alloc": (C.c_void_p, [C.c_size_t, C.c_int]),
+    "lss_pipe_host_free": (C.c_int, [_P]),
     "lss_pipe_stage": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_size_t), _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),

@@ -159,13 +159,39 @@ CALIB_KEYS = ("rots", "trans", "intrins", "post_rots", "post_trans")
 _CALIB_FLOATS = {"rots": 9, "trans": 3, "intrins": 9, "post_rots": 9, "post_trans": 3}
 
 
-def pinned_step_buffers(B, N, channels, fH, fW, probe=1024):
+class _HostBlock:
+    """Pinned float32 host memory owned by the C library (lss_pipe_host_alloc), exposed as a torch tensor."""
+
+    def __init__(self, n_floats, write_combined):
+        import ctypes as C
+        from ._lib import lib
+        self.ptr = lib().lss_pipe_host_alloc(n_floats * 4, 1 if write_combined else 0)
+        if not self.ptr:
+            raise RuntimeError("liblss_b200: lss_pipe_host_alloc failed")
+        self.tensor = torch.frombuffer((C.c_float * n_floats).from_address(self.ptr), dtype=torch.float32)
+
+    def __del__(self):
+        try:
+            from ._lib import lib
+            lib().lss_pipe_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_step_buffers(B, N, channels, fH, fW, probe=1024, write_combined=None):
     """Pinned host buffers of one step for `StepPipeline`: ONE input block (`in_block`: the depthnet output followed by
     the five calibration tensors, 33 floats per camera) and ONE output block (`out_block`: input gradient, BEV probe); the
-    named entries are views, so a step is one copy host -> device and one back."""
+    named entries are views, so a step is one copy host -> device and one back.  `write_combined` (default: environment
+    LSS_PIPE_WC, off) allocates the INPUT block write-combined: the host only writes it."""
     n_x = B * N * channels * fH * fW
-    blk = torch.empty(n_x + B * N * 33, dtype=torch.float32).pin_memory()
-    h = {"in_block": blk, "depthnet_out": blk[:n_x].view(B * N, channels, fH, fW)}
+    if write_combined is None:
+        write_combined = os.environ.get("LSS_PIPE_WC", "0") == "1"
+    if write_combined:
+        owner = _HostBlock(n_x + B * N * 33, True)
+        blk = owner.tensor
+    else:
+        owner, blk = None, torch.empty(n_x + B * N * 33, dtype=torch.float32).pin_memory()
+    h = {"in_block": blk, "_in_owner": owner, "depthnet_out": blk[:n_x].view(B * N, channels, fH, fW)}
     off = n_x
     for k in CALIB_KEYS:
         n = _CALIB_FLOATS[k]

@@ -188,3 +188,17 @@ extern "C" int lss_pipe_stage(void *stream, void *wait_a, void *wait_b, int32_t 
     if (record && cudaEventRecord((cudaEvent_t)record, s) != cudaSuccess) return LSS_ERR_CUDA;
     return LSS_OK;
 }
+
+// Pinned host memory for the pipeline's blocks.  write_combined != 0: cudaHostAllocWriteCombined -- not snooped by the
+// CPU caches, faster for the device to read over PCIe, slow for the CPU to READ: only for buffers the host just writes
+// (the input block).
+extern "C" void *lss_pipe_host_alloc(size_t bytes, int write_combined) {
+    void *p = nullptr;
+    const unsigned flags = write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, flags) != cudaSuccess) return nullptr;
+    return p;
+}
+
+extern "C" int lss_pipe_host_free(void *p) {
+    return (p == nullptr || cudaFreeHost(p) == cudaSuccess) ? LSS_OK : LSS_ERR_CUDA;
+}
