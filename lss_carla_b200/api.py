@@ -205,13 +205,26 @@ def pinned_step_buffers(B, N, channels, fH, fW, probe=1024, write_combined=None)
 
 
 class PipelineStreams:
-    """The three streams a group of `StepPipeline`s shares: copy-in, compute, copy-out."""
+    """The streams a group of `StepPipeline`s shares: copy-in, compute, copy-out.  `copy_in_streams` > 1 spreads the
+    copy-in of consecutive steps over several streams (copy engines): two input blocks are then in flight over PCIe at
+    the same time, which raises the host -> device throughput where a single copy is latency-bound (environment
+    LSS_PIPE_H2D_STREAMS, default 2)."""
 
-    def __init__(self, device):
-        self.h2d, self.compute, self.d2h = (torch.cuda.Stream(device=device) for _ in range(3))
+    def __init__(self, device, copy_in_streams=None):
+        if copy_in_streams is None:
+            copy_in_streams = int(os.environ.get("LSS_PIPE_H2D_STREAMS", "2"))
+        self.h2d_all = [torch.cuda.Stream(device=device) for _ in range(max(1, copy_in_streams))]
+        self.h2d = self.h2d_all[0]
+        self.compute, self.d2h = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        self._next = 0
+
+    def next_h2d(self):
+        s = self.h2d_all[self._next % len(self.h2d_all)]
+        self._next += 1
+        return s
 
     def all(self):
-        return (self.h2d, self.compute, self.d2h)
+        return tuple(self.h2d_all) + (self.compute, self.d2h)
 
 
 class _Event:
@@ -299,7 +312,7 @@ class StepPipeline:
                          (C.c_size_t * 1)(host["in_block"].numel() * 4))
         self._out_args = ((P * 1)(host["out_block"].data_ptr()), (P * 1)(self.out_dev.data_ptr()),
                           (C.c_size_t * 1)(host["out_block"].numel() * 4))
-        self._s = tuple(C.c_void_p(st.cuda_stream) for st in streams.all())
+        self._s = tuple(C.c_void_p(st.cuda_stream) for st in (streams.next_h2d(), streams.compute, streams.d2h))
         cs = streams.compute
         cs.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cs):
