@@ -597,6 +597,13 @@ def main():
             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
             "algorithmic_bytes_per_launch": kbytes, "kernel_us": round(ksec * 1e6, 2),
             "kernel_share_of_step": round(ksec / step_s, 3),
+            # informational: the same kernel right behind its gather (compact rows L2-resident, programmatic launch), by
+            # difference of two direct measurements; `achieved` / `frac` above stay the conservative stand-alone figure
+            "kernel_in_forward": ({"us": round((stages["splat_fwd"] - stages["k_fwd_gather"]) * 1e6, 2),
+                                   "frac": round(kbytes / (stages["splat_fwd"] - stages["k_fwd_gather"]) / 1e9 / peak, 4),
+                                   "how": "lss_splat_fwd alone minus k_fwd_gather alone"}
+                                  if args.mode == "sorted" and "k_fwd_gather" in stages
+                                  and stages["splat_fwd"] > stages["k_fwd_gather"] else None),
             "forward_op": {"what": "lss_splat_fwd (all its launches), IN + G bytes", "bytes": fwd_bytes,
                            "us": round(stages["splat_fwd"] * 1e6, 2), "frac": round(fwd_bytes / stages["splat_fwd"] / 1e9 / peak, 4)},
             "step_algorithmic_bytes": fwd_bytes + bwd_bytes,
