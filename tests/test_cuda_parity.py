@@ -4,6 +4,7 @@ Integer / index results must be bit-exact; BEV values and gradients are compared
 tolerance (rtol 1e-4, atol 1e-5 in fp32), and bit-exactly wherever the summation order is defined.
 Nothing here reads /root/reference."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -569,6 +570,28 @@ def test_bf16_depthnet_output_is_the_f32_path_on_widened_inputs():
     torch.testing.assert_close(outs["bf16"][1].float(), outs["f32"][1], rtol=3e-2, atol=3e-2)
     with pytest.raises(TypeError):
         ls(x32.half(), *cal)
+
+
+def test_tuning_knobs_keep_the_bits():
+    """Every kernel variant behind a tuning knob (the library reads them once per process, hence the
+    subprocesses) reproduces the default build's BEV and input gradient bit for bit: the variants move the same float32
+    sums through different kernels, none of them may change a summation order."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def digest(env_extra):
+        env = dict(os.environ, **env_extra)
+        out = subprocess.run([_sys.executable, os.path.join(root, "scripts", "knob_check.py")], capture_output=True, text=True,
+                             env=env, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][-1]
+
+    want = digest({})
+    for knob in ({"LSS_STORE_LEAN": "0"}, {"LSS_STORE_MINB": "5"}, {"LSS_STORE_PERSIST": "1"}, {"LSS_FWD_ZSPLIT": "1"},
+                 {"LSS_BWD_DIRECT": "1"}, {"LSS_SORT_NT": "128"}, {"LSS_SCAN_IN_SCATTER": "0"}, {"LSS_NO_PDL": "1"},
+                 {"LSS_STORE_ROWS": "0"}):
+        assert digest(knob) == want, knob
 
 
 def test_step_pipeline_matches_eager_api():
