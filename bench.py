@@ -12,10 +12,11 @@ points/step = B*N*D*fH*fW (every frustum point, kept or not).
 Numbers in the JSON line
     value     Mpoints/s, whole job (all ranks), inputs resident in HBM, steps replayed as CUDA graphs,
               4 rotating buffer sets (> 126 MB L2) so no step finds its tensors in L2.
-    e2e       same metric through the public API (`lss_carla_b200.api.LiftSplat` + autograd) with HOST
-              (pinned) depthnet output + calibration copied in and the input gradient copied out per step.
-    roofline  dominant kernel (splat forward) alone: algorithmic bytes per launch / mean launch time,
-              against MEASURED_PEAKS.json hbm_gbs.
+    e2e       same metric through the public host-buffer API (`lss_carla_b200.api.StepPipeline.run`): per step the
+              pinned depthnet output + calibration block copied in, plan + lift-splat fwd/bwd as one CUDA graph, the
+              input gradient + a BEV probe copied out; `--e2e-mode graphs` / `--no-e2e-graph` select the older paths.
+    roofline  dominant HBM-bound kernel (the forward's store kernel) alone: algorithmic bytes per launch / mean launch
+              time, against MEASURED_PEAKS.json hbm_gbs; `kernel_in_forward` = the same kernel right behind its gather.
     cpu_baseline  oracle/ref_torch_cpu.py (the reference's ATen op chain) on the host cores, bounded sample.
 
 `--impl reference` times that CPU port as the reference arm (the reference is pure Python/PyTorch and
