@@ -241,6 +241,70 @@ int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
 int lss_debug_set_timeline(void *store_buf, void *gather_buf);
 
 /* ---------------------------------------------------------------------------------------------- */
+/* Run plan: the channels_last fast path of the fused level (default of bench.py and of the API)   */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* With the BEV in channels_last (physical [B, nx, ny, nz*C]; what bevencode.conv1, models.py:97-98,:118, is fed
+ * through cuDNN's NHWC kernels) every voxel is ONE contiguous C-float row, so the forward needs no tile-owner
+ * store and the backward no gradient transposition.  The plan shrinks accordingly: points are handled as RUNS --
+ * the fH image rows of one (camera, column, depth bin), which almost always share a voxel -- and nothing is sorted:
+ *   k_run_index     per point: geometry + voxel row (models.py:179-188, :212-221); per sub-run (the points of a run
+ *                   that share a voxel): one push on the voxel's list, size added to the voxel's point count
+ *   k_run_classify  a sub-run that is alone on its voxel's list is EXCLUSIVE (summed by its camera-column CTA straight
+ *                   from staged operands); the other voxels go to a queue {list head, points, row, batch}
+ *   forward         zero-fill (bulk-copy engine, may overlap the plan build) + one gather kernel that writes every
+ *                   non-empty voxel row ONCE (exclusive runs: fH staged products in image-row order; shared voxels:
+ *                   their points sorted by flat index first) -- the same per-voxel sequential float32 sum in
+ *                   ascending flat (b,n,d,h,w) order as LSS_SPLAT_SORTED, hence the same bits
+ *   backward        the pixel-owner gather reads gradient rows straight from the channels_last gradient
+ * voxel "row" r = ((b*nx + ix)*ny + iy)*nz + iz; its C floats start at element r*C of the channels_last tensor. */
+typedef struct lss_runplan_layout {
+    int64_t n_points;       /* B*N*D*fH*fW                                                                   */
+    int64_t n_runs;         /* B*N*fW*D                                                                      */
+    int64_t n_voxels;       /* B*nx*ny*nz                                                                    */
+    int64_t n_mixed_cap;    /* capacity (records) of mixed_recs                                              */
+    size_t off_prow;        /* int32 [B,N,fW,D,fH]  voxel row of the point or -1, camera-column major        */
+    size_t off_emask;       /* uint32[B,N,fW,D,fH]  != 0 at the first point of an EXCLUSIVE sub-run: bit j   */
+                            /*                      = image row h+j of the same run belongs to it            */
+    size_t off_sub;         /* int32 [n_points,2]   at the first point of every sub-run: {next sub-run on the voxel's */
+                            /*                      list (point index + 1, 0 = end), row mask}                    */
+    size_t off_pool;        /* uint32[n_points]     point-in-sample indices of the points of LONG voxels (unsorted) */
+    size_t off_mixed_recs;  /* int32 [n_mixed_cap,4] shared voxels {head of the list (point index + 1), points,   */
+                            /*                      voxel row, batch}; voxels with >= 64 points are stored from   */
+                            /*                      the END downwards as {first pool slot, points, row, batch}    */
+    size_t off_counters;    /* int32 [64]           [0] shared voxels < 64 points, [1] pool slots in use, [2] long voxels */
+    size_t off_cnt;         /* int32 [n_voxels]     scratch, all-zero between builds (points per voxel)           */
+    size_t off_head;        /* int32 [n_voxels]     scratch, all-zero between builds (list heads)                 */
+    size_t bytes;
+} lss_runplan_layout;
+
+/* Fill `out` for problem `p`.  LSS_ERR_UNSUPPORTED if fH > 32 (a run must fit a warp) or C is not 32 / 64 / 128:
+ * use the tile plan (lss_plan_build + lss_splat_fwd) for such shapes.  Host-only. */
+int lss_runplan_layout_init(const lss_problem *p, lss_runplan_layout *out);
+/* Zero the scratch grids of a freshly allocated workspace (they clean themselves afterwards). */
+int lss_runplan_reset(const lss_runplan_layout *L, void *workspace, void *stream);
+/* Build the run plan of one batch from calibration (replaces models.py:170-190 + :212-231).  Either the prepared
+ * matrices M1 = inverse(post_rots), M2 = rots @ inverse(intrins) are given (bit-exact w.r.t. the reference's host
+ * inverses) and rots / intrins / post_rots may be null, or M1 and M2 are null and the closed-form inverses of
+ * lss_calib_matrices are evaluated inside the kernel from the raw calibration. */
+int lss_runplan_build(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                      const float *post_trans, const float *M1, const float *M2, const float *trans,
+                      const float *rots, const float *intrins, const float *post_rots, void *stream);
+/* torch.zeros of models.py:240 through the bulk-copy engine (cp.async.bulk shared -> global): one thread per CTA
+ * issues the stores, so the kernel leaves the SMs to whatever runs next to it (the plan build, the lift).
+ * `part` of `n_parts`: zero only that slice of the tensor (callers chain the slices on a side stream next to the kernels
+ * of the plan build); (0, 1) = everything. */
+int lss_bev_zero(const lss_problem *p, float *bev, int part, int n_parts, void *stream);
+/* Forward: bev (channels_last, `precleared` != 0: already all-zero, else zero-filled here first) receives the sum of
+ * every non-empty voxel.  prob_col f32[B*N, fW, D, fH], ctx_t f32[B*N, fH*fW, C] from lss_lift_prepare. */
+int lss_liftsplat_fwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,
+                         const float *prob_col, const float *ctx_t, float *bev, int precleared, void *stream);
+/* Backward to the depthnet output from a channels_last BEV gradient (tools.py:212-219 + autograd of models.py:58-59). */
+int lss_liftsplat_bwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,
+                         const float *grad_bev, const float *prob_col, const float *ctx_t, float *grad_depthnet,
+                         void *stream);
+
+/* ---------------------------------------------------------------------------------------------- */
 /* Operator level: LiftSplatShoot.voxel_pooling(geom_feats, x) with a materialised x                */
 /* ---------------------------------------------------------------------------------------------- */
 

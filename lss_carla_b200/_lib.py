@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "liblss_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["plan.cu", "lift.cu", "splat.cu", "ops.cu"]
+SOURCES = ["plan.cu", "runplan.cu", "lift.cu", "splat.cu", "ops.cu"]
 HEADER = os.path.join(_ROOT, "include", "lss_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -37,6 +37,13 @@ class LssPlanLayout(C.Structure):
                 ("off_sync", C.c_size_t), ("bytes", C.c_size_t)]
 
 
+class LssRunplanLayout(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("n_runs", C.c_int64), ("n_voxels", C.c_int64), ("n_mixed_cap", C.c_int64),
+                ("off_prow", C.c_size_t), ("off_emask", C.c_size_t), ("off_sub", C.c_size_t), ("off_pool", C.c_size_t),
+                ("off_mixed_recs", C.c_size_t), ("off_counters", C.c_size_t), ("off_cnt", C.c_size_t),
+                ("off_head", C.c_size_t), ("bytes", C.c_size_t)]
+
+
 class LssLimits(C.Structure):
     _fields_ = [("max_points_per_sample", C.c_int32), ("max_tile_cols", C.c_int32),
                 ("max_depth_bins", C.c_int32), ("max_channels", C.c_int32)]
@@ -50,6 +57,7 @@ VARIANTS = {"auto": 0, "warp": 1, "group": 2, "group_gather": 3, "group_store": 
 _P = C.c_void_p
 _PP = C.POINTER(LssProblem)
 _PL = C.POINTER(LssPlanLayout)
+_PR = C.POINTER(LssRunplanLayout)
 
 # name -> (restype, argtypes); must list every symbol include/lss_b200.h declares
 SIGNATURES = {
@@ -75,6 +83,12 @@ SIGNATURES = {
     "lss_pipe_stage": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_size_t), _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
+    "lss_runplan_layout_init": (C.c_int, [_PP, _PR]),
+    "lss_runplan_reset": (C.c_int, [_PR, _P, _P]),
+    "lss_runplan_build": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lss_bev_zero": (C.c_int, [_PP, _P, C.c_int, C.c_int, _P]),
+    "lss_liftsplat_fwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, C.c_int, _P]),
+    "lss_liftsplat_bwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_voxel_pooling_fwd": (C.c_int, [_PP, _PL, _P, _P, C.POINTER(C.c_int64), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -95,7 +109,7 @@ def nvcc_path():
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into lss_carla_b200/liblss_b200.so for sm_100a (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), HEADER]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "geom.cuh"), HEADER]
     if not force and os.path.isfile(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
         return SO_PATH
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", SO_PATH]

@@ -141,6 +141,12 @@ __device__ __forceinline__ size_t voxel_row_offset_cl(int v, const Dims &d) {
     return ((size_t)((b * d.nx + ix) * (size_t)d.ny + iy)) * (size_t)(d.nz * d.C) + (size_t)iz * d.C;
 }
 
+// Pixel-owner backward gather over channel-contiguous gradient rows (defined in splat.cu, shared with runplan.cu):
+// `prow` int32[B,N,fW,D,fH] = row of the point's voxel or -1, `rows` = base of the rows (row r starts at element r*C) --
+// the compact rows of a sorted tile plan, or a channels_last BEV gradient itself (run plan).  C in {32, 64, 128}, fH <= 32.
+int lss_bwd_gather_rows(const Dims &d, const int32_t *prow, const float *prob_col, const float *ctx_t, const float *rows,
+                        float *grad_dn, int b0, int b1, bool pdl, cudaStream_t s);
+
 // Single-CTA exclusive scan of a[0..n) in place, a[n] = total (cold paths only: parity dump, run offsets).
 static __global__ void __launch_bounds__(1024) k_scan_single(int32_t *a, int n, int32_t *total) {
     __shared__ int s_warp[32];
@@ -164,5 +170,33 @@ static __global__ void __launch_bounds__(1024) k_scan_single(int32_t *a, int n, 
         __syncthreads();
     }
     if (threadIdx.x == 0) { a[n] = s_carry; if (total) *total = s_carry; }
+}
+
+// Bitonic sort of a[0..n) ascending by the whole CTA (shared or global memory; keys unique): all comparators point the same way ("flip" bitonic
+// network), so the virtual +inf padding beyond n never moves and n need not be a power of two.
+// Index arithmetic uses shifts only (k, j are powers of two).
+template <typename Keys>
+__device__ __forceinline__ void bitonic_sort_block(Keys a, int n) {
+    int m = 1, lm = 0;
+    while (m < n) { m <<= 1; ++lm; }
+    const int half = m >> 1;
+    for (int lk = 1; lk <= lm; ++lk) {
+        const int k = 1 << lk, hk = k >> 1;
+        for (int q = threadIdx.x; q < half; q += blockDim.x) {   // flip stage: i <-> i ^ (k-1)
+            const int i = ((q >> (lk - 1)) << lk) | (q & (hk - 1));
+            const int l = i ^ (k - 1);
+            if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+        }
+        __syncthreads();
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            for (int q = threadIdx.x; q < half; q += blockDim.x) {
+                const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
+                const int l = i + j;
+                if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+            }
+            __syncthreads();
+        }
+    }
 }
 

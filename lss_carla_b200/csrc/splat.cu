@@ -1773,6 +1773,31 @@ static bool bwd_compact_ok(const Dims &d, const float *ctx_t, const float *grows
     return (d.C == 32 || d.C == 64 || d.C == 128) && d.fH <= 32 && lss_aligned(ctx_t, 16) && lss_aligned(grows, 16);
 }
 
+int lss_bwd_gather_rows(const Dims &d, const int32_t *prow, const float *prob_col, const float *ctx_t, const float *rows,
+                        float *grad_dn, int b0, int b1, bool pdl, cudaStream_t s) {
+    if (!bwd_compact_ok(d, ctx_t, rows)) return LSS_ERR_UNSUPPORTED;
+    const int WC = max(1, 32 / d.fH);
+    const dim3 grid((d.fW + WC - 1) / WC, (b1 - b0) * d.N);
+    auto magic = [](unsigned x) { return ((1ull << 40) + x - 1) / x; };
+    const GpxMagic mg{magic((unsigned)(d.D * d.fH)), magic((unsigned)d.fH), magic((unsigned)(d.fH * WC)), magic((unsigned)WC)};
+    size_t smem = ((size_t)96 * d.D + (size_t)(d.D + d.C) * d.fH * WC) * 4;
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16;    // staged gradient rows (+ alignment), if they fit next to a second CTA
+    const int stage_rows = smem + rows_smem <= 100 * 1024;
+    if (stage_rows) smem += rows_smem;
+#define GPX(CPL)                                                                                                  \
+    do {                                                                                                          \
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_bwd_gather_px<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) \
+            return LSS_ERR_CUDA;                                                                                  \
+        if (lss_launch(k_bwd_gather_px<CPL, false>, grid, dim3(SPLAT_THREADS), smem, s, pdl, d, b0 * d.N, WC, stage_rows, mg, \
+                       prow, prob_col, ctx_t, rows, grad_dn) != cudaSuccess) return LSS_ERR_CUDA;                 \
+    } while (0)
+    if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
+#undef GPX
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
 // compact-row backward (sorted plans): gradient rows of the non-empty voxels, then the pixel-owner gather
 static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanPtrs &pp, const int32_t *prow,
                            const float *grad_bev, const float *prob_col, const float *ctx_t, float *grows, float *grad_dn,

@@ -40,15 +40,61 @@ def _fused_get_voxels(self, x, rots, trans, intrins, post_rots, post_trans):
 
 
 def lift_splat_from_depthnet(model, depthnet_out, rots, trans, intrins, post_rots, post_trans, plan=None):
-    """Geometry + lift + splat for a depthnet output [B*N, D+C, fH, fW] -> BEV [B, nz*C, nx, ny]."""
+    """Geometry + lift + splat for a depthnet output [B*N, D+C, fH, fW] -> BEV [B, nz*C, nx, ny].
+
+    `bev_channels_last` + `splat_mode="sorted"` take the run-plan path (ops.RunPlan): the BEV is zero-filled by the
+    bulk-copy kernel on a side stream while the plan is built, then every non-empty voxel row is written once."""
     B, N = trans.shape[:2]
     fH, fW = depthnet_out.shape[-2:]
     C = depthnet_out.shape[1] - model.D
     prob = _problem_for(model, B, N, fH, fW, C)
+    mode = getattr(model, "splat_mode", "sorted")
+    if plan is None and _use_runplan(model, prob):
+        dev = depthnet_out.device
+        cur, side = torch.cuda.current_stream(dev), _side_stream(model, dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            bev = ops.bev_zero(prob, dev)
+        plan = runplan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans)
+        cur.wait_stream(side)
+        bev.record_stream(cur)
+        return ops.lift_splat(depthnet_out, prob, plan, mode, True, bev_out=bev)
     if plan is None:
         plan = plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans)
-    return ops.lift_splat(depthnet_out, prob, plan, getattr(model, "splat_mode", "sorted"),
-                          getattr(model, "bev_channels_last", False))
+    return ops.lift_splat(depthnet_out, prob, plan, mode, getattr(model, "bev_channels_last", False))
+
+
+def _use_runplan(model, prob):
+    return (getattr(model, "bev_channels_last", False) and getattr(model, "splat_mode", "sorted") == "sorted"
+            and ops.runplan_supported(prob))
+
+
+def _side_stream(model, device):
+    streams = model.__dict__.setdefault("_lss_side_streams", {})
+    key = str(device)
+    if key not in streams:
+        streams[key] = torch.cuda.Stream(device=device)
+    return streams[key]
+
+
+def runplan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans):
+    """Run plan (voxel row per point, exclusive runs, shared-voxel queue) from the calibration of `forward`
+    (models.py:256).  inverse_mode "reference": M1/M2 from the reference's own torch calls (bit-identical geometry);
+    "device": closed-form inverses inside the kernel, no host round trip."""
+    ws = _cached_plan(model, prob, rots.device, run=True)
+    frustum = model.frustum.detach()
+    if getattr(model, "inverse_mode", "reference") == "device":
+        try:
+            return ops.build_runplan(prob, frustum, trans.reshape(-1, 3), post_trans.reshape(-1, 3), rots=rots, intrins=intrins,
+                                     post_rots=post_rots, plan=ws)
+        except RuntimeError as e:                  # tiny cameras: a CTA would span too many of them for the fused inverses
+            if "status -3" not in str(e):
+                raise
+            M1, M2 = ops.calib_matrices_device(rots, intrins, post_rots)
+    else:
+        M1, M2 = ops.calib_matrices_reference(rots, intrins, post_rots)
+    return ops.build_runplan(prob, frustum, trans.reshape(-1, 3), post_trans.reshape(-1, 3), M1=M1.reshape(-1, 3, 3),
+                             M2=M2.reshape(-1, 3, 3), plan=ws)
 
 
 def plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans):
@@ -58,8 +104,12 @@ def plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_tra
     mode = getattr(model, "splat_mode", "sorted")
     ws = _cached_plan(model, prob, rots.device)
     frustum = model.frustum.detach()
-    if getattr(model, "inverse_mode", "reference") == "device" and 256 // (prob.D * prob.fH * prob.fW) + 2 <= 8:
-        return ops.build_plan_raw(prob, frustum, rots, trans, intrins, post_rots, post_trans, sorted=(mode == "sorted"), plan=ws)
+    if getattr(model, "inverse_mode", "reference") == "device":
+        try:
+            return ops.build_plan_raw(prob, frustum, rots, trans, intrins, post_rots, post_trans, sorted=(mode == "sorted"), plan=ws)
+        except RuntimeError as e:                  # tiny cameras (LSS_ERR_UNSUPPORTED): separate calibration kernel
+            if "status -3" not in str(e):
+                raise
     M1, M2 = _calib_matrices(model, rots, intrins, post_rots)
     calib = (frustum, post_trans.reshape(-1, 3), M1.reshape(-1, 3, 3), M2.reshape(-1, 3, 3), trans.reshape(-1, 3))
     return ops.build_plan(prob, calib=calib, sorted=(mode == "sorted"), plan=ws)
@@ -79,16 +129,16 @@ def _problem_for(model, B, N, fH, fW, C):
     return cache[key]
 
 
-def _cached_plan(model, prob, device):
-    """Small pool of reusable plan workspaces per (problem, device).  A plan handed to a forward that
-    needs gradients stays busy until its backward ran (`ops._LiftSplatFn` toggles `busy`); if every
+def _cached_plan(model, prob, device, run=False):
+    """Small pool of reusable plan workspaces per (problem, device, kind).  A plan handed to a forward that
+    needs gradients stays busy until its backward ran or its graph died (`ops._LiftSplatFn`); if every
     pooled plan is busy a fresh one is allocated."""
     pool = model.__dict__.setdefault("_lss_plans", {})
-    lst = pool.setdefault((id(prob), str(device)), [])
+    lst = pool.setdefault((id(prob), str(device), run), [])
     for pl in lst:
         if not pl.busy:
             return pl
-    pl = ops.Plan(prob, device, getattr(model, "tile_cols", 0))
+    pl = ops.RunPlan(prob, device) if run else ops.Plan(prob, device, getattr(model, "tile_cols", 0))
     if len(lst) < 4:
         lst.append(pl)
     return pl

@@ -13,12 +13,15 @@ Reference functions replaced (paths under the reference root):
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import torch
 
 from . import _lib
-from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, VARIANTS, LssPlanLayout, LssProblem, check, lib)
+
+from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, VARIANTS, LssPlanLayout, LssProblem, LssRunplanLayout, check,
+                   lib)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,7 +98,8 @@ class Plan:
         self.ws = torch.zeros(self.layout.bytes, dtype=torch.uint8, device=device)   # scratch counters start at 0
         self.sorted = False
         self.built = False
-        self.busy = False     # True between a differentiable forward and its backward
+        self.busy = False     # True between a differentiable forward and its backward (or the death of its graph)
+        self.generation = 0   # bumped by every build: a backward checks that its plan was not rebuilt in between
 
     def _view(self, off, n, dtype):
         item = torch.empty(0, dtype=dtype).element_size()
@@ -199,6 +203,7 @@ def build_plan(prob: Problem, geom=None, calib=None, sorted: bool = True, plan: 
                                *[_ptr(t) for t in cal], 1 if sorted else 0, _stream()), "lss_plan_build")
     plan.sorted = bool(sorted)
     plan.built = True
+    plan.generation += 1
     plan._keepalive = (g, cal)
     return plan
 
@@ -214,6 +219,7 @@ def build_plan_raw(prob: Problem, frustum, rots, trans, intrins, post_rots, post
     check(lib().lss_plan_build_raw(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), *[_ptr(t) for t in ts],
                                    1 if sorted else 0, _stream()), "lss_plan_build_raw")
     plan.sorted, plan.built, plan._keepalive = bool(sorted), True, ts
+    plan.generation += 1
     return plan
 
 
@@ -320,6 +326,118 @@ def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# run plan: channels_last fast path (include/lss_b200.h, "Run plan")
+# ------------------------------------------------------------------------------------------------
+
+def runplan_supported(prob: Problem) -> bool:
+    """Shapes the run plan takes: a run (the fH image rows of one camera column and depth bin) fits a warp, C = 32/64/128."""
+    lay = LssRunplanLayout()
+    return lib().lss_runplan_layout_init(C.byref(prob.c), C.byref(lay)) == 0
+
+
+class RunPlan:
+    """Per-batch index structures of the channels_last path: voxel row per point, exclusive-run masks, shared-voxel queue."""
+
+    def __init__(self, prob: Problem, device):
+        self.prob = prob
+        self.layout = LssRunplanLayout()
+        check(lib().lss_runplan_layout_init(C.byref(prob.c), C.byref(self.layout)), "lss_runplan_layout_init")
+        self.ws = torch.zeros(self.layout.bytes, dtype=torch.uint8, device=device)   # scratch grids start at 0
+        self.built = False
+        self.busy = False
+        self.generation = 0
+
+    def _view(self, off, n, dtype):
+        item = torch.empty(0, dtype=dtype).element_size()
+        return self.ws[off:off + n * item].view(dtype)
+
+    @property
+    def prow(self):
+        """int32[B, N, fW, D, fH]: voxel row ((b*nx+ix)*ny+iy)*nz+iz of every point, -1 where dropped."""
+        p = self.prob
+        return self._view(self.layout.off_prow, p.n_points, torch.int32).view(p.B, p.N, p.fW, p.D, p.fH)
+
+    @property
+    def emask(self):
+        p = self.prob
+        return self._view(self.layout.off_emask, p.n_points, torch.int32).view(p.B, p.N, p.fW, p.D, p.fH)
+
+    @property
+    def counters(self):
+        """int32[3]: shared voxels below 64 points, pool slots in use, shared voxels with >= 64 points."""
+        return self._view(self.layout.off_counters, 3, torch.int32)
+
+    def shared_voxels(self):
+        """int32[n, 4] records {list head or pool slot, points, voxel row, batch} of the voxels that hold points of several
+        sub-runs (short ones first, then the >= 64-point ones); reads the counters (synchronises)."""
+        n_short, _, n_long = self.counters.cpu().tolist()
+        recs = self._view(self.layout.off_mixed_recs, self.layout.n_mixed_cap * 4, torch.int32).view(-1, 4)
+        return torch.cat((recs[:n_short], recs[recs.shape[0] - n_long:]))
+
+    @property
+    def scratch(self):
+        """The per-voxel scratch grids (all-zero between builds)."""
+        return self.ws[self.layout.off_cnt:]
+
+    def reset(self):
+        check(lib().lss_runplan_reset(C.byref(self.layout), _ptr(self.ws), _stream()), "lss_runplan_reset")
+
+
+def build_runplan(prob: Problem, frustum, trans, post_trans, M1=None, M2=None, rots=None, intrins=None, post_rots=None,
+                  plan: RunPlan | None = None) -> RunPlan:
+    """Run plan of one batch from calibration; replaces models.py:170-190 + :212-231.  With M1 / M2 (the reference's
+    own host inverses, `calib_matrices_reference`) the voxel rows are bit-exact; without them the closed-form
+    inverses are evaluated inside the kernel from rots / intrins / post_rots (no host round trip, graph-capturable)."""
+    raw = M1 is None or M2 is None
+    ts = [_f32c(t, n) for t, n in ((frustum, "frustum"), (post_trans, "post_trans"), (trans, "trans"))]
+    mats = [_f32c(t, n) for t, n in ((rots, "rots"), (intrins, "intrins"), (post_rots, "post_rots"))] if raw else \
+           [_f32c(t, n) for t, n in ((M1, "M1"), (M2, "M2"))]
+    if plan is None:
+        plan = RunPlan(prob, ts[0].device)
+    null = C.c_void_p(0)
+    args = (null, null, _ptr(ts[2]), *[_ptr(t) for t in mats]) if raw else (_ptr(mats[0]), _ptr(mats[1]), _ptr(ts[2]), null, null, null)
+    check(lib().lss_runplan_build(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(ts[0]), _ptr(ts[1]), *args, _stream()),
+          "lss_runplan_build")
+    plan.built, plan._keepalive = True, (ts, mats)
+    plan.generation += 1
+    return plan
+
+
+def bev_zero(prob: Problem, device, out=None, part=0, n_parts=1):
+    """A zeroed channels_last BEV tensor (models.py:240) through the bulk-copy kernel; may be issued on a side stream
+    next to the plan build and handed to splat_fwd_cl(..., out=bev, precleared=True).  (part, n_parts): only that slice."""
+    bev = out if out is not None else _empty_bev(prob, device, True)
+    check(lib().lss_bev_zero(C.byref(prob.c), _ptr(bev), int(part), int(n_parts), _stream()), "lss_bev_zero")
+    return bev
+
+
+def splat_fwd_cl(prob: Problem, plan: RunPlan, pr, ct, out=None, precleared=False):
+    """Deterministic forward into a channels_last BEV tensor: same bits as splat_fwd(mode="sorted")."""
+    pc = _prob_col(pr)
+    if pc is None:
+        raise RuntimeError("splat_fwd_cl needs the (prob, ctx) pair of lift_prepare (column-major weights)")
+    bev = out if out is not None else _empty_bev(prob, pr.device, True)
+    if not bev.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("splat_fwd_cl writes channels_last tensors only")
+    check(lib().lss_liftsplat_fwd_cl(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pc), _ptr(ct), _ptr(bev),
+                                     1 if precleared else 0, _stream()), "lss_liftsplat_fwd_cl")
+    return bev
+
+
+def splat_bwd_cl(prob: Problem, plan: RunPlan, grad_bev, pr, ct, prob_col=None, out=None):
+    g = _f32c_keep(grad_bev)
+    if not g.is_contiguous(memory_format=torch.channels_last):
+        g = g.contiguous(memory_format=torch.channels_last)      # an NCHW gradient is transposed once (cuDNN's NHWC conv1 hands us channels_last)
+    if prob_col is None:
+        prob_col = _prob_col(pr)
+    if out is None:
+        out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
+    check(lib().lss_liftsplat_bwd_cl(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), _ptr(prob_col), _ptr(ct),
+                                     _ptr(out), _stream()), "lss_liftsplat_bwd_cl")
+    return out
+
+
 def _parts(B, n):
     n = max(1, min(int(n), B))
     return [(i * B // n, (i + 1) * B // n) for i in range(n)]
@@ -376,32 +494,48 @@ def _f32c_keep(t):
     return t
 
 
+def _release(plan):
+    plan.busy = False
+
+
 class _LiftSplatFn(torch.autograd.Function):
     """depthnet output [B*N, D+C, fH, fW] -> BEV [B, nz*C, nx, ny]; backward = fused gather."""
 
     @staticmethod
-    def forward(ctx, depthnet_out, prob, plan, mode, channels_last):
+    def forward(ctx, depthnet_out, prob, plan, mode, channels_last, bev_out):
         pr, ct = lift_prepare(prob, depthnet_out)
-        bev = splat_fwd(prob, plan, pr, ct, mode, channels_last)
-        ctx.prob, ctx.plan, ctx.in_dtype = prob, plan, depthnet_out.dtype
+        if isinstance(plan, RunPlan):
+            bev = splat_fwd_cl(prob, plan, pr, ct, out=bev_out, precleared=bev_out is not None)
+        else:
+            bev = splat_fwd(prob, plan, pr, ct, mode, channels_last)
+        ctx.prob, ctx.plan, ctx.in_dtype, ctx.generation = prob, plan, depthnet_out.dtype, plan.generation
         ctx.save_for_backward(pr, ct, _prob_col(pr))
-        plan.busy = bool(ctx.needs_input_grad[0])
+        if ctx.needs_input_grad[0]:
+            plan.busy = True                       # released by the backward, or when the graph dies without one
+            weakref.finalize(ctx, _release, plan)
         return bev
 
     @staticmethod
     def backward(ctx, grad_bev):
         pr, ct, pc = ctx.saved_tensors
-        out = splat_bwd(ctx.prob, ctx.plan, grad_bev.float(), pr, ct, prob_col=pc)
+        if ctx.plan.generation != ctx.generation:
+            raise RuntimeError("the plan of this lift-splat forward was rebuilt before its backward ran "
+                               "(backward(retain_graph=True) followed by another forward on the same plan?)")
+        if isinstance(ctx.plan, RunPlan):
+            out = splat_bwd_cl(ctx.prob, ctx.plan, grad_bev.float(), pr, ct, prob_col=pc)
+        else:
+            out = splat_bwd(ctx.prob, ctx.plan, grad_bev.float(), pr, ct, prob_col=pc)
         ctx.plan.busy = False
         if ctx.in_dtype != torch.float32:          # bfloat16 input: the float32 gradient is rounded once, at the very end
             out = out.to(ctx.in_dtype)
-        return out, None, None, None, None
+        return out, None, None, None, None, None
 
 
-def lift_splat(depthnet_out, prob: Problem, plan: Plan, mode="sorted", channels_last=False):
+def lift_splat(depthnet_out, prob: Problem, plan, mode="sorted", channels_last=False, bev_out=None):
     """Fused lift + splat of the depthnet output through an existing plan (differentiable w.r.t.
-    `depthnet_out`; geometry carries no gradient, tools.py:207)."""
-    return _LiftSplatFn.apply(depthnet_out, prob, plan, mode, channels_last)
+    `depthnet_out`; geometry carries no gradient, tools.py:207).  `plan`: a tile `Plan`, or a `RunPlan`
+    (deterministic, channels_last output; `bev_out`: optional pre-zeroed output from `bev_zero`)."""
+    return _LiftSplatFn.apply(depthnet_out, prob, plan, mode, channels_last, bev_out)
 
 
 class _VoxelPoolingFn(torch.autograd.Function):
