@@ -13,8 +13,9 @@
  *     including workspaces (sizes from lss_plan_layout); nothing is allocated or freed inside.
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it; no call synchronises
  *     the device or the stream, so every call is CUDA-graph capturable.
- *   - return value: LSS_OK (0) or a negative lss_status; no exceptions, no global state, re-entrant
- *     (distinct plans may be used from distinct streams concurrently).
+ *   - return value: LSS_OK (0) or a negative lss_status; no exceptions; re-entrant (distinct plans may be used
+ *     from distinct streams concurrently); no global state apart from the process-wide options of
+ *     lss_set_option, no environment variables.
  *   - there is NO CPU fallback: without a CUDA device the compute entry points return LSS_ERR_CUDA.
  *   - float tensors are IEEE binary32, C-contiguous in the stated shape unless strides are passed.
  *
@@ -70,6 +71,12 @@ enum { LSS_SPLAT_SORTED = 0,      /* per voxel, ascending flat point index, sequ
 
 int lss_version(void);
 const char *lss_status_string(int status);
+
+/* Process-wide options (the library's only global state).  LSS_OPT_PDL: launch the kernel chains with programmatic
+ * dependent launch (default 1); 0 = plain stream order (compute-sanitizer runs, A/B measurements). */
+enum { LSS_OPT_PDL = 0, LSS_OPT_COUNT = 1 };
+int lss_set_option(int option, int value);
+int lss_get_option(int option);
 
 /* Compiled limits: max per-sample points (N*D*fH*fW), max tile width, max D for the fused backward. */
 typedef struct lss_limits { int32_t max_points_per_sample, max_tile_cols, max_depth_bins, max_channels; } lss_limits;
@@ -235,11 +242,6 @@ int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
                   const float *grad_bev, int layout, const float *prob, const float *ctx_t, const float *prob_col,
                   float *grad_rows, float *grad_depthnet, int plan_sorted, int stage, int b0, int b1, void *stream);
 
-/* Debug hook (profiling aid, not part of the reference surface): when non-null, the GROUP kernels stamp
- * %globaltimer at their phase boundaries into `store_buf` (device, 8 x u64 per tile) and `gather_buf`
- * (8 x u64 per camera column); null switches the stamps off. */
-int lss_debug_set_timeline(void *store_buf, void *gather_buf);
-
 /* ---------------------------------------------------------------------------------------------- */
 /* Run plan: the channels_last fast path of the fused level (default of bench.py and of the API)   */
 /* ---------------------------------------------------------------------------------------------- */
@@ -290,6 +292,15 @@ int lss_runplan_reset(const lss_runplan_layout *L, void *workspace, void *stream
 int lss_runplan_build(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
                       const float *post_trans, const float *M1, const float *M2, const float *trans,
                       const float *rots, const float *intrins, const float *post_rots, void *stream);
+/* Fused prologue of a step, ONE launch (+ the classify launch when a plan is built): the zero-fill of `bev` (may be null:
+ * off), the run plan (frustum == null: off, e.g. a cached plan; arguments as lss_runplan_build) and the lift operands
+ * (depthnet_out == null: off; outputs as lss_lift_prepare, prob_col required) as independent CTA roles of one grid.  The
+ * zero-fill is the only bandwidth-bound piece of the path; the other two are latency chains that finish in its shadow.
+ * Afterwards: lss_liftsplat_fwd_cl(..., precleared = 1). */
+int lss_liftsplat_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                           const float *post_trans, const float *M1, const float *M2, const float *trans,
+                           const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
+                           float *prob, float *ctx_t, float *prob_col, float *bev, void *stream);
 /* torch.zeros of models.py:240 through the bulk-copy engine (cp.async.bulk shared -> global): one thread per CTA
  * issues the stores, so the kernel leaves the SMs to whatever runs next to it (the plan build, the lift).
  * `part` of `n_parts`: zero only that slice of the tensor (callers chain the slices on a side stream next to the kernels
@@ -348,10 +359,6 @@ int lss_quickcumsum_bwd(int64_t n, int32_t C, const float *grad_sums, const int3
 void *lss_pipe_event_create(void);
 int lss_pipe_event_destroy(void *event);
 int lss_pipe_event_synchronize(void *event);
-/* Pinned host memory for the blocks of a step.  write_combined != 0 allocates with cudaHostAllocWriteCombined (faster
- * for the device to read over PCIe, slow for the CPU to read back: input blocks only).  NULL on failure. */
-void *lss_pipe_host_alloc(size_t bytes, int write_combined);
-int lss_pipe_host_free(void *ptr);
 /* One pipeline stage, enqueued with a single call: `stream` waits for wait_a and wait_b (each may be NULL), runs
  * n_copies (<= 4) cudaMemcpyAsync(dst[i], src[i], bytes[i], default kind: pinned host <-> device), then records
  * `record` (may be NULL).  Returns LSS_OK or LSS_ERR_CUDA. */

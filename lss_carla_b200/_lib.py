@@ -74,12 +74,11 @@ SIGNATURES = {
     "lss_plan_reference_order": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P]),
     "lss_lift_prepare": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
     "lss_lift_prepare_bf16": (C.c_int, [_PP, _P, _P, _P, _P, _P]),
-    "lss_debug_set_timeline": (C.c_int, [_P, _P]),
+    "lss_set_option": (C.c_int, [C.c_int, C.c_int]),
+    "lss_get_option": (C.c_int, [C.c_int]),
     "lss_pipe_event_create": (C.c_void_p, []),
     "lss_pipe_event_destroy": (C.c_int, [_P]),
     "lss_pipe_event_synchronize": (C.c_int, [_P]),
-    "lss_pipe_host_alloc": (C.c_void_p, [C.c_size_t, C.c_int]),
-    "lss_pipe_host_free": (C.c_int, [_P]),
     "lss_pipe_stage": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_size_t), _P]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
@@ -87,6 +86,7 @@ SIGNATURES = {
     "lss_runplan_reset": (C.c_int, [_PR, _P, _P]),
     "lss_runplan_build": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lss_bev_zero": (C.c_int, [_PP, _P, C.c_int, C.c_int, _P]),
+    "lss_liftsplat_prologue": (C.c_int, [_PP, _PR] + [_P] * 15),
     "lss_liftsplat_fwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, C.c_int, _P]),
     "lss_liftsplat_bwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -26,13 +26,15 @@
         if (!(cond)) return (code); \
     } while (0)
 
+int lss_option_value(int option);     // ops.cu: process-wide options of lss_set_option
+
 // Kernel launch with optional programmatic dependent launch (PDL): with `pdl`, the grid may start while the
 // previous kernel of the stream is still draining; the kernel must execute lss_pdl_wait() before it reads anything that
 // kernel wrote, and producers call lss_pdl_trigger() early.  Captured into CUDA graphs as programmatic edges.
 template <typename... KArgs, typename... Args>
 static inline cudaError_t lss_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
                                      Args... args) {
-    static const bool no_pdl = getenv("LSS_NO_PDL") != nullptr;
+    const bool no_pdl = lss_option_value(LSS_OPT_PDL) == 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];

@@ -189,16 +189,18 @@ extern "C" int lss_pipe_stage(void *stream, void *wait_a, void *wait_b, int32_t 
     return LSS_OK;
 }
 
-// Pinned host memory for the pipeline's blocks.  write_combined != 0: cudaHostAllocWriteCombined -- not snooped by the
-// CPU caches, faster for the device to read over PCIe, slow for the CPU to READ: only for buffers the host just writes
-// (the input block).
-extern "C" void *lss_pipe_host_alloc(size_t bytes, int write_combined) {
-    void *p = nullptr;
-    const unsigned flags = write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
-    if (bytes == 0 || cudaHostAlloc(&p, bytes, flags) != cudaSuccess) return nullptr;
-    return p;
+// ------------------------------------------------------------------------------------------------
+// process-wide options (the only global state of the library)
+// ------------------------------------------------------------------------------------------------
+
+static int g_lss_options[LSS_OPT_COUNT] = {1};      // LSS_OPT_PDL: on
+
+int lss_option_value(int option) { return option >= 0 && option < LSS_OPT_COUNT ? g_lss_options[option] : 0; }
+
+extern "C" int lss_set_option(int option, int value) {
+    LSS_REQUIRE(option >= 0 && option < LSS_OPT_COUNT, LSS_ERR_BAD_ARG);
+    g_lss_options[option] = value;
+    return LSS_OK;
 }
 
-extern "C" int lss_pipe_host_free(void *p) {
-    return (p == nullptr || cudaFreeHost(p) == cudaSuccess) ? LSS_OK : LSS_ERR_CUDA;
-}
+extern "C" int lss_get_option(int option) { return lss_option_value(option); }

@@ -236,7 +236,7 @@ k_plan_scatter(Dims d, Tiling tl, const int32_t *__restrict__ vox, int32_t *__re
 }
 
 #define LSS_SORT_SMEM_CAP 4096   // entries grouped in shared memory (16 KB); larger buckets sort in global memory
-#define LSS_SORT_THREADS 256          // default CTA size of k_plan_sort (LSS_SORT_NT=128 selects the 128-thread build)
+#define LSS_SORT_THREADS 256          // CTA size of k_plan_sort (128-thread CTAs measured no faster: the phases are latency chains)
 
 // Exclusive scan of a[0..L) in shared memory by the whole CTA (L <= LSS_MAX_TILE_COLS); a[L] = total.
 template <int NT>
@@ -566,12 +566,11 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
     int32_t *key_count = (int32_t *)(w + L->off_key_count);
     int32_t *prow = (int32_t *)(w + L->off_prow);
     const int grid = (d.n_points + 255) / 256;
-    // the histogram scan rides in the scatter kernel when its table fits shared memory (LSS_SCAN_IN_SCATTER=0: old path)
-    static const int scan_knob = getenv("LSS_SCAN_IN_SCATTER") ? atoi(getenv("LSS_SCAN_IN_SCATTER")) : 1;
+    // the histogram scan rides in the scatter kernel when its table fits shared memory
     const size_t scan_smem = ((size_t)tl.n_tiles + 1) * sizeof(int);
     // ... and is one 2048-counter step: every scatter CTA repeats the scan, which stops paying with many tiles AND many
     // CTAs (cfg 4, 6400 tiles x 3895 CTAs: plan 138.7 us with the scan in the scatter kernel, 122.6 us with the ticket path)
-    const bool scan_in_scatter = scan_knob && tl.n_tiles <= 2048 && scan_smem <= 64 * 1024;
+    const bool scan_in_scatter = tl.n_tiles <= 2048 && scan_smem <= 64 * 1024;
     const int grid_vi = (grid + 1) / 2;
 #define VI_ARGS d, tl, geom, c, vox, nullptr, nullptr, nullptr, tile_count, tile_start, cursor, sync, counters, key_count, prow
     if (geom != nullptr) {
@@ -585,11 +584,8 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
 #undef VI_ARGS
     LSS_CHECK_LAUNCH();
     if (scan_in_scatter) {
-        static bool configured = false;
-        if (scan_smem > 40 * 1024 && !configured) {
-            if (cudaFuncSetAttribute(k_plan_scatter<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
-            configured = true;
-        }
+        if (scan_smem > 40 * 1024 &&       // (per device, cheap: no per-process cache)
+            cudaFuncSetAttribute(k_plan_scatter<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
         if (lss_launch(k_plan_scatter<2, true>, dim3(grid_vi), dim3(256), scan_smem, s, true, d, tl, vox, tile_start, cursor, entries,
                        tile_count, key_count, counters) != cudaSuccess) return LSS_ERR_CUDA;
         if (!sorted) {      // no sort kernel to clear the scratch counters of the next build: tile_count and cursor are contiguous
@@ -601,11 +597,9 @@ static int plan_build_impl(const lss_problem *p, const lss_plan_layout *L, void 
     if (sorted) {
         const size_t sort_smem = (size_t)(3 * tl.TY + 1) * sizeof(int);
         if (sort_smem > 24 * 1024 &&
-            (cudaFuncSetAttribute(k_plan_sort<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess ||
-             cudaFuncSetAttribute(k_plan_sort<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess))
+            cudaFuncSetAttribute(k_plan_sort<LSS_SORT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem) != cudaSuccess)
             return LSS_ERR_CUDA;
-        static const int sort_nt = getenv("LSS_SORT_NT") ? atoi(getenv("LSS_SORT_NT")) : LSS_SORT_THREADS;   // tuning knob
-        if (lss_launch(sort_nt == 128 ? k_plan_sort<128> : k_plan_sort<256>, dim3(tl.n_tiles), dim3(sort_nt == 128 ? 128 : 256), sort_smem, s, true,
+        if (lss_launch(k_plan_sort<LSS_SORT_THREADS>, dim3(tl.n_tiles), dim3(LSS_SORT_THREADS), sort_smem, s, true,
                        d, tl, tile_start, entries, (uint32_t *)(w + L->off_segs), (int32_t *)(w + L->off_tile_nseg),
                        (int32_t *)(w + L->off_tile_row0), (int4 *)(w + L->off_seg_recs), key_count,
                        (int4 *)(w + L->off_mixed_recs), counters, prow, (long long)L->n_rows_cap,

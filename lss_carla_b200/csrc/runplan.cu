@@ -21,16 +21,19 @@
 // the definition of LSS_SPLAT_SORTED (the reference's stable argsort order), bit for bit.
 #include "common.cuh"
 #include "geom.cuh"
+#include "lift.cuh"
 
 #define RP_THREADS 256
 #define RP_WARPS (RP_THREADS / 32)
-#define RP_U 2                     // warp-rounds per thread: the index / classify grids then fit one wave at cfg 2
+#define RP_U 2                     // warp-rounds per thread (measured at cfg 2: 2 -> 61.0 us per step, 3 -> 63.2, 4 -> 64.1)
 #define GCL_THREADS 128
 #define GCL_NG (GCL_THREADS / 8)   // 8-lane groups per gather CTA
 #define GCL_SHORT_CAP 64           // == LSS_LONG_VOXEL: shared voxels below this are summed by a group
 #define GCL_SORT_CAP 1024          // long voxels up to this many points are sorted in shared memory
 
-// DEV timeline: [2k] = earliest start, [2k+1] = latest end (globaltimer ns) of kernel k (0 zero, 1 index, 2 classify, 3 gather)
+// Profiling aid, compiled in with -DLSS_RP_TIMELINE only (scripts/bench_runplan_quick.py): earliest start / latest end
+// (globaltimer ns) of the zero role (0), the index role (1), k_run_classify (2) and the column CTAs of the gather (3).
+#ifdef LSS_RP_TIMELINE
 __device__ unsigned long long g_rp_tl[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
 __device__ int g_rp_tl_on = 0;
 __device__ __forceinline__ void tl_stamp(int k, bool end) {
@@ -46,6 +49,9 @@ extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) 
     if (cudaMemcpyToSymbol(g_rp_tl, init, sizeof(init)) != cudaSuccess) return -4;
     return cudaMemcpyToSymbol(g_rp_tl_on, &on, sizeof(on)) == cudaSuccess ? 0 : -4;
 }
+#else
+#define tl_stamp(k, end) ((void)0)
+#endif
 
 // thread -> point mapping shared by k_run_index and k_run_classify (they must agree on what a sub-run is)
 struct RunDims {
@@ -57,12 +63,12 @@ struct RunDims {
 
 struct RunLane { int r, h, rw; bool valid; unsigned run_mask; };
 
-__device__ __forceinline__ RunLane run_lane(const RunDims &rd, int u) {
+__device__ __forceinline__ RunLane run_lane(const RunDims &rd, int cta, int u) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RunLane q;
     q.rw = lane / rd.fH;
     q.h = lane - q.rw * rd.fH;
-    const int wg = (blockIdx.x * RP_WARPS + warp) * RP_U + u;
+    const int wg = (cta * RP_WARPS + warp) * RP_U + u;
     q.r = wg * rd.RPW + q.rw;
     q.valid = q.rw < rd.RPW && q.r < rd.R;
     q.run_mask = q.rw < rd.RPW ? rd.fmask << (q.rw * rd.fH) : 0u;
@@ -73,15 +79,15 @@ __device__ __forceinline__ RunLane run_lane(const RunDims &rd, int u) {
 // plan kernels
 // ------------------------------------------------------------------------------------------------
 
+// The work of one CTA of the index pass (RP_THREADS threads); `cta` in [0, ceil(R / runs per CTA)).
 template <bool RAW>
-__global__ void __launch_bounds__(RP_THREADS)
-k_run_index(Dims d, RunDims rd, CalibPtrs c, int32_t *__restrict__ prow, int32_t *__restrict__ cnt, int32_t *__restrict__ head,
-            int2 *__restrict__ sub, int32_t *__restrict__ counters) {
-    lss_pdl_trigger();                                    // k_run_classify may be scheduled while this grid drains
+__device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, const CalibPtrs &c, int32_t *__restrict__ prow,
+                                              int32_t *__restrict__ cnt, int32_t *__restrict__ head, int2 *__restrict__ sub,
+                                              int32_t *__restrict__ counters, int cta) {
     tl_stamp(1, false);
-    if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
+    if (cta == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
-    const int cam0 = (int)(((long long)blockIdx.x * RP_WARPS * RP_U * rd.RPW) / rd.fWD);
+    const int cam0 = (int)(((long long)cta * RP_WARPS * RP_U * rd.RPW) / rd.fWD);
     if (RAW) {      // the calibration matrices of the few cameras this CTA touches, made on the fly (no extra launch)
         const int cam = cam0 + (int)threadIdx.x;
         if (threadIdx.x < LSS_RAW_CAMS && cam < d.B * d.N) calib_matrices_of(c.rots, c.intrins, c.post_rots, cam, s_m[threadIdx.x], s_m[threadIdx.x] + 9);
@@ -90,7 +96,7 @@ k_run_index(Dims d, RunDims rd, CalibPtrs c, int32_t *__restrict__ prow, int32_t
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int u = 0; u < RP_U; ++u) {
-        const RunLane q = run_lane(rd, u);
+        const RunLane q = run_lane(rd, cta, u);
         int row = -1;
         if (q.valid) {
             const int bn = q.r / rd.fWD, rem = q.r - bn * rd.fWD;
@@ -141,7 +147,7 @@ k_run_classify(Dims d, RunDims rd, const int32_t *__restrict__ prow, uint32_t *_
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int u = 0; u < RP_U; ++u) {
-        const RunLane q = run_lane(rd, u);
+        const RunLane q = run_lane(rd, (int)blockIdx.x, u);
         const size_t cm = (size_t)q.r * d.fH + q.h;
         const int row = q.valid ? __ldg(prow + cm) : -1;
         const unsigned peers = __match_any_sync(LSS_FULL_MASK, row >= 0 ? row : -1 - lane) & q.run_mask;
@@ -181,36 +187,62 @@ k_run_classify(Dims d, RunDims rd, const int32_t *__restrict__ prow, uint32_t *_
 // zero-fill through the bulk-copy engine
 // ------------------------------------------------------------------------------------------------
 
-#define ZERO_CHUNK_MAX (64 * 1024)
-// `inflight` > 0: at most that many bulk copies of this CTA are outstanding (completed writes, not only source reads);
-// 0: everything is issued at once.  Throttling keeps the queues of the memory system shallow for the kernels that run
-// next to the zero-fill (plan build, lift): their loads and atomics are latency chains.
-template <int INFLIGHT>
-__device__ __forceinline__ void zero_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(INFLIGHT) : "memory"); }
-
-__global__ void __launch_bounds__(128)
-k_bev_zero(float *__restrict__ dst, size_t bytes, int chunk, int inflight) {
-    extern __shared__ __align__(128) float s_zero[];
+// Zero role of one CTA: thread 0 streams its share of [dst, dst + bytes) out of a zeroed shared-memory chunk with bulk copies
+// (cp.async.bulk shared -> global: the copies need no registers and no issue slots, the source is read-only, so all of them
+// stay in flight).  With `evict_first` the lines are marked evict-first in L2: 82 MB of zeros should not push the plan and the
+// lift operands, which the gather is about to read, out of the cache.
+#define ZERO_CHUNK (16 * 1024)
+__device__ __forceinline__ void zero_role(float *__restrict__ dst, size_t bytes, int cta, int n_cta, float *s_zero, int evict_first) {
     tl_stamp(0, false);
-    for (int i = threadIdx.x; i < chunk / 16; i += blockDim.x) reinterpret_cast<float4 *>(s_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < ZERO_CHUNK / 16; i += blockDim.x) reinterpret_cast<float4 *>(s_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy
     __syncthreads();
     if (threadIdx.x != 0) return;
-    const size_t n_chunks = (bytes + chunk - 1) / chunk;
+    const size_t n_chunks = (bytes + ZERO_CHUNK - 1) / ZERO_CHUNK;
     const unsigned src = (unsigned)__cvta_generic_to_shared(s_zero);
-    for (size_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {     // the source is read-only: copies need no hand-shake
-        const size_t off = ch * chunk;
-        const unsigned sz = (unsigned)min((size_t)chunk, bytes - off);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(reinterpret_cast<char *>(dst) + off), "r"(src), "r"(sz) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (inflight == 1) zero_wait<0>();
-        else if (inflight == 2) zero_wait<1>();
-        else if (inflight == 4) zero_wait<3>();
-        else if (inflight == 8) zero_wait<7>();
+    unsigned long long pol = 0;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    for (size_t ch = cta; ch < n_chunks; ch += n_cta) {
+        const size_t off = ch * ZERO_CHUNK;
+        const unsigned sz = (unsigned)min((size_t)ZERO_CHUNK, bytes - off);
+        if (evict_first)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         :: "l"(reinterpret_cast<char *>(dst) + off), "r"(src), "r"(sz), "l"(pol) : "memory");
+        else
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(reinterpret_cast<char *>(dst) + off), "r"(src), "r"(sz) : "memory");
     }
-    zero_wait<0>();
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tl_stamp(0, true);
+}
+
+// Fused prologue of a step: ONE launch whose CTAs take one of three independent roles --
+//   [0, n_zero)                    zero-fill of the BEV tensor (models.py:240), the only bandwidth-bound piece of the path
+//   [n_zero, n_zero + n_lift)      lift operands: depth softmax + pixel-major context (models.py:49-61)
+//   [.., + n_index)                run index: geometry + voxel rows + list pushes (models.py:170-190, :212-221)
+// (measured at cfg 2: lift before index 61.0 us per step, index before lift 63.1 -- the grid is a little more than one wave)
+// The index and lift roles are chains of memory latencies that would otherwise queue behind the zero-fill on other streams
+// (measured: on separate graph branches each of them ends when the zero-fill ends, plus ~10 us of fork / join overhead);
+// inside one grid they share the SMs with the zero role's single issuing thread and finish within its shadow.
+struct PrologueArgs {
+    float *bev; size_t bev_bytes; int n_zero, evict_first;            // zero role (n_zero = 0: off)
+    int n_index; RunDims rd; CalibPtrs c;                             // index role (n_index = 0: off)
+    int32_t *prow, *cnt, *head, *counters; int2 *sub;
+    int n_lift; const float *dn; float *prob, *ctx_t, *prob_col;      // lift role (n_lift = 0: off)
+};
+
+template <bool RAW>
+__global__ void __launch_bounds__(RP_THREADS)
+k_prologue(Dims d, PrologueArgs a) {
+    extern __shared__ __align__(128) float s_pro[];
+    lss_pdl_trigger();                                    // k_run_classify may be scheduled while this grid drains
+    int cta = (int)blockIdx.x;
+    if (cta < a.n_zero) { zero_role(a.bev, a.bev_bytes, cta, a.n_zero, s_pro, a.evict_first); return; }
+    cta -= a.n_zero;
+    if (cta < a.n_lift) { lift_prepare_cta<float>(d, a.dn, a.prob, a.ctx_t, a.prob_col, cta, s_pro); return; }
+    cta -= a.n_lift;
+    run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.cnt, a.head, a.sub, a.counters, cta);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,71 +527,85 @@ extern "C" int lss_runplan_reset(const lss_runplan_layout *L, void *ws, void *st
     return LSS_OK;
 }
 
+static int launch_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, bool index, const CalibPtrs &c, bool raw,
+                           const float *dn, float *prob, float *ctx_t, float *prob_col, float *bev, size_t bev_bytes,
+                           cudaStream_t s) {
+    const Dims d = make_dims(p);
+    PrologueArgs a = {};
+    a.rd = make_run_dims(p);
+    char *w = (char *)workspace;
+    if (bev != nullptr && bev_bytes > 0) {
+        // two issuing CTAs per SM (one: 67.5 us per step at cfg 2 against 63); evict-first lines: the zeros should not push
+        // the plan and the lift operands out of L2 (measured neutral to slightly better)
+        const size_t n_chunks = (bev_bytes + ZERO_CHUNK - 1) / ZERO_CHUNK;
+        a.bev = bev; a.bev_bytes = bev_bytes; a.evict_first = 1;
+        a.n_zero = (int)min((size_t)2 * rp_num_sms(), n_chunks);
+    }
+    if (index) {
+        const int runs_per_cta = RP_WARPS * RP_U * a.rd.RPW;
+        if (raw) LSS_REQUIRE(runs_per_cta / a.rd.fWD + 2 <= LSS_RAW_CAMS, LSS_ERR_UNSUPPORTED);   // cameras one CTA may span
+        a.n_index = (a.rd.R + runs_per_cta - 1) / runs_per_cta;
+        a.c = c;
+        a.prow = (int32_t *)(w + L->off_prow); a.cnt = (int32_t *)(w + L->off_cnt); a.head = (int32_t *)(w + L->off_head);
+        a.counters = (int32_t *)(w + L->off_counters); a.sub = (int2 *)(w + L->off_sub);
+    }
+    size_t smem = a.n_zero ? ZERO_CHUNK : 0;
+    if (dn != nullptr) {
+        a.n_lift = p->B * p->N * ((d.HW + LIFT_PX - 1) / LIFT_PX);
+        a.dn = dn; a.prob = prob; a.ctx_t = ctx_t; a.prob_col = prob_col;
+        smem = max(smem, (size_t)(d.D + d.C) * (LIFT_PX + 1) * sizeof(float));
+    }
+    const int grid = a.n_zero + a.n_index + a.n_lift;
+    if (grid == 0) return LSS_OK;
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    auto kern = raw ? k_prologue<true> : k_prologue<false>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LSS_ERR_CUDA;
+    kern<<<grid, RP_THREADS, smem, s>>>(d, a);
+    LSS_CHECK_LAUNCH();
+    if (index) {
+        if (lss_launch(k_run_classify, dim3(a.n_index), dim3(RP_THREADS), 0, s, true, d, a.rd, (const int32_t *)a.prow,
+                       (uint32_t *)(w + L->off_emask), a.cnt, a.head, (const int2 *)a.sub, (uint32_t *)(w + L->off_pool),
+                       (int4 *)(w + L->off_mixed_recs), a.counters, (long long)L->n_mixed_cap) != cudaSuccess) return LSS_ERR_CUDA;
+        LSS_CHECK_LAUNCH();
+    }
+    return LSS_OK;
+}
+
 extern "C" int lss_runplan_build(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
                                  const float *post_trans, const float *M1, const float *M2, const float *trans,
                                  const float *rots, const float *intrins, const float *post_rots, void *stream) {
-    int st = runplan_supported(p);
-    if (st != LSS_OK) return st;
-    LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
-    LSS_REQUIRE(frustum && post_trans && trans, LSS_ERR_BAD_ARG);
-    const bool raw = M1 == nullptr || M2 == nullptr;
-    LSS_REQUIRE(!raw || (rots && intrins && post_rots), LSS_ERR_BAD_ARG);
-    const Dims d = make_dims(p);
-    LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
-    const RunDims rd = make_run_dims(p);
-    const int runs_per_cta = RP_WARPS * RP_U * rd.RPW;
-    if (raw) LSS_REQUIRE(runs_per_cta / rd.fWD + 2 <= LSS_RAW_CAMS, LSS_ERR_UNSUPPORTED);   // cameras one CTA may span
-    char *w = (char *)workspace;
-    int32_t *prow = (int32_t *)(w + L->off_prow);
-    int32_t *cnt = (int32_t *)(w + L->off_cnt);
-    int32_t *counters = (int32_t *)(w + L->off_counters);
-    const CalibPtrs c{frustum, post_trans, M1, M2, trans, rots, intrins, post_rots};
-    const int grid = (rd.R + runs_per_cta - 1) / runs_per_cta;
-    cudaStream_t s = (cudaStream_t)stream;
-    int32_t *head = (int32_t *)(w + L->off_head);
-    int2 *sub = (int2 *)(w + L->off_sub);
-    if (raw) k_run_index<true><<<grid, RP_THREADS, 0, s>>>(d, rd, c, prow, cnt, head, sub, counters);
-    else k_run_index<false><<<grid, RP_THREADS, 0, s>>>(d, rd, c, prow, cnt, head, sub, counters);
-    LSS_CHECK_LAUNCH();
-    if (lss_launch(k_run_classify, dim3(grid), dim3(RP_THREADS), 0, s, true, d, rd, (const int32_t *)prow,
-                   (uint32_t *)(w + L->off_emask), cnt, head, (const int2 *)sub, (uint32_t *)(w + L->off_pool),
-                   (int4 *)(w + L->off_mixed_recs), counters,
-                   (long long)L->n_mixed_cap) != cudaSuccess) return LSS_ERR_CUDA;
-    LSS_CHECK_LAUNCH();
-    return LSS_OK;
+    return lss_liftsplat_prologue(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, stream);
 }
 
-// plain 16-byte stores, grid-stride (DEV variant)
-__global__ void __launch_bounds__(256)
-k_bev_zero_stg(float4 *__restrict__ dst, size_t n16) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t stride = (size_t)gridDim.x * 256;
-    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    for (; i + 3 * stride < n16; i += 4 * stride) { dst[i] = z; dst[i + stride] = z; dst[i + 2 * stride] = z; dst[i + 3 * stride] = z; }
-    for (; i < n16; i += stride) dst[i] = z;
+extern "C" int lss_liftsplat_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                                      const float *post_trans, const float *M1, const float *M2, const float *trans,
+                                      const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
+                                      float *prob, float *ctx_t, float *prob_col, float *bev, void *stream) {
+    int st = runplan_supported(p);
+    if (st != LSS_OK) return st;
+    const bool index = frustum != nullptr;
+    const bool raw = M1 == nullptr || M2 == nullptr;
+    if (index) {
+        LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
+        LSS_REQUIRE(post_trans && trans, LSS_ERR_BAD_ARG);
+        LSS_REQUIRE(!raw || (rots && intrins && post_rots), LSS_ERR_BAD_ARG);
+        LSS_REQUIRE(L->n_points == (int64_t)p->B * p->N * p->D * p->fH * p->fW, LSS_ERR_WORKSPACE);
+    }
+    if (depthnet_out != nullptr) LSS_REQUIRE(prob && ctx_t && prob_col, LSS_ERR_BAD_ARG);
+    const size_t bytes = (size_t)p->B * p->nz * p->C * p->nx * p->ny * 4;
+    if (bev != nullptr) LSS_REQUIRE(lss_aligned(bev, 16) && bytes % 16 == 0, LSS_ERR_ALIGN);
+    const CalibPtrs c{frustum, post_trans, M1, M2, trans, rots, intrins, post_rots};
+    return launch_prologue(p, L, workspace, index, c, index && raw, depthnet_out, prob, ctx_t, prob_col, bev, bytes, (cudaStream_t)stream);
 }
 
 static int launch_bev_zero(float *bev, size_t bytes, cudaStream_t s) {
-    static const int mode = getenv("LSS_ZERO_MODE") ? atoi(getenv("LSS_ZERO_MODE")) : 0;                  // DEV knobs
-    if (bytes % 16 != 0 || !lss_aligned(bev, 16) || mode == 2)
+    if (bytes % 16 != 0 || !lss_aligned(bev, 16))
         return cudaMemsetAsync(bev, 0, bytes, s) == cudaSuccess ? LSS_OK : LSS_ERR_CUDA;
-    static const int chunk_kb = getenv("LSS_ZERO_CHUNK_KB") ? atoi(getenv("LSS_ZERO_CHUNK_KB")) : 32;
-    static const int grid_mul = getenv("LSS_ZERO_GRID") ? atoi(getenv("LSS_ZERO_GRID")) : 2;
-    static const int inflight = getenv("LSS_ZERO_INFLIGHT") ? atoi(getenv("LSS_ZERO_INFLIGHT")) : 0;
-    if (mode == 1) {
-        k_bev_zero_stg<<<grid_mul * rp_num_sms(), 256, 0, s>>>((float4 *)bev, bytes / 16);
-        LSS_CHECK_LAUNCH();
-        return LSS_OK;
-    }
-    const int chunk = chunk_kb * 1024;
-    if (chunk > 48 * 1024 && cudaFuncSetAttribute(k_bev_zero, cudaFuncAttributeMaxDynamicSharedMemorySize, ZERO_CHUNK_MAX) != cudaSuccess) return LSS_ERR_CUDA;
-    const size_t n_chunks = (bytes + chunk - 1) / chunk;
-    const int grid = mode == 3 ? (int)n_chunks : (int)min((size_t)grid_mul * rp_num_sms(), n_chunks);
-    static const int pad_kb = getenv("LSS_ZERO_PAD_KB") ? atoi(getenv("LSS_ZERO_PAD_KB")) : 0;          // DEV: limits resident CTAs
-    if (pad_kb > 0 && cudaFuncSetAttribute(k_bev_zero, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
-    k_bev_zero<<<grid, 128, chunk + pad_kb * 1024, s>>>(bev, bytes, chunk, inflight);
-    LSS_CHECK_LAUNCH();
-    return LSS_OK;
+    lss_problem dummy = {};
+    dummy.B = dummy.N = dummy.D = dummy.fH = dummy.fW = 1; dummy.C = 32; dummy.nx = dummy.ny = dummy.nz = 1;
+    dummy.dx[0] = dummy.dx[1] = dummy.dx[2] = 1.f;
+    return launch_prologue(&dummy, nullptr, nullptr, false, CalibPtrs{}, false, nullptr, nullptr, nullptr, nullptr, bev, bytes, s);
 }
 
 extern "C" int lss_bev_zero(const lss_problem *p, float *bev, int part, int n_parts, void *stream) {

@@ -25,23 +25,6 @@
 #define SPLAT_THREADS 256
 #define SPLAT_WARPS (SPLAT_THREADS / 32)
 #define GATHER_THREADS 128
-#ifndef QUEUE_FIRST
-#define QUEUE_FIRST 1
-#endif
-
-// Debug hook (lss_debug_set_timeline): when set, CTAs of the forward kernel stamp %globaltimer at their
-// phase boundaries into this buffer, 8 x u64 per tile.  Null in production: one uniform branch per phase.
-__device__ unsigned long long *g_lss_timeline = nullptr;          // store kernel, per tile
-__device__ unsigned long long *g_lss_timeline_gather = nullptr;   // gather kernel, per camera column
-template <bool GATHER = false>
-__device__ __forceinline__ void lss_stamp(int tile, int slot) {
-    unsigned long long *tb = GATHER ? g_lss_timeline_gather : g_lss_timeline;
-    if (tb != nullptr && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        tb[(size_t)tile * 8 + slot] = t;
-    }
-}
 
 struct SrcArgs {
     const float *base;   // LIFT: ctx_t [B*N, HW, C]        DENSE: x with strides s[0..5]
@@ -304,59 +287,27 @@ k_splat_fwd_tile(Dims d, Tiling tl, const int32_t *__restrict__ tile_start, cons
 // takes its row and weight from global memory.  Groups look 8 entries ahead (lane gl resolves entry
 // base+gl) and add float32(prob*ctx) in ascending point order.  The sum goes to the voxel's compact row
 // of vsum (L2-resident, 4*C*V_hit bytes).
-// Zero role (ZeroArgs::n_tiles > 0, NCHW with 16-byte rows): the LAST n_tiles CTAs of the grid do not gather.  CTA j
-// zero-fills, in every channel row of BEV tile tile_lo + j, the 32-byte sectors that hold no non-empty column (known
-// from the plan alone).  They are scheduled after all gather CTAs, i.e. into the SMs that idle while the queue of
-// mixed voxels drains, so about a third of the BEV bytes are written before the store kernel starts; that kernel
-// (k_fwd_store_rows<.., SKIPZ>) then skips exactly these sectors.
-struct ZeroArgs { float *bev; const int32_t *tile_start, *tile_nseg; const uint32_t *segs; Tiling tl; int tile_lo, n_tiles; };
-
-__device__ __forceinline__ void zero_empty_sectors(const Dims &d, const ZeroArgs &z, int tile) {
-    __shared__ unsigned s_hit;                           // bit j: sector j (columns 8j .. 8j+7 of the tile) has a voxel
-    const int nseg = __ldg(z.tile_nseg + tile), s = __ldg(z.tile_start + tile);
-    if (threadIdx.x == 0) s_hit = 0u;
-    __syncthreads();
-    for (int k = threadIdx.x; k < nseg; k += GATHER_THREADS) atomicOr(&s_hit, 1u << ((__ldg(z.segs + s + k) >> LSS_PIDX_BITS) >> 3));
-    __syncthreads();
-    const unsigned hit = s_hit;
-    const TileCoord tc = tile_coord(d, z.tl, tile);
-    const Tile2D t2 = tile_2d<false>(d, z.tl, tc);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int vpr = t2.RL >> 2;                          // 16-byte slots per channel row; slots 2j, 2j+1 = sector j
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int v0 = lane; v0 < vpr; v0 += 32) {
-        if ((hit >> (v0 >> 1)) & 1u) continue;
-        float4 *gp = reinterpret_cast<float4 *>(z.bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
-        const size_t gstep = (size_t)(GATHER_THREADS / 32) * t2.GRS / 4;
-        for (int c = warp; c < d.C; c += GATHER_THREADS / 32, gp += gstep) *gp = zero;
-    }
-}
-
 template <int CPL>
 __global__ void __launch_bounds__(GATHER_THREADS, 1024 / GATHER_THREADS)
 k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_count, const int4 *__restrict__ seg_recs,
              const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs, long long n_rows_cap,
              const uint32_t *__restrict__ entries, const float *__restrict__ prob, const float *__restrict__ prob_col,
-             const float *__restrict__ ctx_t, float *__restrict__ vsum, ZeroArgs z) {
+             const float *__restrict__ ctx_t, float *__restrict__ vsum) {
     extern __shared__ __align__(16) float s_col[];       // [fH][C] context rows of the column, [D][fH] softmax weights
     constexpr int NG = GATHER_THREADS / 8;               // groups per CTA
     constexpr int LF = CPL <= 8 ? 4 : 2;                 // context rows in flight per group (generic voxels)
-    lss_pdl_trigger();                                   // PDL: the store kernel may start its prologue in our tail
     lss_pdl_wait();                                      // launched programmatically behind the plan build (or lift_prepare):
                                                          // everything below reads what those kernels wrote
-    if ((int)blockIdx.x >= (int)gridDim.x - z.n_tiles) {  // zero role
-        zero_empty_sectors(d, z, z.tile_lo + (int)blockIdx.x - ((int)gridDim.x - z.n_tiles));
-        return;
-    }
+    lss_pdl_trigger();                                   // PDL: the store kernel may be scheduled in our tail.  The trigger comes
+                                                         // AFTER the wait: a dependent that starts early then knows that every
+                                                         // kernel before this one is complete (transitivity of the chain)
     // The FIRST CTAs of the grid drain the queue of mixed voxels (group per voxel, all operands from global memory):
     // they start at once, live a few microseconds and hand their slots to the column CTAs that did not fit the first
     // wave, instead of forming the tail of the kernel.
-    const int n_queue = (int)gridDim.x - z.n_tiles - n_keys, qfirst = QUEUE_FIRST ? n_queue : 0;
-    const int bid = QUEUE_FIRST ? ((int)blockIdx.x < n_queue ? n_keys + (int)blockIdx.x : (int)blockIdx.x - n_queue) : (int)blockIdx.x;
-    (void)qfirst;
+    const int n_queue = (int)gridDim.x - n_keys;
+    const int bid = (int)blockIdx.x < n_queue ? n_keys + (int)blockIdx.x : (int)blockIdx.x - n_queue;
     const bool column = bid < n_keys;                    // (measured: a warp per mixed voxel -- 16 rows in flight, sum
     const int key = column ? key_lo + bid : 0;           // handed on by shuffle -- is slower than a group per voxel)
-    lss_stamp<true>(blockIdx.x, 0);                      // voxel (16 rows in flight, sum handed on by shuffle) is slower
     const int n_rec = column ? __ldg(key_count + key) : __ldg(counters + 1);
     const int w0 = column ? key % d.fW : -1, bn = key / d.fW;
     const int n0 = column ? bn % d.N : -1;
@@ -429,7 +380,6 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
     if (r < n_rec) rec = __ldg(recs + r);
     if (rec.y > 0 && gl < rec.y) e0 = __ldg(entries + rec.x + gl);
     if (column) __syncthreads();
-    lss_stamp<true>(blockIdx.x, 1);
     while (__any_sync(LSS_FULL_MASK, r < n_rec)) {
         const int nr = r + stride;
         const float *prob_b = prob + (size_t)rec.z * d.P;
@@ -508,18 +458,6 @@ k_fwd_gather(Dims d, int key_lo, int n_keys, const int32_t *__restrict__ key_cou
         rec = nrec;
         if (rec.y > 0 && gl < rec.y) e0 = __ldg(entries + rec.x + gl);    // generic voxel: its first 8 entries
     }
-    if (lane == 0 && g_lss_timeline_gather != nullptr) {
-        const int key = blockIdx.x;
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMax(g_lss_timeline_gather + (size_t)key * 8 + 3, t);
-        if (threadIdx.x == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_lss_timeline_gather[(size_t)key * 8 + 7] = n_rec;
-            g_lss_timeline_gather[(size_t)key * 8 + 4] = smid;
-        }
-    }
 }
 
 // (2) k_fwd_store -- tile owner, pure streaming: the compact rows of the tile (one contiguous block) are
@@ -534,7 +472,6 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
     extern __shared__ __align__(16) float smem[];
     const int tile = tile_lo + blockIdx.x;
     const int c0 = blockIdx.y * (CH < 0 ? -CH : CH);      // this CTA owns channels [c0, c0 + CH) of the tile
-    if (blockIdx.y == 0) lss_stamp(tile, 0);
     const TileCoord tc = tile_coord(d, tl, tile);
     Tile2D t2 = tile_2d<CL>(d, tl, tc);
     { const int ch = CH < 0 ? -CH : CH;
@@ -542,12 +479,11 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
       else { t2.NR = ch; t2.gbase += (size_t)c0 * t2.GRS; } }
     const int nseg = CH < 0 ? 0 : __ldg(tile_nseg + tile);      // CH < 0: measurement aid, zero tiles only
     if (CH < 0) CH = -CH;
-    if (nseg == 0) { store_tile<VEC4, NT>(t2, nullptr, bev); if (blockIdx.y == 0) lss_stamp(tile, 3); return; }
+    if (nseg == 0) { store_tile<VEC4, NT>(t2, nullptr, bev); return; }
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
     const int C = d.C, c4 = CH >> 2;                      // C % 4 == 0 and CH % 4 == 0 on this path
     const int per_pass = NT / c4;              // rows per pass
     const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
-    if (blockIdx.y == 0) lss_stamp(tile, 1);
     // PDL: everything above reads plan data only (written by earlier, completed launches); the compact rows come
     // from the gather kernel, which may still be running if this kernel was launched programmatically
     lss_pdl_wait();
@@ -578,10 +514,7 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
         }
     }
     __syncthreads();
-    if (blockIdx.y == 0) lss_stamp(tile, 2);
     store_tile<VEC4, NT>(t2, smem, bev);
-    if (blockIdx.y == 0) lss_stamp(tile, 3);
-    if (threadIdx.x == 0 && blockIdx.y == 0 && g_lss_timeline != nullptr) g_lss_timeline[(size_t)tile * 8 + 7] = nseg;
 }
 
 // (2a) k_fwd_store_rows -- NCHW, 16-byte aligned rows: the same streaming store WITHOUT a staging tile.  All C channel
@@ -591,43 +524,29 @@ k_fwd_store(Dims d, Tiling tl, int tile_lo, int CH, const int32_t *__restrict__ 
 // shared memory (a few KB, odd stride).  Shared memory per CTA drops from 52 KB to ~8 KB, so the SM runs its full
 // complement of CTAs, and the 51 KB zero-fill / read-back of the staging tile disappears.
 #define ROWS_CAP 64      // compact rows staged in shared memory (tiles with more non-empty columns read the rest from global)
-#ifndef STORE_ROWS_MINB
-#define STORE_ROWS_MINB 4       // 6 (40 registers, spills) measured no better
-#endif
-// LEAN (default; LSS_STORE_LEAN=0 selects the first version): the prologue is two global round trips instead of
-// four -- the three words of tile meta data are requested together, and the tile's compact rows are requested
-// (into registers) together with its column list, before the column map is built; rows and map then go to shared
-// memory behind one barrier.  A CTA lives ~6 us of which ~2 us are stores, so the dependent loads in front of the
-// store stream are what keeps the kernel away from the write floor.
-// SKIPZ: the 32-byte sectors of the tile that hold no non-empty column (about a third of the grid at cfg 2) were
-// already zero-filled by the zero-role CTAs that ride at the end of the gather grid (k_fwd_gather, ZeroArgs), in the
-// shadow of the gather's tail; this kernel then writes the remaining sectors only (a sector is always written whole
-// and by one kernel).  Both sides derive "empty sector" from the tile's column list in the same way.
-template <bool LEAN, bool SKIPZ, int MINB = STORE_ROWS_MINB>
-__global__ void __launch_bounds__(SPLAT_THREADS, MINB)
+// The prologue is two global round trips: the three words of tile meta data are requested together, and the tile's compact
+// rows are requested (into registers) together with its column list, before the column map is built; rows and map then go
+// to shared memory behind one barrier.  A CTA lives ~6 us of which ~2 us are stores, so the dependent loads in front of the
+// store stream are what keeps the kernel away from the write floor.  (Measured and dropped in round 1: a four-round-trip
+// prologue, 5 CTAs per SM, a persistent cp.async-pipelined variant, zero sectors written by spare CTAs of the gather grid.)
+__global__ void __launch_bounds__(SPLAT_THREADS, 4)
 k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                  const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs, const float *__restrict__ vsum,
                  float *__restrict__ bev) {
     extern __shared__ __align__(16) float s_rows[];               // [ROWS_CAP][C + 1], then short map[TY rounded to 8]
+    lss_pdl_wait();                                               // plan data and compact rows come from the kernels before this one
     lss_pdl_trigger();                                            // a dependent launch (the backward's row gather) may be scheduled in our tail
     const int tile = tile_lo + blockIdx.x;
     const int C = d.C, SR = C + 1, c4 = C >> 2;
     short *s_map = reinterpret_cast<short *>(s_rows + ROWS_CAP * SR + (ROWS_CAP & 1));
-    int nseg, s, row0;
-    if (LEAN) {
-        nseg = __ldg(tile_nseg + tile); s = __ldg(tile_start + tile); row0 = __ldg(tile_row0 + tile);   // one round trip
-        for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
-    } else {
-        nseg = __ldg(tile_nseg + tile);
-    }
+    const int nseg = __ldg(tile_nseg + tile), s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);   // one round trip
+    for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
     const TileCoord tc = tile_coord(d, tl, tile);
     const Tile2D t2 = tile_2d<false>(d, tl, tc);
-    if (nseg == 0) { if (!SKIPZ) { lss_pdl_wait(); store_tile<true>(t2, nullptr, bev); } return; }
+    if (nseg == 0) { store_tile<true>(t2, nullptr, bev); return; }
     const int nst = min(nseg, ROWS_CAP);
-    if (LEAN) {
-        // the column list is plan data (older than the gather): request it before waiting for the gather
+    {
         const uint32_t e0 = threadIdx.x < nseg ? __ldg(segs + s + threadIdx.x) : 0u;
-        lss_pdl_wait();                                           // the compact rows come from the gather kernel
         float4 r[4];                                              // this thread's share of the first 4 * 256 row quads
         const float4 *rsrc = reinterpret_cast<const float4 *>(vsum + (size_t)row0 * C);   // the tile's rows are one block
         const int nq = nst * c4;
@@ -655,34 +574,15 @@ k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ til
             dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
         }
         __syncthreads();
-    } else {
-        s = __ldg(tile_start + tile); row0 = __ldg(tile_row0 + tile);
-        for (int i = threadIdx.x; i < (tl.TY + 7) / 8 * 4; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
-        __syncthreads();
-        for (int k = threadIdx.x; k < nseg; k += SPLAT_THREADS) s_map[__ldg(segs + s + k) >> LSS_PIDX_BITS] = (short)k;
-        lss_pdl_wait();                                           // the compact rows come from the gather kernel
-        for (int i = threadIdx.x; i < nst * c4; i += SPLAT_THREADS) { // coalesced: the tile's rows are one block
-            const int k = i / c4, q = i - k * c4;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(vsum + (size_t)(row0 + k) * C) + q);
-            float *dst = s_rows + k * SR + 4 * q;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-        }
-        __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = t2.RL >> 2;                                   // 16-byte slots per channel row (<= 64 handled per lane pair)
     const float *rows_g = vsum + (size_t)row0 * C;
     for (int vb = 0; vb < vpr; vb += 32) {                        // usually 2 slots per lane (warp-uniform loop)
         const int v0 = vb + lane;
-        const bool valid = v0 < vpr;
-        uint2 m = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-        if (valid) m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
+        if (v0 >= vpr) continue;
+        const uint2 m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
         const int k0 = (short)(m.x & 0xFFFFu), k1 = (short)(m.x >> 16), k2 = (short)(m.y & 0xFFFFu), k3 = (short)(m.y >> 16);
-        if (SKIPZ) {                                              // slots 2j, 2j+1 = lanes 2j, 2j+1 form a sector
-            const bool empty = (m.x & m.y & 0x80008000u) == 0x80008000u;     // all four columns without a voxel
-            const bool pair_empty = __shfl_xor_sync(LSS_FULL_MASK, empty ? 1 : 0, 1) != 0;
-            if (!valid || (empty && pair_empty)) continue;
-        } else if (!valid) continue;
         float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
         const size_t gstep = (size_t)SPLAT_WARPS * t2.GRS / 4;
         if (nseg <= ROWS_CAP) {                                   // CTA-uniform: every compact row is staged
@@ -703,95 +603,7 @@ k_fwd_store_rows(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ til
     }
 }
 
-// (2a') k_fwd_store_rows_persist (experiment, off: see launch_fwd_store) -- the same row store as a PERSISTENT,
-// software-pipelined kernel: a CTA walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... with two shared-memory stages.  While tile i streams out, the column list and the
-// compact rows of tile i+1 are already on their way into the other stage (cp.async, no registers), and the meta words of
-// tile i+2 are in flight into registers: after a CTA's first tile the dependent loads in front of the store stream are
-// hidden, so the SM keeps storing.  Rows are staged with a stride of C + 4 floats (16-byte aligned for cp.async; the
-// lanes of a warp read one channel of different rows, 8 distinct bank groups).
-__global__ void __launch_bounds__(SPLAT_THREADS, STORE_ROWS_MINB)
-k_fwd_store_rows_persist(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__restrict__ tile_start,
-                         const int32_t *__restrict__ tile_nseg, const int32_t *__restrict__ tile_row0,
-                         const uint32_t *__restrict__ segs, const float *__restrict__ vsum, float *__restrict__ bev) {
-    extern __shared__ __align__(16) float sm_p[];
-    const int C = d.C, SR = C + 4, c4 = C >> 2;
-    const int stage_floats = ROWS_CAP * SR;
-    const int TYp = (tl.TY + 7) & ~7;
-    uint32_t *s_segs = reinterpret_cast<uint32_t *>(sm_p + 2 * stage_floats);      // [2][TYp]
-    short *s_map = reinterpret_cast<short *>(s_segs + 2 * TYp);                    // [TYp]
-    const unsigned rows_addr = (unsigned)__cvta_generic_to_shared(sm_p);
-    const unsigned segs_addr = (unsigned)__cvta_generic_to_shared(s_segs);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int t = blockIdx.x;
-    if (t >= n_tiles) return;
-    int tn = t + gridDim.x;
-    int c_nseg = __ldg(tile_nseg + tile_lo + t), c_s = __ldg(tile_start + tile_lo + t), c_row0 = __ldg(tile_row0 + tile_lo + t);
-    int n_nseg = 0, n_s = 0, n_row0 = 0;
-    if (tn < n_tiles) { n_nseg = __ldg(tile_nseg + tile_lo + tn); n_s = __ldg(tile_start + tile_lo + tn); n_row0 = __ldg(tile_row0 + tile_lo + tn); }
-    auto issue = [&](int nseg, int s, int row0, int b) {      // column list + compact rows of one tile -> stage b
-        if (nseg > 0) {
-            for (int k = threadIdx.x; k < nseg; k += SPLAT_THREADS)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(segs_addr + 4u * (unsigned)(b * TYp + k)), "l"(segs + s + k) : "memory");
-            const int nq = min(nseg, ROWS_CAP) * c4;
-            const float4 *rsrc = reinterpret_cast<const float4 *>(vsum + (size_t)row0 * C);    // the tile's rows are one block
-            for (int i = threadIdx.x; i < nq; i += SPLAT_THREADS) {
-                const int k = i / c4, q = i - k * c4;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rows_addr + 4u * (unsigned)(b * stage_floats + k * SR + 4 * q)), "l"(rsrc + i) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    lss_pdl_wait();                                               // the compact rows come from the gather kernel
-    issue(c_nseg, c_s, c_row0, 0);
-    for (int b = 0; t < n_tiles; b ^= 1) {
-        const int tnn = tn + gridDim.x;
-        int nn_nseg = 0, nn_s = 0, nn_row0 = 0;
-        if (tnn < n_tiles) { nn_nseg = __ldg(tile_nseg + tile_lo + tnn); nn_s = __ldg(tile_start + tile_lo + tnn); nn_row0 = __ldg(tile_row0 + tile_lo + tnn); }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                          // stage b has landed; everybody is done with the previous tile
-        const TileCoord tc = tile_coord(d, tl, tile_lo + t);
-        const Tile2D t2 = tile_2d<false>(d, tl, tc);
-        if (c_nseg == 0) {                                        // CTA-uniform
-            issue(n_nseg, n_s, n_row0, b ^ 1);
-            store_tile<true>(t2, nullptr, bev);
-        } else {
-            for (int i = threadIdx.x; i < TYp / 2; i += SPLAT_THREADS) reinterpret_cast<unsigned *>(s_map)[i] = 0xFFFFFFFFu;
-            __syncthreads();
-            for (int k = threadIdx.x; k < c_nseg; k += SPLAT_THREADS) s_map[s_segs[b * TYp + k] >> LSS_PIDX_BITS] = (short)k;
-            issue(n_nseg, n_s, n_row0, b ^ 1);                    // next tile on its way while this one is stored
-            __syncthreads();
-            const float *s_rows = sm_p + b * stage_floats;
-            const float *rows_g = vsum + (size_t)c_row0 * C;
-            const int vpr = t2.RL >> 2;
-            for (int v0 = lane; v0 < vpr; v0 += 32) {
-                const uint2 m = *reinterpret_cast<const uint2 *>(s_map + 4 * v0);
-                const int k0 = (short)(m.x & 0xFFFFu), k1 = (short)(m.x >> 16), k2 = (short)(m.y & 0xFFFFu), k3 = (short)(m.y >> 16);
-                float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)warp * t2.GRS) + v0;
-                const size_t gstep = (size_t)SPLAT_WARPS * t2.GRS / 4;
-                if (c_nseg <= ROWS_CAP) {
-                    const float *p0 = s_rows + max(k0, 0) * SR, *p1 = s_rows + max(k1, 0) * SR;
-                    const float *p2 = s_rows + max(k2, 0) * SR, *p3 = s_rows + max(k3, 0) * SR;
-#pragma unroll 4
-                    for (int c = warp; c < C; c += SPLAT_WARPS, gp += gstep) {
-                        float4 o;
-                        o.x = k0 >= 0 ? p0[c] : 0.f; o.y = k1 >= 0 ? p1[c] : 0.f;
-                        o.z = k2 >= 0 ? p2[c] : 0.f; o.w = k3 >= 0 ? p3[c] : 0.f;
-                        *gp = o;
-                    }
-                } else {
-                    auto val = [&](int k, int c) { return k < 0 ? 0.f : (k < ROWS_CAP ? s_rows[k * SR + c] : __ldg(rows_g + (size_t)k * C + c)); };
-                    for (int c = warp; c < C; c += SPLAT_WARPS, gp += gstep) *gp = make_float4(val(k0, c), val(k1, c), val(k2, c), val(k3, c));
-                }
-            }
-        }
-        t = tn; tn = tnn;
-        c_nseg = n_nseg; c_s = n_s; c_row0 = n_row0;
-        n_nseg = nn_nseg; n_s = nn_s; n_row0 = nn_row0;
-    }
-}
-
-// (2b) k_fwd_store_tma -- the same streaming store as a PERSISTENT kernel: every CTA walks tiles with two staging
+// (2b) k_fwd_store_tma (contiguous channels_last tiles of TILE plans) -- the same streaming store as a PERSISTENT kernel: every CTA walks tiles with two staging
 // buffers.  The rows of the staged tile leave through the bulk-copy engine (cp.async.bulk shared -> global, issued by
 // one warp), so the CTA does not wait for its stores: while tile k drains it zero-fills the other buffer and
 // transposes tile k+1 into it; the meta data and the first compact rows of tile k+1 are requested one iteration
@@ -805,12 +617,12 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool CL, bool USE_TMA = true>
+template <bool CL>
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__restrict__ tile_start,
                 const int32_t *__restrict__ tile_nseg, const int32_t *__restrict__ tile_row0,
                 const uint32_t *__restrict__ segs, const float *__restrict__ vsum, float *__restrict__ bev) {
-    extern __shared__ __align__(128) float smem[];
+    extern __shared__ __align__(16) float smem[];    // (dynamic shared memory starts 128-byte aligned)
     const int C = d.C, c4 = C >> 2;
     const int SRS = CL ? C : tl.TY + 4;
     const int tile_floats = CL ? tl.TY * C : C * SRS;
@@ -840,13 +652,13 @@ k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__re
     prefetch(blockIdx.x);
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        float *buf = smem + (USE_TMA ? (it & 1) * tile_floats : 0);
+        float *buf = smem + (it & 1) * tile_floats;
         const int nseg = n_nseg, s = n_s, row0 = n_row0;
         const int col[2] = {n_col[0], n_col[1]};
         const float4 v[2] = {n_v[0], n_v[1]};
         prefetch(t + gridDim.x);                          // dependent loads of the next tile start now
-        if (USE_TMA && threadIdx.x < 32) bulk_wait_read<1>();   // this buffer was handed to the copy engine two tiles ago
-        __syncthreads();                                  // (LSU variant: everybody has read the previous tile)
+        if (threadIdx.x < 32) bulk_wait_read<1>();        // this buffer was handed to the copy engine two tiles ago
+        __syncthreads();
         zero_smem(buf, tile_floats);
         __syncthreads();
         if (loader) {
@@ -864,28 +676,9 @@ k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__re
                 }
             }
         }
-        if (USE_TMA) fence_async_smem();                  // generic-proxy writes -> visible to the async proxy
+        fence_async_smem();                               // generic-proxy writes -> visible to the async proxy
         __syncthreads();
-        if (!USE_TMA) {                                   // persistent LSU variant: ordinary 16-byte stores
-            const TileCoord tc = tile_coord(d, tl, tile_lo + t);
-            const Tile2D t2 = tile_2d<CL>(d, tl, tc);
-            if (true) {                                   // store_tile may return early for idle lanes: keep it last
-                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-                const int vpr = t2.RL >> 2;
-                const int rpw = vpr >= 32 ? 1 : 32 / vpr;
-                const int sub = rpw == 1 ? 0 : lane / vpr;
-                const int v0 = rpw == 1 ? lane : lane - sub * vpr;
-                if (sub < rpw) {
-                    const int rowa = warp * rpw + sub, rstep = SPLAT_WARPS * rpw;
-                    float4 *gp = reinterpret_cast<float4 *>(bev + t2.gbase + (size_t)rowa * t2.GRS) + v0;
-                    const size_t gstep = (size_t)rstep * t2.GRS / 4;
-                    const float4 *sp = reinterpret_cast<const float4 *>(buf + rowa * SRS) + v0;
-                    const int sstep = rstep * SRS / 4;
-                    for (int row = rowa; row < t2.NR; row += rstep, gp += gstep, sp += sstep)
-                        for (int v = v0; v < vpr; v += 32) gp[v - v0] = sp[v - v0];
-                }
-            }
-        } else if (threadIdx.x < 32) {
+        if (threadIdx.x < 32) {
             const TileCoord tc = tile_coord(d, tl, tile_lo + t);
             const Tile2D t2 = tile_2d<CL>(d, tl, tc);
             float *g = bev + t2.gbase;
@@ -897,7 +690,7 @@ k_fwd_store_tma(Dims d, Tiling tl, int tile_lo, int n_tiles, const int32_t *__re
             bulk_commit();                                // one group per tile and lane (possibly empty)
         }
     }
-    if (USE_TMA && threadIdx.x < 32) bulk_wait_all();
+    if (threadIdx.x < 32) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1097,11 +890,11 @@ __global__ void __launch_bounds__(SPLAT_THREADS, 4)
 k_bwd_rows_compact(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ tile_start, const int32_t *__restrict__ tile_nseg,
                    const int32_t *__restrict__ tile_row0, const uint32_t *__restrict__ segs,
                    const float *__restrict__ grad_bev, float *__restrict__ grows) {
+    lss_pdl_wait();                                // the gradient (and, in a captured step, the plan) come from kernels before this one
     lss_pdl_trigger();
     const int tile = tile_lo + blockIdx.x;
-    const int nseg = __ldg(tile_nseg + tile);      // plan data: older than the previous launch
+    const int nseg = __ldg(tile_nseg + tile);
     const int s = __ldg(tile_start + tile), row0 = __ldg(tile_row0 + tile);
-    lss_pdl_wait();                                // the gradient may come from the kernel right before this one
     if (nseg == 0) return;
     const TileCoord tc = tile_coord(d, tl, tile);
     const int C = d.C;
@@ -1147,15 +940,9 @@ k_bwd_rows_compact(Dims d, Tiling tl, int tile_lo, const int32_t *__restrict__ t
 // reads shared memory, keeps LF gradient rows in flight and needs no control flow (dropped points read
 // row 0 with weight 0).  Outputs are staged and written as runs of WC floats.
 //
-// DIRECT (NCHW gradients; experiment, off by default -- see run_bwd_compact): no k_bwd_rows_compact launch and no compact gradient rows.  `prow` is
-// then the plan's voxel id per point (point-major), and the CTA stages the gradient rows of its columns' primary voxels
-// straight from the NCHW tensor: one 4-byte cp.async per (voxel, channel), a warp covering 32 voxels along the CTA's
-// rays for one channel (neighbouring voxels share 32-byte sectors), ALL of the CTA's ~10 k requests in flight together.
-// The sector-bound DRAM read (63 MB at cfg 2) that was a kernel of its own now overlaps this kernel's other phases and
-// the compact rows' round trip through L2 disappears.  Shared-memory rows are XOR-swizzled at 16-byte granularity
-// (chunk ^= voxel & 7) so that the 4-byte writes of a warp spread over the banks; a group still reads one 128-byte line.
+// (Measured and dropped in round 1: fetching the rows straight from an NCHW gradient inside this kernel, 83 us.)
 struct GpxMagic { unsigned long long per, fH, npx, WC; };   // ceil(2^40 / x) of D*fH, fH, fH*WC, WC (lss_div20)
-template <int CPL, bool DIRECT>
+template <int CPL>
 __global__ void __launch_bounds__(SPLAT_THREADS)
 k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const int32_t *__restrict__ prow, const float *__restrict__ prob_col,
                 const float *__restrict__ ctx_t, const float *__restrict__ grows, float *__restrict__ grad_dn) {
@@ -1170,9 +957,7 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
     int *s_row = reinterpret_cast<int *>(smem + 32 * D);  // [32][D] compact row or -1
     float *s_gp = smem + 64 * D;                          // [32][D] <grad row, ctx>
     float *s_out = smem + 96 * D;                         // [D + C][npx] staged outputs
-    int *s_off = reinterpret_cast<int *>(smem + 96 * D + DC * npx);   // DIRECT: [WC][D] NCHW element offset of the primary voxel, or -1
-    float *s_g = smem + ((96 * D + DC * npx + (DIRECT ? WC * D : 0) + 3) & ~3);   // [WC][D][C] rows of the columns' primary voxels (16-byte aligned)
-    const int plane = d.nx * d.ny;                        // DIRECT: elements per channel plane of the NCHW gradient
+    float *s_g = smem + ((96 * D + DC * npx + 3) & ~3);   // [WC][D][C] rows of the columns' primary voxels (16-byte aligned)
     {   // the CTA's columns are one contiguous block [wl][D][fH] in the column-major arrays
         const int ncol = min(WC, d.fW - w0), per = D * fH;
         const size_t base = ((size_t)bn * d.fW + w0) * per;
@@ -1181,16 +966,7 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
             const int dd = (int)lss_div20((unsigned)r, mg.fH), h = r - dd * fH;
             const bool ok = wl < ncol;
             s_p[(h * WC + wl) * D + dd] = ok ? __ldg(prob_col + base + i) : 0.f;
-            if (DIRECT) {       // voxel id of the point, point-major: ((bn*D + dd)*fH + h)*fW + w
-                const int v = ok ? __ldg(prow + ((size_t)(bn * D + dd) * fH + h) * d.fW + w0 + wl) : -1;
-                s_row[(h * WC + wl) * D + dd] = v;
-                if (h == 0) {
-                    const int qz = v >= 0 ? v / plane : 0;                      // b*nz + iz
-                    s_off[wl * D + dd] = v >= 0 ? (qz * C) * plane + (v - qz * plane) : -1;
-                }
-            } else {
-                s_row[(h * WC + wl) * D + dd] = ok ? __ldg(prow + base + i) : -1;
-            }
+            s_row[(h * WC + wl) * D + dd] = ok ? __ldg(prow + base + i) : -1;
         }
     }
     const int lane = threadIdx.x & 31, gl = lane & 7;
@@ -1223,20 +999,6 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
         // (cp.async, global -> shared without a register round trip: ALL the CTA's rows are in flight together; a
         // source size of 0 zero-fills the slot of a dropped point)
         const unsigned s_g_addr = (unsigned)__cvta_generic_to_shared(s_g);
-        if (DIRECT) {
-            const int nv = WC * D, warp_i = threadIdx.x >> 5;
-            for (int cd = lane; cd < nv; cd += 32) {
-                const int off = s_off[cd];
-                const float *src = grows + (off >= 0 ? off : 0);                 // grows = the NCHW gradient tensor here
-                const unsigned row_addr = s_g_addr + 4u * (unsigned)(cd * C);
-                const int sw = cd & 7;
-#pragma unroll 4
-                for (int c = warp_i; c < C; c += NT / 32) {
-                    const unsigned dst = row_addr + 4u * (unsigned)(((((c >> 2) ^ sw)) << 2) | (c & 3));
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src + (size_t)c * plane), "r"(off >= 0 ? 4 : 0) : "memory");
-                }
-            }
-        } else
         for (int i = threadIdx.x; i < WC * D * c4; i += NT) {
             const int cd = i / c4, q = i - cd * c4;       // cd = wl * D + dd; pixel (h = 0, wl) has index wl
             const int r = s_row[cd];
@@ -1249,7 +1011,6 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
         const int *col_row = s_row + (g < npx ? wl : 0) * D;
         const float4 *my_sg = reinterpret_cast<const float4 *>(s_g + (size_t)(g < npx ? wl : 0) * D * C) + gl;
         unsigned exc = 0;                                 // does this pixel hit other voxels than the primary ones?
-        const int cd0 = (g < npx ? wl : 0) * D;              // DIRECT: swizzle key of voxel (wl, dd) is (cd0 + dd) & 7
 #pragma unroll 4
         for (int dd = 0; dd < D; ++dd) {
             const int rj = my_row[dd];
@@ -1257,10 +1018,9 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
             exc |= (active && rj >= 0 && !same) ? 1u : 0u;
             const float pj = (active && same) ? my_p[dd] : 0.f;       // dropped: the staged row is zero anyway
             float dot = 0.f;
-            const int swz = DIRECT ? ((gl ^ ((cd0 + dd) & 7)) - gl) : 0;        // my_sg already points at chunk gl
 #pragma unroll
             for (int q = 0; q < CPL / 4; ++q) {
-                const float4 v = my_sg[dd * c4 + 8 * q + swz];
+                const float4 v = my_sg[dd * c4 + 8 * q];
                 dot = fmaf(v.x, ctx[4 * q], dot); dot = fmaf(v.y, ctx[4 * q + 1], dot);
                 dot = fmaf(v.z, ctx[4 * q + 2], dot); dot = fmaf(v.w, ctx[4 * q + 3], dot);
                 dctx[4 * q] = fmaf(pj, v.x, dctx[4 * q]); dctx[4 * q + 1] = fmaf(pj, v.y, dctx[4 * q + 1]);
@@ -1280,17 +1040,9 @@ k_bwd_gather_px(Dims d, int bn_lo, int WC, int stage_rows, GpxMagic mg, const in
                 const float pj = mine ? my_p[dd] : 0.f;
                 float dot = 0.f;
                 if (mine) {
-                    const int qz = DIRECT ? rj / plane : 0;
-                    const float *gsrc = grows + (size_t)(qz * C) * plane + (rj - qz * plane);   // DIRECT: voxel rj in the NCHW tensor
 #pragma unroll
                     for (int q = 0; q < CPL / 4; ++q) {
-                        float4 v;
-                        if (DIRECT) {
-                            const float *gp4 = gsrc + (size_t)(4 * (gl + 8 * q)) * plane;
-                            v = make_float4(__ldg(gp4), __ldg(gp4 + plane), __ldg(gp4 + 2 * (size_t)plane), __ldg(gp4 + 3 * (size_t)plane));
-                        } else {
-                            v = __ldg(rows4 + (size_t)rj * c4 + 8 * q);
-                        }
+                        const float4 v = __ldg(rows4 + (size_t)rj * c4 + 8 * q);
                         dot = fmaf(v.x, ctx[4 * q], dot); dot = fmaf(v.y, ctx[4 * q + 1], dot);
                         dot = fmaf(v.z, ctx[4 * q + 2], dot); dot = fmaf(v.w, ctx[4 * q + 3], dot);
                         dctx[4 * q] = fmaf(pj, v.x, dctx[4 * q]); dctx[4 * q + 1] = fmaf(pj, v.y, dctx[4 * q + 1]);
@@ -1383,23 +1135,17 @@ static inline Tiling make_tiling(const lss_plan_layout *L) {
     Tiling t; t.TY = L->tile_cols; t.nty = L->tiles_per_row; t.n_tiles = L->n_tiles; return t;
 }
 
-static int num_sms() {
-    static int n_sms = 0;
-    if (n_sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        n_sms = n;
-    }
-    return n_sms;
+static int num_sms() {     // of the CURRENT device (one process may drive several GPUs)
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    return n;
 }
 
+// cudaFuncSetAttribute applies to the current device and is cheap: no per-process cache
 template <typename K>
-static int opt_in_smem(K kern, size_t smem, bool &configured) {
+static int opt_in_smem_dev(K kern, size_t smem) {
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 && !configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
-        configured = true;
-    }
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return LSS_ERR_CUDA;
     return LSS_OK;
 }
 
@@ -1408,8 +1154,7 @@ static int launch_fwd_tile(const Dims &d, const Tiling &tl, const int32_t *tile_
                            const SrcArgs &src, float *bev, cudaStream_t s) {
     const size_t smem = (size_t)(CL ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
     auto kern = k_splat_fwd_tile<VW, KC, ATOMIC, CL, DENSE, VEC4>;
-    static bool configured = false;    // per instantiation
-    int st = opt_in_smem(kern, smem, configured);
+    int st = opt_in_smem_dev(kern, smem);
     if (st != LSS_OK) return st;
     kern<<<tl.n_tiles, SPLAT_THREADS, smem, s>>>(d, tl, tile_start, entries, src, bev);
     LSS_CHECK_LAUNCH();
@@ -1434,102 +1179,41 @@ static inline PlanPtrs plan_ptrs(const lss_plan_layout *L, const void *workspace
     return pp;
 }
 
-// does the NCHW forward go through k_fwd_store_rows (16-byte rows, whole channel range per CTA)?
-static bool store_rows_path(const Dims &d, const Tiling &tl, bool cl, bool vec4) {
-    static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;
-    static int rows_mode = getenv("LSS_STORE_ROWS") ? atoi(getenv("LSS_STORE_ROWS")) : 1;
-    static bool zero_only = getenv("LSS_STORE_ZERO") != nullptr;
-    return rows_mode && !cl && vec4 && (ch_override <= 0 || ch_override == d.C) && !zero_only && tl.TY <= 32767;
-}
-
 template <bool CL, bool VEC4>
 static int launch_fwd_store(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
-                            bool pdl, cudaStream_t s, bool skipz = false) {
-    static int ch_override = getenv("LSS_STORE_CH") ? atoi(getenv("LSS_STORE_CH")) : 0;   // tuning knob
-    int CH = ch_override > 0 ? ch_override : d.C;         // channels per CTA (a smaller staging tile = more CTAs per SM)
-    if (d.C % CH != 0 || CH % 4 != 0) CH = d.C;
-    const size_t smem = (size_t)(CL ? tl.TY * CH : CH * (tl.TY + 4)) * 4;
-    // NCHW with 16-byte rows: the staging-free kernel (36.1 vs 37.9 us forward at cfg 2); LSS_STORE_ROWS=0 switches it off
-    static int rows_mode = getenv("LSS_STORE_ROWS") ? atoi(getenv("LSS_STORE_ROWS")) : 1;
-    if (rows_mode && !CL && VEC4 && CH == d.C && getenv("LSS_STORE_ZERO") == nullptr && tl.TY <= 32767) {
-        const size_t rsm = (size_t)(ROWS_CAP * (d.C + 1) + 1) * 4 + (size_t)((tl.TY + 7) / 8) * 16;
-        const int tpsr = tl.n_tiles / d.B;
-        // persistent, software-pipelined variant (experiment, LSS_STORE_PERSIST=1).  Measured at cfg 2: 23.2 us against
-        // 20.5 us for one CTA per tile (forward 37.4 vs 33.1 us) -- like the earlier persistent stores, the statically
-        // strided CTAs lose more to their lock-step start and uneven tile counts than the hidden prologues win: OFF.
-        static int persist = getenv("LSS_STORE_PERSIST") ? atoi(getenv("LSS_STORE_PERSIST")) : 0;
-        const int TYp = (tl.TY + 7) & ~7;
-        const size_t psm = (size_t)2 * ROWS_CAP * (d.C + 4) * 4 + (size_t)2 * TYp * 4 + (size_t)TYp * 2;
-        if (persist && !skipz && psm <= 100 * 1024) {
-            static bool configured_p = false;
-            int stp = opt_in_smem(k_fwd_store_rows_persist, psm, configured_p);
-            if (stp != LSS_OK) return stp;
-            static int per_sm_p = 0;
-            static size_t per_sm_p_smem = 0;
-            if (per_sm_p == 0 || per_sm_p_smem != psm) {
-                int nb = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fwd_store_rows_persist, SPLAT_THREADS, psm) != cudaSuccess || nb < 1) nb = 1;
-                per_sm_p = nb; per_sm_p_smem = psm;
-            }
-            const int n_t = (b1 - b0) * tpsr;
-            const int grid_p = min(n_t, num_sms() * per_sm_p);
-            if (lss_launch(k_fwd_store_rows_persist, dim3(grid_p), dim3(SPLAT_THREADS), psm, s, pdl, d, tl, b0 * tpsr, n_t,
-                           pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
-            LSS_CHECK_LAUNCH();
-            return LSS_OK;
-        }
-        static int lean = getenv("LSS_STORE_LEAN") ? atoi(getenv("LSS_STORE_LEAN")) : 1;
-        static int minb = getenv("LSS_STORE_MINB") ? atoi(getenv("LSS_STORE_MINB")) : 4;      // tuning knob: CTAs per SM the registers allow
-        auto kern = skipz ? k_fwd_store_rows<true, true> : (lean ? (minb == 5 ? k_fwd_store_rows<true, false, 5> : k_fwd_store_rows<true, false>) : k_fwd_store_rows<false, false>);
-        if (lss_launch(kern, dim3((b1 - b0) * tpsr), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tpsr,
-                       pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
-        LSS_CHECK_LAUNCH();
-        return LSS_OK;
-    }
-    static int nt512 = getenv("LSS_STORE_NT") ? atoi(getenv("LSS_STORE_NT")) == 512 : 0;                 // tuning knob
-    if (nt512) {
-        auto kern5 = k_fwd_store<CL, VEC4, 512>;
-        static bool configured5 = false;
-        int st5 = opt_in_smem(kern5, smem, configured5);
-        if (st5 != LSS_OK) return st5;
-        const int tps5 = tl.n_tiles / d.B;
-        if (lss_launch(kern5, dim3((b1 - b0) * tps5, d.C / CH), dim3(512), smem, s, pdl, d, tl, b0 * tps5, CH,
-                       pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
-        LSS_CHECK_LAUNCH();
-        return LSS_OK;
-    }
-    auto kern = k_fwd_store<CL, VEC4, SPLAT_THREADS>;
-    static bool configured = false;
-    int st = opt_in_smem(kern, smem, configured);
-    if (st != LSS_OK) return st;
-    static int zero_only = getenv("LSS_STORE_ZERO") ? 1 : 0;                                // measurement aid
+                            bool pdl, cudaStream_t s) {
     const int tps = tl.n_tiles / d.B;                     // tiles per sample
-    if (lss_launch(kern, dim3((b1 - b0) * tps, d.C / CH), dim3(SPLAT_THREADS), smem, s, pdl, d, tl, b0 * tps, zero_only ? -CH : CH,
+    // NCHW with 16-byte rows: the staging-free kernel (36.1 vs 37.9 us forward at cfg 2)
+    if (!CL && VEC4 && tl.TY <= 32767) {
+        const size_t rsm = (size_t)(ROWS_CAP * (d.C + 1) + 1) * 4 + (size_t)((tl.TY + 7) / 8) * 16;
+        if (lss_launch(k_fwd_store_rows, dim3((b1 - b0) * tps), dim3(SPLAT_THREADS), rsm, s, pdl, d, tl, b0 * tps,
+                       pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
+        LSS_CHECK_LAUNCH();
+        return LSS_OK;
+    }
+    const size_t smem = (size_t)(CL ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
+    auto kern = k_fwd_store<CL, VEC4, SPLAT_THREADS>;
+    int st = opt_in_smem_dev(kern, smem);
+    if (st != LSS_OK) return st;
+    if (lss_launch(kern, dim3((b1 - b0) * tps, 1), dim3(SPLAT_THREADS), smem, s, pdl, d, tl, b0 * tps, d.C,
                    pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
 
-template <bool CL, bool USE_TMA>
+template <bool CL>
 static int launch_fwd_store_tma(const Dims &d, const Tiling &tl, const PlanPtrs &pp, const float *vsum, float *bev, int b0, int b1,
                                 cudaStream_t s) {
     const int tile_floats = CL ? tl.TY * d.C : d.C * (tl.TY + 4);
-    const size_t smem = (size_t)(USE_TMA ? 2 : 1) * tile_floats * 4;
-    auto kern = k_fwd_store_tma<CL, USE_TMA>;
-    static bool configured = false;
-    int st = opt_in_smem(kern, smem, configured);
+    const size_t smem = (size_t)2 * tile_floats * 4;
+    auto kern = k_fwd_store_tma<CL>;
+    int st = opt_in_smem_dev(kern, smem);
     if (st != LSS_OK) return st;
-    static int per_sm = 0;
-    static size_t per_sm_smem = 0;
-    if (per_sm == 0 || per_sm_smem != smem) {
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SPLAT_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
-        per_sm = nb; per_sm_smem = smem;
-    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SPLAT_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int tps = tl.n_tiles / d.B, n_tiles = (b1 - b0) * tps;
     const int grid = min(n_tiles, num_sms() * per_sm);
-    static int zero_only = getenv("LSS_STORE_ZERO") ? 1 : 0;                                // measurement aid
-    kern<<<grid, SPLAT_THREADS, smem, s>>>(d, tl, b0 * tps, n_tiles, pp.tile_start, zero_only ? nullptr : pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
+    kern<<<grid, SPLAT_THREADS, smem, s>>>(d, tl, b0 * tps, n_tiles, pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, vsum, bev);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -1538,50 +1222,31 @@ static int launch_fwd_store_tma(const Dims &d, const Tiling &tl, const PlanPtrs 
 static int run_fwd_group(bool cl, bool vec4, const Dims &d, const Tiling &tl, const PlanPtrs &pp, long long L_rows_cap,
                          const float *prob, const float *prob_col, const float *ctx_t, float *vsum, float *bev,
                          int variant, int b0, int b1, cudaStream_t s) {
-    bool zsplit = false;                                  // empty sectors zero-filled by the gather grid, skipped by the store
-    if (variant == LSS_VARIANT_GROUP_STORE) goto store;
-    {
-    const int key_lo = b0 * d.N * d.fW;
-    const int n_keys = (b1 - b0) * d.N * d.fW;           // one CTA per camera column of the samples [b0, b1) ...
-    // ... plus the CTAs that drain the queue of mixed voxels (of ALL samples): they ride with the part that starts at 0
-    // zero-role CTAs (see ZeroArgs): only when the NCHW row store follows in this call (experiment, LSS_FWD_ZSPLIT=1)
-    // Measured at cfg 2: the store kernel writes a third fewer bytes but shrinks only from 20.7 to 18.1 us (it is bound by
-    // its per-CTA latency chain, not by bytes), while the gather grows from 13.7 to 18.1 us -> forward 36.5 vs 31.6 us: OFF.
-    static int zsplit_knob = getenv("LSS_FWD_ZSPLIT") ? atoi(getenv("LSS_FWD_ZSPLIT")) : 0;
-    const int tps_z = tl.n_tiles / d.B;
-    zsplit = zsplit_knob && variant != LSS_VARIANT_GROUP_GATHER && store_rows_path(d, tl, cl, vec4) && d.ny % 8 == 0 && tl.TY <= 256;
-    const ZeroArgs za{zsplit ? bev : nullptr, pp.tile_start, pp.tile_nseg, pp.segs, tl, b0 * tps_z, zsplit ? (b1 - b0) * tps_z : 0};
-    const int grid = n_keys + (b0 == 0 ? 2 * num_sms() : 0) + za.n_tiles;
-    const size_t gsm = max((size_t)(d.fH * d.C + d.D * d.fH), (size_t)(GATHER_THREADS / 8) * d.C) * 4;   // column operands / long-voxel products
-    if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
-#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, L_rows_cap, pp.entries, prob, prob_col, ctx_t, vsum, za
-    // programmatic launch: the grid is scheduled while its predecessor drains and waits at its top (launch latency only)
-    cudaError_t ge;
-    if (d.C == 32) ge = lss_launch(k_fwd_gather<4>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
-    else if (d.C == 64) ge = lss_launch(k_fwd_gather<8>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
-    else ge = lss_launch(k_fwd_gather<16>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
-    if (ge != cudaSuccess) return LSS_ERR_CUDA;
+    if (variant != LSS_VARIANT_GROUP_STORE) {
+        const int key_lo = b0 * d.N * d.fW;
+        const int n_keys = (b1 - b0) * d.N * d.fW;       // one CTA per camera column of the samples [b0, b1) ...
+        // ... plus the CTAs that drain the queue of mixed voxels (of ALL samples): they ride with the part that starts at 0
+        const int grid = n_keys + (b0 == 0 ? 2 * num_sms() : 0);
+        const size_t gsm = max((size_t)(d.fH * d.C + d.D * d.fH), (size_t)(GATHER_THREADS / 8) * d.C) * 4;   // column operands / long-voxel products
+        if (gsm > 48 * 1024) return LSS_ERR_UNSUPPORTED;
+#define GATHER_ARGS d, key_lo, n_keys, pp.key_count, pp.seg_recs, pp.counters, pp.mixed_recs, L_rows_cap, pp.entries, prob, prob_col, ctx_t, vsum
+        // programmatic launch: the grid is scheduled while its predecessor drains and waits at its top (launch latency only)
+        cudaError_t ge;
+        if (d.C == 32) ge = lss_launch(k_fwd_gather<4>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
+        else if (d.C == 64) ge = lss_launch(k_fwd_gather<8>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
+        else ge = lss_launch(k_fwd_gather<16>, dim3(grid), dim3(GATHER_THREADS), gsm, s, true, GATHER_ARGS);
+        if (ge != cudaSuccess) return LSS_ERR_CUDA;
 #undef GATHER_ARGS
+        LSS_CHECK_LAUNCH();
+        if (variant == LSS_VARIANT_GROUP_GATHER) return LSS_OK;
     }
-    LSS_CHECK_LAUNCH();
-    if (variant == LSS_VARIANT_GROUP_GATHER) return LSS_OK;
-store:
-    {
-        // persistent bulk-copy variant: measured faster only where a tile is ONE contiguous run (channels_last, nz = 1:
-        // 36.7 vs 38.7 us forward at cfg 2); with one 800-byte bulk copy per channel row (NCHW) it is slower (42.7 us).
-        // LSS_STORE_TMA=1 / 0 forces it on / off.
-        static int tma_mode = getenv("LSS_STORE_TMA") ? atoi(getenv("LSS_STORE_TMA")) : -1;
-        const size_t tma_smem = (size_t)2 * (cl ? tl.TY * d.C : d.C * (tl.TY + 4)) * 4;
-        const bool want = tma_mode < 0 ? (cl && d.nz == 1) : tma_mode > 0;
-        if (want && vec4 && tma_smem <= 227 * 1024 && (cl || tl.nty == 1 || tl.TY % 4 == 0)) {
-            if (tma_mode == 2)      // persistent CTAs with prefetch, ordinary stores (experiment)
-                return cl ? launch_fwd_store_tma<true, false>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false, false>(d, tl, pp, vsum, bev, b0, b1, s);
-            return cl ? launch_fwd_store_tma<true, true>(d, tl, pp, vsum, bev, b0, b1, s) : launch_fwd_store_tma<false, true>(d, tl, pp, vsum, bev, b0, b1, s);
-        }
-    }
+    // persistent bulk-copy variant: measured faster only where a tile is ONE contiguous run (channels_last, nz = 1:
+    // 36.7 vs 38.7 us forward at cfg 2); with one 800-byte bulk copy per channel row (NCHW) it is slower (42.7 us)
+    const size_t tma_smem = (size_t)2 * tl.TY * d.C * 4;
+    if (cl && d.nz == 1 && vec4 && tma_smem <= 227 * 1024) return launch_fwd_store_tma<true>(d, tl, pp, vsum, bev, b0, b1, s);
     const bool pdl = variant != LSS_VARIANT_GROUP_STORE;  // only right behind its gather
     if (cl) return vec4 ? launch_fwd_store<true, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<true, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
-    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s, zsplit) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
+    return vec4 ? launch_fwd_store<false, true>(d, tl, pp, vsum, bev, b0, b1, pdl, s) : launch_fwd_store<false, false>(d, tl, pp, vsum, bev, b0, b1, pdl, s);
 }
 
 template <int VW, int KC, bool DENSE>
@@ -1628,12 +1293,6 @@ static int dispatch_fwd(bool atomic, bool cl, int variant, const Dims &d, const 
 }
 
 static size_t bev_elems(const Dims &d) { return (size_t)d.B * d.nz * d.C * d.nx * d.ny; }
-
-extern "C" int lss_debug_set_timeline(void *store_buf, void *gather_buf) {
-    unsigned long long *p = (unsigned long long *)store_buf, *q = (unsigned long long *)gather_buf;
-    if (cudaMemcpyToSymbol(g_lss_timeline, &p, sizeof(p)) != cudaSuccess) return LSS_ERR_CUDA;
-    return cudaMemcpyToSymbol(g_lss_timeline_gather, &q, sizeof(q)) == cudaSuccess ? LSS_OK : LSS_ERR_CUDA;
-}
 
 extern "C" int lss_bev_clear(const lss_problem *p, float *bev, void *stream) {
     int st = lss_check_problem(p);
@@ -1728,15 +1387,8 @@ template <int VW, int KC, int NCH, bool CL>
 static int launch_gather_one(int grid, size_t smem, cudaStream_t s, const Dims &d, const int32_t *vox, const float *prob,
                              const float *ctx_t, const float *rows, float *grad_dn) {
     auto kern = k_bwd_gather<VW, KC, NCH, CL>;
-    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) {
-        static bool configured = false;
-        if (!configured) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-                return LSS_ERR_CUDA;
-            configured = true;
-        }
-    }
+    const int st = opt_in_smem_dev(kern, smem);
+    if (st != LSS_OK) return st;
     kern<<<grid, SPLAT_THREADS, smem, s>>>(d, vox, prob, ctx_t, rows, grad_dn);
     LSS_CHECK_LAUNCH();
     return LSS_OK;
@@ -1787,9 +1439,9 @@ int lss_bwd_gather_rows(const Dims &d, const int32_t *prow, const float *prob_co
     if (stage_rows) smem += rows_smem;
 #define GPX(CPL)                                                                                                  \
     do {                                                                                                          \
-        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_bwd_gather_px<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) \
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_bwd_gather_px<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) \
             return LSS_ERR_CUDA;                                                                                  \
-        if (lss_launch(k_bwd_gather_px<CPL, false>, grid, dim3(SPLAT_THREADS), smem, s, pdl, d, b0 * d.N, WC, stage_rows, mg, \
+        if (lss_launch(k_bwd_gather_px<CPL>, grid, dim3(SPLAT_THREADS), smem, s, pdl, d, b0 * d.N, WC, stage_rows, mg, \
                        prow, prob_col, ctx_t, rows, grad_dn) != cudaSuccess) return LSS_ERR_CUDA;                 \
     } while (0)
     if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
@@ -1812,14 +1464,7 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
     const size_t rows_smem = (size_t)WC * d.D * d.C * 4 + 16 + (size_t)WC * d.D * 4;  // staged gradient rows (+ alignment, + offsets), if they fit next to a second CTA
     const int stage_rows = smem + rows_smem <= 100 * 1024;
     if (stage_rows) smem += rows_smem;
-    // Experiment (LSS_BWD_DIRECT=1): gradient rows straight from the NCHW tensor inside the gather, no rows kernel.
-    // Measured at cfg 2: 83 us for the fused kernel against 16 + 16 us for the two kernels -- 288 CTAs issuing ~10 k
-    // 4-byte cp.async each have far less memory-level parallelism than the tile-owner rows kernel (1600 CTAs, 8
-    // independent loads per lane): OFF.
-    static int direct_knob = getenv("LSS_BWD_DIRECT") ? atoi(getenv("LSS_BWD_DIRECT")) : 0;
-    const bool direct = direct_knob && !cl && stage_rows && (size_t)d.B * d.nz * d.C * d.nx * d.ny < ((size_t)1 << 31);
-    if (direct && stage == 1) return LSS_OK;              // (stage 1 = the rows kernel alone: nothing to do)
-    if (!direct && stage != 2) {
+    if (stage != 2) {
         const cudaError_t e = cl
             ? lss_launch(k_bwd_rows_compact<true>, dim3((b1 - b0) * tps), dim3(SPLAT_THREADS), 0, s, true, d, tl, b0 * tps,
                          pp.tile_start, pp.tile_nseg, pp.tile_row0, pp.segs, grad_bev, grows)
@@ -1829,23 +1474,7 @@ static int run_bwd_compact(bool cl, const Dims &d, const Tiling &tl, const PlanP
         LSS_CHECK_LAUNCH();
         if (stage == 1) return LSS_OK;
     }
-#define GPX(CPL)                                                                                                 \
-    do {                                                                                                         \
-        static bool configured = false, configured_d = false;                                                    \
-        int st = direct ? opt_in_smem(k_bwd_gather_px<CPL, true>, smem, configured_d)                            \
-                        : opt_in_smem(k_bwd_gather_px<CPL, false>, smem, configured);                            \
-        if (st != LSS_OK) return st;                                                                             \
-        const cudaError_t e = direct                                                                             \
-            ? lss_launch(k_bwd_gather_px<CPL, true>, grid, dim3(SPLAT_THREADS), smem, s, true, d, b0 * d.N, WC, stage_rows, mg, \
-                         pp.vox, prob_col, ctx_t, grad_bev, grad_dn)                                             \
-            : lss_launch(k_bwd_gather_px<CPL, false>, grid, dim3(SPLAT_THREADS), smem, s, stage != 2, d, b0 * d.N, WC, stage_rows, mg, \
-                         prow, prob_col, ctx_t, (const float *)grows, grad_dn);                                  \
-        if (e != cudaSuccess) return LSS_ERR_CUDA;                                                               \
-    } while (0)
-    if (d.C == 32) GPX(4); else if (d.C == 64) GPX(8); else GPX(16);
-#undef GPX
-    LSS_CHECK_LAUNCH();
-    return LSS_OK;
+    return lss_bwd_gather_rows(d, prow, prob_col, ctx_t, grows, grad_dn, b0, b1, stage != 2, s);
 }
 
 extern "C" int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *workspace,

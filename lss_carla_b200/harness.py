@@ -7,6 +7,8 @@ BEV encoder are the PyTorch stand-ins of `trunk.py` (they stay in PyTorch per no
 them is the CUDA path -- or, for the baseline arm, whatever `splat_override` the caller supplies."""
 from __future__ import annotations
 
+import types
+
 import torch
 from torch import nn
 
@@ -29,13 +31,25 @@ def make_train_batch(cfg, B, seed, device):
 
 
 class TrainStep:
+    """`channels_last`: BEV emitted in channels_last strides and BevEncode converted to that memory format (the faster
+    layout end to end on B200, see models.install); `splat_override(model, depthnet_out, *calibration) -> BEV` replaces the
+    lift-splat by something else -- the baseline arm passes the reference's stock ATen op chain here (measurement only: the
+    hook lives in this harness, not in the product's model code)."""
+
     def __init__(self, cfg, device, splat_mode="sorted", inverse_mode="device", splat_override=None, ddp=False,
-                 local_rank=0, seed=0):
+                 local_rank=0, seed=0, channels_last=True):
         torch.manual_seed(seed)                       # same initial weights on every rank (DDP broadcasts anyway)
         self.model = models.LiftSplatShoot(cfg.grid_conf, cfg.data_aug_conf, outC=1, splat_mode=splat_mode,
-                                           inverse_mode=inverse_mode).to(device)
+                                           inverse_mode=inverse_mode, bev_channels_last=channels_last).to(device)
+        if channels_last:
+            self.model.bevencode.to(memory_format=torch.channels_last)
         if splat_override is not None:
-            self.model._splat_override = splat_override
+            def get_voxels(m, x, rots, trans, intrins, post_rots, post_trans):
+                B, N, _, imH, imW = x.shape
+                ce = m.camencode
+                dn = ce.depthnet(ce.dropout(ce.get_eff_depth(x.view(B * N, x.shape[2], imH, imW))))
+                return splat_override(m, dn, rots, trans, intrins, post_rots, post_trans)
+            self.model.get_voxels = types.MethodType(get_voxels, self.model)
         self.net = self.model
         if ddp:
             self.net = nn.parallel.DistributedDataParallel(self.model, device_ids=[local_rank], gradient_as_bucket_view=True)

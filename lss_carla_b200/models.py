@@ -33,9 +33,6 @@ def _fused_get_voxels(self, x, rots, trans, intrins, post_rots, post_trans):
     ce = self.camencode
     feat = ce.get_eff_depth(x.view(B * N, x.shape[2], imH, imW))          # PyTorch trunk (models.py:53)
     dn = ce.depthnet(ce.dropout(feat))                                     # models.py:55-56
-    override = getattr(self, "_splat_override", None)                      # measurement hook: baseline arm of the harness
-    if override is not None:
-        return override(self, dn, rots, trans, intrins, post_rots, post_trans)
     return lift_splat_from_depthnet(self, dn, rots, trans, intrins, post_rots, post_trans)
 
 
@@ -167,6 +164,11 @@ def install(model, splat_mode="sorted", inverse_mode="reference", bev_channels_l
     The instance keeps its class, sub-modules, parameters and state_dict.  `use_quickcumsum` keeps its
     meaning as "which backward derivation" only: both settings run the same kernels (the gather backward
     is exact), so toggling it does not change results.
+
+    `bev_channels_last=False` (default) returns the reference's NCHW-contiguous tensor (tile-plan kernels);
+    `True` returns the same logical tensor in torch.channels_last strides through the sort-free run plan -- the
+    faster path end to end on B200 (cuDNN runs `bevencode.conv1`, models.py:97-98, on NHWC data: BevEncode
+    forward + backward 7.8 ms against 11.6 ms, profiles/r02_conv1_layout.json) and what bench.py measures.
     """
     if inverse_mode not in INVERSE_MODES:
         raise ValueError(f"inverse_mode must be one of {INVERSE_MODES}")

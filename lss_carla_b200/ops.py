@@ -36,6 +36,11 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def set_option(name: str, value: int):
+    """Process-wide library options (lss_set_option): "pdl" = programmatic dependent launch of the kernel chains (default 1)."""
+    check(lib().lss_set_option({"pdl": 0}[name], int(value)), "lss_set_option")
+
+
 def _f32c(t, name):
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: the lift-splat path has no CPU implementation")
@@ -297,7 +302,7 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
               voxel_sums=None, batch_range=(0, 0), precleared=None):
     """`out`: optional output tensor (pre-zeroed, from bev_clear, for mode 'red').  `voxel_sums`: optional
     workspace f32[plan.layout.n_rows_cap, C] of the two-kernel GROUP variant (allocated when omitted).
-    `batch_range` = (b0, b1): only these samples (GROUP variant; see splat_fwd_pipelined)."""
+    `batch_range` = (b0, b1): only these samples (GROUP variant; samples are independent)."""
     if mode == "sorted" and not plan.sorted:
         raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
     bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
@@ -404,6 +409,45 @@ def build_runplan(prob: Problem, frustum, trans, post_trans, M1=None, M2=None, r
     return plan
 
 
+def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None, plan: RunPlan | None = None, frustum=None, trans=None,
+                       post_trans=None, M1=None, M2=None, rots=None, intrins=None, post_rots=None):
+    """Fused prologue of a step in ONE launch (+ classify): zero-fill of `bev` (channels_last; None: off), run plan from the
+    calibration (`plan` and `frustum` given; arguments as build_runplan) and lift operands of `depthnet_out` (float32; None: off)
+    as independent CTA roles of one grid.  Returns (pr, ct) of the lift (or None).  Then: splat_fwd_cl(..., out=bev, precleared=True)."""
+    null = C.c_void_p(0)
+    build = plan is not None and frustum is not None
+    cal = [null] * 8
+    keep = []
+    if build:
+        raw = M1 is None or M2 is None
+        ts = [_f32c(t, n) for t, n in ((frustum, "frustum"), (post_trans, "post_trans"), (trans, "trans"))]
+        mats = [_f32c(t, n) for t, n in ((rots, "rots"), (intrins, "intrins"), (post_rots, "post_rots"))] if raw else \
+               [_f32c(t, n) for t, n in ((M1, "M1"), (M2, "M2"))]
+        keep = [ts, mats]
+        cal = [_ptr(ts[0]), _ptr(ts[1])] + ([null, null, _ptr(ts[2])] + [_ptr(t) for t in mats] if raw else
+                                          [_ptr(mats[0]), _ptr(mats[1]), _ptr(ts[2]), null, null, null])
+    lift_args, res = [null] * 4, None
+    if depthnet_out is not None:
+        x = _f32c(depthnet_out, "depthnet_out")
+        BN, HW = prob.B * prob.N, prob.fH * prob.fW
+        if tuple(x.shape) != (BN, prob.D + prob.C, prob.fH, prob.fW):
+            raise ValueError(f"depthnet_out has shape {tuple(x.shape)}, expected {(BN, prob.D + prob.C, prob.fH, prob.fW)}")
+        both, ct = lift_out if lift_out is not None else (
+            torch.empty((2, BN, prob.D, prob.fH, prob.fW), dtype=torch.float32, device=x.device),
+            torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device))
+        lift_args, res = [_ptr(x), _ptr(both[0]), _ptr(ct), _ptr(both[1])], (both[0], ct)
+        keep.append(x)
+    if bev is not None and not bev.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("liftsplat_prologue zero-fills channels_last tensors only")
+    lay = C.byref(plan.layout) if plan is not None else None
+    check(lib().lss_liftsplat_prologue(C.byref(prob.c), lay, _ptr(plan.ws) if plan is not None else null, *cal, *lift_args,
+                                       _ptr(bev), _stream()), "lss_liftsplat_prologue")
+    if build:
+        plan.built, plan._keepalive = True, keep
+        plan.generation += 1
+    return res
+
+
 def bev_zero(prob: Problem, device, out=None, part=0, n_parts=1):
     """A zeroed channels_last BEV tensor (models.py:240) through the bulk-copy kernel; may be issued on a side stream
     next to the plan build and handed to splat_fwd_cl(..., out=bev, precleared=True).  (part, n_parts): only that slice."""
@@ -435,56 +479,6 @@ def splat_bwd_cl(prob: Problem, plan: RunPlan, grad_bev, pr, ct, prob_col=None, 
         out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
     check(lib().lss_liftsplat_bwd_cl(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(g), _ptr(prob_col), _ptr(ct),
                                      _ptr(out), _stream()), "lss_liftsplat_bwd_cl")
-    return out
-
-
-def _parts(B, n):
-    n = max(1, min(int(n), B))
-    return [(i * B // n, (i + 1) * B // n) for i in range(n)]
-
-
-def splat_fwd_pipelined(prob: Problem, plan: Plan, pr, ct, side, parts=2, channels_last=False, voxel_sums=None, out=None):
-    """Deterministic forward issued in `parts` sample ranges on two streams: the current stream runs the gathers
-    back to back, `side` runs each part's store as soon as its gather is done, so the HBM-bound store of one part
-    overlaps the issue-bound gather of the next.  Same kernels, same bits as splat_fwd(mode="sorted")."""
-    if not plan.sorted or prob.C not in (32, 64, 128):
-        return splat_fwd(prob, plan, pr, ct, "sorted", channels_last, voxel_sums=voxel_sums, out=out)
-    cur = torch.cuda.current_stream()
-    bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
-    if voxel_sums is None:
-        voxel_sums = torch.empty((plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=pr.device)
-    for t in (bev, voxel_sums, pr, ct):
-        t.record_stream(side)
-    for rng in _parts(prob.B, parts):
-        splat_fwd(prob, plan, pr, ct, "sorted", channels_last, variant="group_gather", out=bev, voxel_sums=voxel_sums,
-                  batch_range=rng, precleared=0)
-        side.wait_stream(cur)                       # this part's rows are complete
-        with torch.cuda.stream(side):
-            splat_fwd(prob, plan, pr, ct, "sorted", channels_last, variant="group_store", out=bev, voxel_sums=voxel_sums,
-                      batch_range=rng, precleared=0)
-    cur.wait_stream(side)
-    return bev
-
-
-def splat_bwd_pipelined(prob: Problem, plan: Plan, grad_bev, pr, ct, side, parts=2, grad_rows=None, prob_col=None, out=None):
-    """Backward in `parts` sample ranges on two streams: the DRAM-bound gradient-row gather of one part (current
-    stream) overlaps the pixel gather of the previous part (`side`)."""
-    g, layout = _bev_layout(_f32c_keep(grad_bev))
-    if not plan.sorted or prob.C not in (32, 64, 128) or (prob_col is None and _prob_col(pr) is None):
-        return splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out)
-    cur = torch.cuda.current_stream()
-    if grad_rows is None:
-        grad_rows = torch.empty((max(prob.n_voxels, plan.layout.n_rows_cap), prob.C), dtype=torch.float32, device=g.device)
-    if out is None:
-        out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
-    for t in (g, grad_rows, out, pr, ct):
-        t.record_stream(side)
-    for rng in _parts(prob.B, parts):
-        splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out, stage=1, batch_range=rng)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            splat_bwd(prob, plan, g, pr, ct, grad_rows, prob_col, out, stage=2, batch_range=rng)
-    cur.wait_stream(side)
     return out
 
 

@@ -113,6 +113,24 @@ def main():
         if upto >= 3:
             bwd(s)
 
+    def prologue(s):
+        s.pr, s.ct = ops.liftsplat_prologue(prob, s.dn, s.lift, s.bev, s.rp, fr, s.cal["trans"].reshape(-1, 3), s.cal["post_trans"].reshape(-1, 3),
+                                            rots=s.cal["rots"], intrins=s.cal["intrins"], post_rots=s.cal["post_rots"])
+
+    def prologue_cached(s):      # plan cached: zero + lift only
+        s.pr, s.ct = ops.liftsplat_prologue(prob, s.dn, s.lift, s.bev)
+
+    def fused_step(s, upto=3):
+        prologue(s)
+        if upto >= 2:
+            gather(s)
+        if upto >= 3:
+            bwd(s)
+
+    def fused_fwd_cached(s):
+        prologue_cached(s)
+        gather(s)
+
     def pair(a, b=None, c=None):
         def f(s):
             cur = torch.cuda.current_stream()
@@ -159,14 +177,17 @@ def main():
     for nm, fn in (("plan", plan), ("lift", lift), ("zero", zero), ("gather", gather), ("fwd_serial(zero+gather)", fwd_serial),
                    ("fwd_op(zero||lift->gather)", fwd_op), ("bwd", bwd), ("zero||plan", pair(zero, plan)), ("zero||lift", pair(zero, lift)),
                    ("lift||plan", pair(lift, plan)), ("zero||gather", pair(zero, gather)), ("zero||bwd", pair(zero, bwd)), ("zero_side_only", pair(zero)), ("step_upto_plan", lambda s: step(s, 1)),
-                   ("step_upto_fwd", lambda s: step(s, 2)), ("step", step), ("split_upto_plan", lambda s: step_split(s, 1)),
-                   ("split_step", step_split)):
+                   ("step_upto_fwd", lambda s: step(s, 2)), ("step", step), ("prologue", prologue), ("prologue_cached(zero+lift)", prologue_cached), ("fused_upto_fwd", lambda s: fused_step(s, 2)),
+                   ("fused_fwd_cached", fused_fwd_cached), ("fused_step", fused_step)):
         res[nm + "_us"] = round(timeit(fn), 2)
-    res["mpoints_per_s"] = round(cfg.points / res["step_us"], 1)
+    res["mpoints_per_s"] = round(cfg.points / res["fused_step_us"], 1)
     # timeline of one step in the rotating (L2-cold) regime: globaltimer stamps inside the kernels
     import ctypes as C
     from lss_carla_b200 import _lib
     L = _lib.lib()
+    if not hasattr(L, "lss_debug_runplan_timeline"):          # library built without -DLSS_RP_TIMELINE
+        print(json.dumps(res))
+        return
     L.lss_debug_runplan_timeline.restype = C.c_int
     L.lss_debug_runplan_timeline.argtypes = [C.c_int, C.c_void_p]
     side = torch.cuda.Stream()
@@ -174,7 +195,7 @@ def main():
     for s in sets:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            step(s)
+            fused_step(s)
         graphs.append(g)
     for i in range(12):
         graphs[i % 4].replay()

@@ -42,6 +42,34 @@ def test_struct_sizes_match_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     c_fields = re.findall(r"(?:int32_t|int64_t|size_t)\s+([a-z_0-9]+)\s*;", body)
     assert c_fields == [f[0] for f in _lib.LssPlanLayout._fields_]
+    body = hdr[hdr.index("typedef struct lss_runplan_layout {"):hdr.index("} lss_runplan_layout;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = re.findall(r"(?:int32_t|int64_t|size_t)\s+([a-z_0-9]+)\s*;", body)
+    assert c_fields == [f[0] for f in _lib.LssRunplanLayout._fields_]
+    assert C.sizeof(_lib.LssRunplanLayout) == 8 * len(c_fields)
+
+
+def test_runplan_layout_and_options_host_only(L):
+    cfg = CONFIGS["cfg2"]
+    p = _problem(cfg)
+    lay = _lib.LssRunplanLayout()
+    assert L.lss_runplan_layout_init(C.byref(p.c), C.byref(lay)) == 0
+    assert lay.n_points == cfg.points and lay.n_runs == cfg.points // cfg.fHW[0] and lay.n_voxels == 8 * 200 * 200
+    offs = [getattr(lay, f[0]) for f in _lib.LssRunplanLayout._fields_ if f[0].startswith("off_")]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and offs[-1] < lay.bytes
+    assert lay.bytes - lay.off_counters >= 2 * 4 * lay.n_voxels       # the scratch grids sit at the end (lss_runplan_reset)
+    assert ops.runplan_supported(p)
+    odd = ops.Problem.from_grid(1, 1, 8, 40, 4, 64, *gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound))   # a run must fit a warp
+    assert L.lss_runplan_layout_init(C.byref(odd.c), C.byref(lay)) == -3 and not ops.runplan_supported(odd)
+    c48 = ops.Problem.from_grid(1, 1, 8, 8, 4, 48, *gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound))
+    assert not ops.runplan_supported(c48)
+    # process-wide options: the library's only global state
+    assert L.lss_get_option(0) == 1
+    assert L.lss_set_option(0, 0) == 0 and L.lss_get_option(0) == 0
+    assert L.lss_set_option(0, 1) == 0 and L.lss_set_option(7, 1) == -1
+    null = C.c_void_p(0)
+    assert L.lss_liftsplat_fwd_cl(C.byref(p.c), None, null, null, null, null, 0, null) == -5
+    assert L.lss_bev_zero(C.byref(p.c), null, 0, 1, null) == -1
 
 
 def _problem(cfg):
