@@ -240,7 +240,8 @@ def train_measure(cfg, dev, local, rank, world, per_gpu, steps, warm, mode, inve
         n_par = sum(p.numel() * 4 for p in step.model.parameters() if p.requires_grad)
         out["allreduce_bytes_per_step"] = n_par
         try:
-            sizes = str(step.net._get_ddp_logging_data().get("bucket_sizes", ""))
+            log = step.net._get_ddp_logging_data()
+            sizes = str(log.get("rebuilt_bucket_sizes") or log.get("bucket_sizes", ""))
             out["allreduce_buckets"] = len([s for s in sizes.split(",") if s.strip()]) or None
         except Exception:
             out["allreduce_buckets"] = None

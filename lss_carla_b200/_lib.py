@@ -106,21 +106,24 @@ def nvcc_path():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into lss_carla_b200/liblss_b200.so for sm_100a (cross-compiles without a GPU)."""
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """Compile csrc/*.cu into lss_carla_b200/liblss_b200.so for sm_100a (cross-compiles without a GPU).
+    `out` / `defines`: a second build next to it, e.g. the bounds-checking one of scripts/run_with_asserts.py."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "geom.cuh"), HEADER]
-    if not force and os.path.isfile(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
-        return SO_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", SO_PATH]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "geom.cuh", "lift.cuh")] + [HEADER]
+    target = out or SO_PATH
+    if not force and os.path.isfile(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps):
+        return target
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", target]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    global _lib
-    _lib = None
-    return SO_PATH
+    if target == SO_PATH:
+        global _lib
+        _lib = None
+    return target
 
 
 def lib():

@@ -53,6 +53,16 @@ extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) 
 #define tl_stamp(k, end) ((void)0)
 #endif
 
+// Bounds / invariant checks of the run-plan kernels, compiled in with -DLSS_DEVICE_ASSERTS only (scripts/run_with_asserts.py:
+// compute-sanitizer is closed on this GPU pool, so index ranges, list integrity and capacity limits are checked by the kernels
+// themselves on the small cases; a violated check traps and the next CUDA call fails).
+#ifdef LSS_DEVICE_ASSERTS
+#include <cstdio>
+#define LSS_DASSERT(cond) do { if (!(cond)) { printf("LSS_DASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define LSS_DASSERT(cond) ((void)0)
+#endif
+
 // thread -> point mapping shared by k_run_index and k_run_classify (they must agree on what a sub-run is)
 struct RunDims {
     int fH, RPW;        // runs per warp = 32 / fH
@@ -114,7 +124,9 @@ __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, 
         const unsigned peers = __match_any_sync(LSS_FULL_MASK, row >= 0 ? row : -1 - lane) & q.run_mask;
         if (row >= 0 && lane == __ffs(peers) - 1) {      // sub-run leader: push on the voxel's list, count its points
             const size_t cm = (size_t)q.r * d.fH + q.h;
+            LSS_DASSERT(row < d.B * d.nx * d.ny * d.nz && cm < (size_t)d.n_points);
             const int old = atomicExch(head + row, (int)cm + 1);
+            LSS_DASSERT(old >= 0 && old <= d.n_points && old != (int)cm + 1);
             atomicAdd(cnt + row, __popc(peers));         // result unused: red.global
             sub[cm] = make_int2(old, (int)(peers >> lane));
         }
@@ -163,15 +175,22 @@ k_run_classify(Dims d, RunDims rd, const int32_t *__restrict__ prow, uint32_t *_
                     const int b = row / (d.nx * d.ny * d.nz);
                     if (c >= GCL_SHORT_CAP) {             // long voxel: its point set is written out for the CTA path
                         const int pos = atomicAdd(counters + 1, c);
+                        LSS_DASSERT(pos >= 0 && pos + c <= d.n_points);
                         int i = 0;
                         for (int cur = hd; cur != 0;) {
+                            LSS_DASSERT(cur >= 1 && cur <= d.n_points);
                             const int2 nd = __ldcg(sub + (cur - 1));
+                            LSS_DASSERT(nd.y != 0 && __ldg(prow + (cur - 1)) == row && i + __popc((unsigned)nd.y) <= c);
                             i += expand_subrun(d, rd.fWD, cur - 1, (unsigned)nd.y, pool + pos + i, 0, 1);
                             cur = nd.x;
                         }
+                        LSS_DASSERT(i == c);
                         mixed_recs[n_mixed_cap - 1 - atomicAdd(counters + 2, 1)] = make_int4(pos, c, row, b);
                     } else {
-                        mixed_recs[atomicAdd(counters, 1)] = make_int4(hd, c, row, b);
+                        LSS_DASSERT(c >= 2 && hd >= 1 && hd <= d.n_points && hd != (int)cm + 1);
+                        const int slot = atomicAdd(counters, 1);
+                        LSS_DASSERT(slot + __ldcg(counters + 2) < n_mixed_cap);
+                        mixed_recs[slot] = make_int4(hd, c, row, b);
                     }
                 }
                 head[row] = 0;                            // scratch grids are left clean for the next build: only the
@@ -297,6 +316,7 @@ k_fwd_gather_cl(Dims d, int n_keys, unsigned long long mfH, const int32_t *__res
             int wbase = 0;
             if (lane == 0 && hb) wbase = atomicAdd(&s_n, __popc(hb));
             wbase = __shfl_sync(LSS_FULL_MASK, wbase, 0);
+            LSS_DASSERT(em == 0u || wbase + __popc(hb) <= per);
             if (em != 0u) s_list[wbase + __popc(hb & ((1u << lane) - 1u))] = (unsigned short)i;
         }
         __syncthreads();
@@ -327,6 +347,7 @@ k_fwd_gather_cl(Dims d, int n_keys, unsigned long long mfH, const int32_t *__res
                 }
             }
             if (live) {
+                LSS_DASSERT(s_row[s] >= 0 && s_row[s] < d.B * d.nx * d.ny * d.nz && (m >> (d.fH - h0)) == 0u);
                 float4 *dst = reinterpret_cast<float4 *>(bev + (size_t)s_row[s] * C) + gl;
 #pragma unroll
                 for (int q = 0; q < CPL / 4; ++q) dst[8 * q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
@@ -407,7 +428,9 @@ k_fwd_gather_cl(Dims d, int n_keys, unsigned long long mfH, const int32_t *__res
             while (__any_sync(LSS_FULL_MASK, cur != 0)) {
                 int2 nd = make_int2(0, 0);
                 if (cur != 0) {
+                    LSS_DASSERT(cur >= 1 && cur <= d.n_points);
                     nd = __ldcg(sub + (cur - 1));
+                    LSS_DASSERT(filled + __popc((unsigned)nd.y) <= len && len < GCL_SHORT_CAP);
                     filled += expand_subrun(d, fWD, cur - 1, (unsigned)nd.y, s_un + filled, gl, 8);
                 }
                 cur = nd.x;
@@ -460,6 +483,7 @@ k_fwd_gather_cl(Dims d, int n_keys, unsigned long long mfH, const int32_t *__res
             }
         }
         if (live) {
+            LSS_DASSERT(rec.z >= 0 && rec.z < d.B * d.nx * d.ny * d.nz && rec.w == rec.z / (d.nx * d.ny * d.nz));
             float4 *dst = reinterpret_cast<float4 *>(bev + (size_t)rec.z * C) + gl;
 #pragma unroll
             for (int q = 0; q < CPL / 4; ++q) dst[8 * q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);

@@ -28,6 +28,22 @@ from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, VARIANTS, Lss
 # helpers
 # ------------------------------------------------------------------------------------------------
 
+def _nvtx(name):
+    """NVTX range around a public operator (ranges around geometry / lift / splat for nsys timelines)."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -164,6 +180,7 @@ def calib_matrices_device(rots, intrins, post_rots):
     return M1, M2
 
 
+@_nvtx("lss:geometry")
 def geometry(prob: Problem, frustum, post_trans, M1, M2, trans):
     """get_geometry (models.py:170-190) given prepared matrices -> f32[B,N,D,fH,fW,3]."""
     frustum, post_trans, M1, M2, trans = (_f32c(t, n) for t, n in (
@@ -196,6 +213,7 @@ def voxel_index(prob: Problem, geom=None, calib=None, want=("vox", "idx", "kept"
     return out
 
 
+@_nvtx("lss:plan_build")
 def build_plan(prob: Problem, geom=None, calib=None, sorted: bool = True, plan: Plan | None = None,
                tile_cols: int = 0) -> Plan:
     """Voxel ids + tile buckets (+ in-bucket sort) for one batch; replaces models.py:212-231."""
@@ -213,6 +231,7 @@ def build_plan(prob: Problem, geom=None, calib=None, sorted: bool = True, plan: 
     return plan
 
 
+@_nvtx("lss:plan_build")
 def build_plan_raw(prob: Problem, frustum, rots, trans, intrins, post_rots, post_trans, sorted: bool = True,
                    plan: Plan | None = None, tile_cols: int = 0) -> Plan:
     """build_plan straight from the raw calibration (device inverse mode): the 3x3 inverses are evaluated inside
@@ -245,6 +264,7 @@ def reference_order(plan: Plan):
 # lift + splat
 # ------------------------------------------------------------------------------------------------
 
+@_nvtx("lss:lift_prepare")
 def lift_prepare(prob: Problem, depthnet_out, out=None):
     """softmax over depth + pixel-major context (models.py:49-61) -> (prob [BN,D,fH,fW], ctx_t [BN,HW,C]).
     `out`: optional preallocated (f32[2,BN,D,fH,fW], f32[BN,HW,C]) pair, e.g. when the call runs on a side stream."""
@@ -298,6 +318,7 @@ def bev_clear(prob: Problem, device, channels_last=False):
     return bev
 
 
+@_nvtx("lss:splat_fwd")
 def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=False, variant="auto", out=None,
               voxel_sums=None, batch_range=(0, 0), precleared=None):
     """`out`: optional output tensor (pre-zeroed, from bev_clear, for mode 'red').  `voxel_sums`: optional
@@ -316,6 +337,7 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
     return bev
 
 
+@_nvtx("lss:splat_bwd")
 def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_col=None, out=None, stage=0,
               batch_range=(0, 0)):
     g, layout = _bev_layout(_f32c_keep(grad_bev))
@@ -389,6 +411,7 @@ class RunPlan:
         check(lib().lss_runplan_reset(C.byref(self.layout), _ptr(self.ws), _stream()), "lss_runplan_reset")
 
 
+@_nvtx("lss:runplan_build")
 def build_runplan(prob: Problem, frustum, trans, post_trans, M1=None, M2=None, rots=None, intrins=None, post_rots=None,
                   plan: RunPlan | None = None) -> RunPlan:
     """Run plan of one batch from calibration; replaces models.py:170-190 + :212-231.  With M1 / M2 (the reference's
@@ -409,6 +432,7 @@ def build_runplan(prob: Problem, frustum, trans, post_trans, M1=None, M2=None, r
     return plan
 
 
+@_nvtx("lss:prologue(zero+lift+index)")
 def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None, plan: RunPlan | None = None, frustum=None, trans=None,
                        post_trans=None, M1=None, M2=None, rots=None, intrins=None, post_rots=None):
     """Fused prologue of a step in ONE launch (+ classify): zero-fill of `bev` (channels_last; None: off), run plan from the
@@ -448,6 +472,7 @@ def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None
     return res
 
 
+@_nvtx("lss:bev_zero")
 def bev_zero(prob: Problem, device, out=None, part=0, n_parts=1):
     """A zeroed channels_last BEV tensor (models.py:240) through the bulk-copy kernel; may be issued on a side stream
     next to the plan build and handed to splat_fwd_cl(..., out=bev, precleared=True).  (part, n_parts): only that slice."""
@@ -456,6 +481,7 @@ def bev_zero(prob: Problem, device, out=None, part=0, n_parts=1):
     return bev
 
 
+@_nvtx("lss:splat_fwd_cl")
 def splat_fwd_cl(prob: Problem, plan: RunPlan, pr, ct, out=None, precleared=False):
     """Deterministic forward into a channels_last BEV tensor: same bits as splat_fwd(mode="sorted")."""
     pc = _prob_col(pr)
@@ -469,6 +495,7 @@ def splat_fwd_cl(prob: Problem, plan: RunPlan, pr, ct, out=None, precleared=Fals
     return bev
 
 
+@_nvtx("lss:splat_bwd_cl")
 def splat_bwd_cl(prob: Problem, plan: RunPlan, grad_bev, pr, ct, prob_col=None, out=None):
     g = _f32c_keep(grad_bev)
     if not g.is_contiguous(memory_format=torch.channels_last):
