@@ -319,26 +319,28 @@ class BufferSet:
 
 
 class RunPlanPath:
-    """channels_last, sorted: k_prologue (zero-fill || lift || run index) -> k_run_classify -> k_fwd_gather_cl -> k_bwd_gather_px."""
+    """channels_last, sorted: k_zero_flags || k_prologue (lift || run index) || k_fwd_columns (classify + gather + shared voxels,
+    polling READY and the zero-fill progress) -> k_bwd_gather_px."""
     launches = 4
-    kernels = "k_prologue<raw> (zero-fill + lift + run-index roles), k_run_classify, k_fwd_gather_cl<8>, k_bwd_gather_px<8>"
-    stages = ("prologue+classify", "gather", "backward")
+    kernels = ("k_zero_flags (bulk-copy zero-fill with progress counters), k_prologue<raw> (lift + run-index roles), "
+               "k_fwd_columns<8> (classify + gather + shared voxels), k_bwd_gather_px<8>")
+    stages = ("forward", "backward")
 
     def __init__(self, ops, prob, frustum):
         self.ops, self.prob, self.fr = ops, prob, frustum
 
     def plan_args(self, bs):
-        return dict(plan=bs.plan, frustum=self.fr, trans=bs.trans, post_trans=bs.post_trans, rots=bs.rots, intrins=bs.intrins,
-                    post_rots=bs.post_rots)
+        return dict(frustum=self.fr, trans=bs.trans, post_trans=bs.post_trans, rots=bs.rots, intrins=bs.intrins, post_rots=bs.post_rots)
 
-    def prologue(self, bs):
-        bs.out["pr"], bs.out["ct"] = self.ops.liftsplat_prologue(self.prob, bs.dn, bs.lift_out, bs.bev_out, **self.plan_args(bs))
+    def forward_op(self, bs):            # the whole forward of a step, plan build included (lss_liftsplat_forward): IN + G bytes
+        bs.out["bev"], bs.out["pr"], bs.out["ct"] = self.ops.liftsplat_forward(self.prob, bs.plan, bs.dn, bs.lift_out, bs.bev_out,
+                                                                                **self.plan_args(bs))
 
-    def prologue_cached(self, bs):       # plan already built (static calibration): zero-fill + lift only
-        bs.out["pr"], bs.out["ct"] = self.ops.liftsplat_prologue(self.prob, bs.dn, bs.lift_out, bs.bev_out)
+    def forward_kept_plan(self, bs):     # static calibration: the plan of the previous step is kept
+        bs.out["bev"], bs.out["pr"], bs.out["ct"] = self.ops.liftsplat_forward(self.prob, bs.plan, bs.dn, bs.lift_out, bs.bev_out)
 
     def plan_only(self, bs):
-        self.ops.liftsplat_prologue(self.prob, **self.plan_args(bs))
+        self.ops.build_runplan(self.prob, plan=bs.plan, **self.plan_args(bs))
 
     def zero_only(self, bs):
         self.ops.bev_zero(self.prob, bs.bev_out.device, out=bs.bev_out)
@@ -346,21 +348,21 @@ class RunPlanPath:
     def lift_only(self, bs):
         self.ops.lift_prepare(self.prob, bs.dn, out=bs.lift_out)
 
-    def gather(self, bs):
-        bs.out["bev"] = self.ops.splat_fwd_cl(self.prob, bs.plan, bs.out["pr"], bs.out["ct"], out=bs.bev_out, precleared=True)
+    def prologue_without_zero(self, bs):
+        self.ops.liftsplat_prologue(self.prob, bs.dn, bs.lift_out, None, bs.plan, **self.plan_args(bs))
+
+    def gather(self, bs):                # classify + gather alone, from the existing plan (the tensor is NOT cleared: timing only)
+        self.ops.splat_fwd_cl(self.prob, bs.plan, bs.out["pr"], bs.out["ct"], out=bs.bev_out, precleared=True)
+
+    def gather_with_zero(self, bs):      # the one-launch forward from an existing plan (zero CTAs inside the kernel)
+        self.ops.splat_fwd_cl(self.prob, bs.plan, bs.out["pr"], bs.out["ct"], out=bs.bev_out)
 
     def backward(self, bs):
         bs.out["grad"] = self.ops.splat_bwd_cl(self.prob, bs.plan, bs.grad_bev, bs.out["pr"], bs.out["ct"], out=bs.grad_out)
 
-    def forward_op(self, bs):            # the fused forward with a cached plan: IN + G bytes
-        self.prologue_cached(bs)
-        self.gather(bs)
-
-    def step(self, bs, upto=3):
-        self.prologue(bs)
+    def step(self, bs, upto=2):
+        self.forward_op(bs)
         if upto >= 2:
-            self.gather(bs)
-        if upto >= 3:
             self.backward(bs)
 
 
@@ -605,8 +607,9 @@ def main():
              "backward": time_kernel(path.backward, sets, kiters, stream)}
     if run:
         alone["zero_fill"] = time_kernel(path.zero_only, sets, kiters, stream)
-        alone["prologue(zero+lift+plan)"] = time_kernel(path.prologue, sets, kiters, stream)
-        alone["prologue_cached(zero+lift)"] = time_kernel(path.prologue_cached, sets, kiters, stream)
+        alone["prologue(lift+plan, no zero-fill)"] = time_kernel(path.prologue_without_zero, sets, kiters, stream)
+        alone["forward_kept_plan"] = time_kernel(path.forward_kept_plan, sets, kiters, stream)
+        alone["one_launch_forward_from_plan(zero+classify+gather)"] = time_kernel(path.gather_with_zero, sets, kiters, stream)
 
     IN = 4 * cfg.B * cfg.N * (cfg.D + cfg.C) * fH * fW
     G = 4 * cfg.B * cfg.C * Z * X * Y
@@ -625,7 +628,7 @@ def main():
     except Exception:
         pass
     fwd_s = alone["forward_op"]
-    roof = {"bound": "hbm", "kernel": "fused forward op (lift + zero-fill + gather; plan cached): " + path.kernels.split(", k_bwd")[0],
+    roof = {"bound": "hbm", "kernel": "forward of a step (plan build + lift + zero-fill + classify + gather): " + path.kernels.split(", k_bwd")[0],
             "achieved": round(fwd_bytes / fwd_s / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(fwd_bytes / fwd_s / 1e9 / peak, 4),
             "traffic": traffic, "traffic_per_kernel": traffic_detail, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
             "algorithmic_bytes_per_launch": fwd_bytes, "algorithmic_bytes": "IN + G (SURVEY.md 8d, forward fused)",

@@ -250,66 +250,99 @@ int lss_splat_bwd(const lss_problem *p, const lss_plan_layout *L, const void *wo
  * through cuDNN's NHWC kernels) every voxel is ONE contiguous C-float row, so the forward needs no tile-owner
  * store and the backward no gradient transposition.  The plan shrinks accordingly: points are handled as RUNS --
  * the fH image rows of one (camera, column, depth bin), which almost always share a voxel -- and nothing is sorted:
- *   k_run_index     per point: geometry + voxel row (models.py:179-188, :212-221); per sub-run (the points of a run
- *                   that share a voxel): one push on the voxel's list, size added to the voxel's point count
- *   k_run_classify  a sub-run that is alone on its voxel's list is EXCLUSIVE (summed by its camera-column CTA straight
- *                   from staged operands); the other voxels go to a queue {list head, points, row, batch}
- *   forward         zero-fill (bulk-copy engine, may overlap the plan build) + one gather kernel that writes every
- *                   non-empty voxel row ONCE (exclusive runs: fH staged products in image-row order; shared voxels:
- *                   their points sorted by flat index first) -- the same per-voxel sequential float32 sum in
- *                   ascending flat (b,n,d,h,w) order as LSS_SPLAT_SORTED, hence the same bits
+ *   plan build      per point: geometry + voxel row (models.py:179-188, :212-221); per sub-run (the points of a run
+ *                   that share a voxel): one push on the voxel's list (a 64-bit exchange on head[voxel], tagged with
+ *                   the build's epoch, so that nothing has to be cleared between builds)
+ *   forward         the zero-fill of the tensor (bulk-copy engine, sample by sample, with a progress counter per
+ *                   sample) runs next to the camera-column CTAs, which classify their sub-runs (alone on the voxel's
+ *                   list = EXCLUSIVE: fH staged products in image-row order; otherwise the voxel is queued and a warp
+ *                   at the end of the grid walks its list and sums its few points sorted by flat index), wait for
+ *                   their sample's zeros and write every non-empty voxel row ONCE -- the same per-voxel sequential
+ *                   float32 sum in ascending flat (b,n,d,h,w) order as LSS_SPLAT_SORTED, hence the same bits.  The
+ *                   forward only reads the plan: a plan may be kept and used again while the calibration repeats
  *   backward        the pixel-owner gather reads gradient rows straight from the channels_last gradient
  * voxel "row" r = ((b*nx + ix)*ny + iy)*nz + iz; its C floats start at element r*C of the channels_last tensor. */
 typedef struct lss_runplan_layout {
     int64_t n_points;       /* B*N*D*fH*fW                                                                   */
     int64_t n_runs;         /* B*N*fW*D                                                                      */
     int64_t n_voxels;       /* B*nx*ny*nz                                                                    */
-    int64_t n_mixed_cap;    /* capacity (records) of mixed_recs                                              */
     size_t off_prow;        /* int32 [B,N,fW,D,fH]  voxel row of the point or -1, camera-column major        */
-    size_t off_emask;       /* uint32[B,N,fW,D,fH]  != 0 at the first point of an EXCLUSIVE sub-run: bit j   */
-                            /*                      = image row h+j of the same run belongs to it            */
-    size_t off_sub;         /* int32 [n_points,2]   at the first point of every sub-run: {next sub-run on the voxel's */
-                            /*                      list (point index + 1, 0 = end), row mask}                    */
-    size_t off_pool;        /* uint32[n_points]     point-in-sample indices of the points of LONG voxels (unsorted) */
-    size_t off_mixed_recs;  /* int32 [n_mixed_cap,4] shared voxels {head of the list (point index + 1), points,   */
-                            /*                      voxel row, batch}; voxels with >= 64 points are stored from   */
-                            /*                      the END downwards as {first pool slot, points, row, batch}    */
-    size_t off_counters;    /* int32 [64]           [0] shared voxels < 64 points, [1] pool slots in use, [2] long voxels */
-    size_t off_cnt;         /* int32 [n_voxels]     scratch, all-zero between builds (points per voxel)           */
-    size_t off_head;        /* int32 [n_voxels]     scratch, all-zero between builds (list heads)                 */
+    size_t off_sub;         /* int32 [n_points,2]   at the first point of every sub-run: {the sub-run pushed on the   */
+                            /*                      voxel's list before it (point index + 1, 0 = none), row mask:     */
+                            /*                      bit j = image row h+j of the same run belongs to it}; {0,0} elsewhere */
+    size_t off_sub2;        /* int32 [n_points,2]   per point {context row = pixel (bn*fH + h)*fW + w, flat index in the sample */
+                            /*                      ((n*D + d)*fH + h)*fW + w}: what the sums of shared voxels need        */
+    size_t off_pool;        /* uint32[n_points]     forward scratch: point keys of voxels beyond the shared-memory sort */
+    int64_t n_rec_cap;      /* capacity (records) of recs                                                    */
+    size_t off_recs;        /* int32 [n_rec_cap,4]  forward scratch: queue of the voxels shared by several sub-runs       */
+                            /*                      {head of the voxel's list, voxel row, first pusher, its row mask}     */
+    size_t off_counters;    /* int32 [64]           [0] epoch of the last build; [1..5] scratch, zero between launches;  */
+                            /*                      [6] voxels shared by several sub-runs and [7] voxels with            */
+                            /*                      >= 64 points, as met by the last forward                             */
+    size_t off_zero_done;   /* int32 [B,32]         forward scratch: zero-fill progress per sample ([b][0]; one 128-byte  */
+                            /*                      line each), zero between launches                                    */
+    size_t off_ready;       /* int32 [32,32]        forward scratch: 32 copies ([i][0]) of the "plan + lift operands     */
+                            /*                      complete" flag of lss_liftsplat_forward, zero between launches       */
+    size_t off_head;        /* uint64[n_voxels]     (build epoch << 32) | (point index + 1) of the last sub-run pushed on */
+                            /*                      the voxel's list; entries of older epochs are stale and read as empty */
     size_t bytes;
 } lss_runplan_layout;
 
 /* Fill `out` for problem `p`.  LSS_ERR_UNSUPPORTED if fH > 32 (a run must fit a warp) or C is not 32 / 64 / 128:
  * use the tile plan (lss_plan_build + lss_splat_fwd) for such shapes.  Host-only. */
 int lss_runplan_layout_init(const lss_problem *p, lss_runplan_layout *out);
-/* Zero the scratch grids of a freshly allocated workspace (they clean themselves afterwards). */
+/* Zero the counters and list heads of a freshly allocated workspace (build epochs keep them consistent afterwards;
+ * the epoch is 32 bits wide: reset once more before 2^32 builds into the same workspace). */
 int lss_runplan_reset(const lss_runplan_layout *L, void *workspace, void *stream);
 /* Build the run plan of one batch from calibration (replaces models.py:170-190 + :212-231).  Either the prepared
  * matrices M1 = inverse(post_rots), M2 = rots @ inverse(intrins) are given (bit-exact w.r.t. the reference's host
  * inverses) and rots / intrins / post_rots may be null, or M1 and M2 are null and the closed-form inverses of
  * lss_calib_matrices are evaluated inside the kernel from the raw calibration. */
+/* LSS_OK if lss_runplan_build / lss_liftsplat_prologue take the raw calibration (M1 == M2 == null) for this problem,
+ * LSS_ERR_UNSUPPORTED if the cameras are so small that an index CTA would span too many of them: prepare M1 / M2 with
+ * lss_calib_matrices then.  Host-only. */
+int lss_runplan_raw_supported(const lss_problem *p);
 int lss_runplan_build(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
                       const float *post_trans, const float *M1, const float *M2, const float *trans,
                       const float *rots, const float *intrins, const float *post_rots, void *stream);
-/* Fused prologue of a step, ONE launch (+ the classify launch when a plan is built): the zero-fill of `bev` (may be null:
- * off), the run plan (frustum == null: off, e.g. a cached plan; arguments as lss_runplan_build) and the lift operands
- * (depthnet_out == null: off; outputs as lss_lift_prepare, prob_col required) as independent CTA roles of one grid.  The
- * zero-fill is the only bandwidth-bound piece of the path; the other two are latency chains that finish in its shadow.
- * Afterwards: lss_liftsplat_fwd_cl(..., precleared = 1). */
+/* Fused prologue, ONE launch: the run plan (frustum == null: off, e.g. a kept plan; arguments as lss_runplan_build), the
+ * lift operands (depthnet_out == null: off; outputs as lss_lift_prepare, prob_col required) and, optionally, a zero-fill of
+ * `bev` (null: off) as independent CTA roles of one grid.  Afterwards: lss_liftsplat_fwd_cl(..., LSS_ZERO_PRECLEARED) if `bev`
+ * was given here, LSS_ZERO_ORDERED otherwise.  (The pieces of lss_liftsplat_forward as separate, stream-ordered calls.) */
 int lss_liftsplat_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
                            const float *post_trans, const float *M1, const float *M2, const float *trans,
                            const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
                            float *prob, float *ctx_t, float *prob_col, float *bev, void *stream);
 /* torch.zeros of models.py:240 through the bulk-copy engine (cp.async.bulk shared -> global): one thread per CTA
- * issues the stores, so the kernel leaves the SMs to whatever runs next to it (the plan build, the lift).
- * `part` of `n_parts`: zero only that slice of the tensor (callers chain the slices on a side stream next to the kernels
- * of the plan build); (0, 1) = everything. */
+ * issues the stores, so the kernel leaves the SMs to whatever runs next to it.
+ * `part` of `n_parts`: zero only that slice of the tensor; (0, 1) = everything. */
 int lss_bev_zero(const lss_problem *p, float *bev, int part, int n_parts, void *stream);
-/* Forward: bev (channels_last, `precleared` != 0: already all-zero, else zero-filled here first) receives the sum of
- * every non-empty voxel.  prob_col f32[B*N, fW, D, fH], ctx_t f32[B*N, fH*fW, C] from lss_lift_prepare. */
-int lss_liftsplat_fwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,
-                         const float *prob_col, const float *ctx_t, float *bev, int precleared, void *stream);
+/* Forward from an existing plan and existing lift operands, ONE launch (k_fwd_columns): bev (channels_last) receives the
+ * sum of every non-empty voxel and zeros elsewhere.  prob_col f32[B*N, fW, D, fH], ctx_t f32[B*N, fH*fW, C] from lss_lift_prepare /
+ * lss_liftsplat_prologue.  `zero_mode`:
+ *   LSS_ZERO_ORDERED     the kernel zero-fills `bev` itself: its first CTAs stream the zeros sample by sample, the camera-column
+ *                        CTAs wait for their sample's progress counter before they write
+ *   LSS_ZERO_PRECLEARED  `bev` is already all-zero (lss_bev_zero, the prologue's zero role)
+ * The workspace is scratch for the duration of the launch (progress counters, pool): one forward per plan at a time. */
+enum { LSS_ZERO_ORDERED = 0, LSS_ZERO_PRECLEARED = 1 };
+int lss_liftsplat_fwd_cl(const lss_problem *p, const lss_runplan_layout *L, void *workspace,
+                         const float *prob_col, const float *ctx_t, float *bev, int zero_mode, void *stream);
+/* The whole forward of a step (replaces models.py:170-190, :49-61, :192-246 for one batch) as THREE launches that run
+ * side by side:
+ *   k_zero_flags   zero-fill of `bev` by the bulk-copy engine, sample by sample, one progress counter per sample; two
+ *                  one-warp CTAs per SM, launched first so that they are spread evenly; lets its successors start at once
+ *   k_prologue     lift operands of `depthnet_out` || plan build from the calibration (frustum == null: the plan in the
+ *                  workspace is kept); its last CTA raises READY
+ *   k_fwd_columns  launched programmatically: one CTA per camera column polls READY (not the completion of the grids
+ *                  before it), classifies its sub-runs, sums the exclusive voxels from staged operands, waits for its
+ *                  sample's zeros and writes the rows; the voxels shared by several sub-runs are queued and summed, one
+ *                  warp each, by the CTAs at the end of the same grid
+ * so that the only bandwidth-bound piece (G bytes of zeros) runs from the first microsecond of the step, and the latency
+ * chains next to it.  Arguments as lss_liftsplat_prologue (depthnet_out, prob, ctx_t, prob_col, bev required). */
+int lss_liftsplat_forward(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                          const float *post_trans, const float *M1, const float *M2, const float *trans,
+                          const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
+                          float *prob, float *ctx_t, float *prob_col, float *bev, void *stream);
 /* Backward to the depthnet output from a channels_last BEV gradient (tools.py:212-219 + autograd of models.py:58-59). */
 int lss_liftsplat_bwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,
                          const float *grad_bev, const float *prob_col, const float *ctx_t, float *grad_depthnet,

@@ -15,11 +15,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "liblss_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["plan.cu", "runplan.cu", "lift.cu", "splat.cu", "ops.cu"]
+SOURCES = {"plan.cu": [], "runplan.cu": [], "lift.cu": [], "splat.cu": [], "ops.cu": []}      # source -> extra nvcc flags
 HEADER = os.path.join(_ROOT, "include", "lss_b200.h")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 class LssProblem(C.Structure):
@@ -38,9 +37,9 @@ class LssPlanLayout(C.Structure):
 
 
 class LssRunplanLayout(C.Structure):
-    _fields_ = [("n_points", C.c_int64), ("n_runs", C.c_int64), ("n_voxels", C.c_int64), ("n_mixed_cap", C.c_int64),
-                ("off_prow", C.c_size_t), ("off_emask", C.c_size_t), ("off_sub", C.c_size_t), ("off_pool", C.c_size_t),
-                ("off_mixed_recs", C.c_size_t), ("off_counters", C.c_size_t), ("off_cnt", C.c_size_t),
+    _fields_ = [("n_points", C.c_int64), ("n_runs", C.c_int64), ("n_voxels", C.c_int64),
+                ("off_prow", C.c_size_t), ("off_sub", C.c_size_t), ("off_sub2", C.c_size_t), ("off_pool", C.c_size_t),
+                ("n_rec_cap", C.c_int64), ("off_recs", C.c_size_t), ("off_counters", C.c_size_t), ("off_zero_done", C.c_size_t), ("off_ready", C.c_size_t),
                 ("off_head", C.c_size_t), ("bytes", C.c_size_t)]
 
 
@@ -51,6 +50,7 @@ class LssLimits(C.Structure):
 
 LAYOUT_NCHW, LAYOUT_CHANNELS_LAST = 0, 1
 SPLAT_SORTED, SPLAT_SMEM_ATOMIC, SPLAT_RED_GLOBAL = 0, 1, 2
+ZERO_ORDERED, ZERO_PRECLEARED = 0, 1
 SPLAT_MODES = {"sorted": SPLAT_SORTED, "atomic": SPLAT_SMEM_ATOMIC, "red": SPLAT_RED_GLOBAL}
 VARIANTS = {"auto": 0, "warp": 1, "group": 2, "group_gather": 3, "group_store": 4}
 
@@ -84,10 +84,12 @@ SIGNATURES = {
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
     "lss_runplan_layout_init": (C.c_int, [_PP, _PR]),
     "lss_runplan_reset": (C.c_int, [_PR, _P, _P]),
+    "lss_runplan_raw_supported": (C.c_int, [_PP]),
     "lss_runplan_build": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lss_bev_zero": (C.c_int, [_PP, _P, C.c_int, C.c_int, _P]),
     "lss_liftsplat_prologue": (C.c_int, [_PP, _PR] + [_P] * 15),
     "lss_liftsplat_fwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, C.c_int, _P]),
+    "lss_liftsplat_forward": (C.c_int, [_PP, _PR] + [_P] * 15),
     "lss_liftsplat_bwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -107,19 +109,34 @@ def nvcc_path():
 
 
 def build_library(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
-    """Compile csrc/*.cu into lss_carla_b200/liblss_b200.so for sm_100a (cross-compiles without a GPU).
-    `out` / `defines`: a second build next to it, e.g. the bounds-checking one of scripts/run_with_asserts.py."""
+    """Compile csrc/*.cu into lss_carla_b200/liblss_b200.so for sm_100a (cross-compiles without a GPU): one object per source
+    (in parallel, under build/obj/), then one link.  `out` / `defines`: a second build next to it, e.g. the bounds-checking
+    one of scripts/run_with_asserts.py."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "geom.cuh", "lift.cuh")] + [HEADER]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "geom.cuh", "lift.cuh")] + [HEADER, os.path.abspath(__file__)]
     target = out or SO_PATH
     if not force and os.path.isfile(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps):
         return target
-    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", target]
+    objdir = os.path.join(_ROOT, "build", "obj", os.path.splitext(os.path.basename(target))[0])
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for name, extra in SOURCES.items():
+        obj = os.path.join(objdir, os.path.splitext(name)[0] + ".o")
+        cmd = ([nvcc_path()] + NVCC_FLAGS + extra + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", os.path.join(CSRC, name), "-o", obj])
+        jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for cmd, obj, proc in jobs:
+        log, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + log)
+        if verbose:
+            print(log)
+        objs.append(obj)
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + objs + ["-o", target]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if target == SO_PATH:
         global _lib
         _lib = None

@@ -117,7 +117,7 @@ class LiftSplat:
 
 def _step_fn(ls, prob, x, cal, grad_bev, grad_out, probe_out, dev, tile_cols):
     """The kernels of one forward + backward step on preallocated device buffers (no autograd graph, capturable).
-    channels_last + sorted: fused prologue (zero-fill + lift + run index) -> classify -> gather -> backward gather;
+    channels_last + sorted: prologue (zero-fill || lift || run index) -> classify + gather in its shadow -> backward gather;
     otherwise: tile plan -> lift on a forked branch -> gather + store -> gradient rows + gather."""
     if models._use_runplan(ls, prob):
         rp = ops.RunPlan(prob, dev)
@@ -129,9 +129,8 @@ def _step_fn(ls, prob, x, cal, grad_bev, grad_out, probe_out, dev, tile_cols):
 
         def step():
             rots, trans, intrins, post_rots, post_trans = cal
-            pr, ct = ops.liftsplat_prologue(prob, x, lift_out, bev, rp, ls.frustum, trans.reshape(-1, 3), post_trans.reshape(-1, 3),
-                                            rots=rots, intrins=intrins, post_rots=post_rots)
-            ops.splat_fwd_cl(prob, rp, pr, ct, out=bev, precleared=True)
+            _, pr, ct = ops.liftsplat_forward(prob, rp, x, lift_out, bev, ls.frustum, trans.reshape(-1, 3), post_trans.reshape(-1, 3),
+                                              rots=rots, intrins=intrins, post_rots=post_rots)
             ops.splat_bwd_cl(prob, rp, gb, pr, ct, out=grad_out)
             probe_out.copy_(flat[:probe_out.numel()])
         return step, (rp, bev, lift_out, gb)

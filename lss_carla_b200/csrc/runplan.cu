@@ -2,21 +2,26 @@
 //
 // Replaces, for shdragron/LSS-Carla (paths under the reference root):
 //   LiftSplatShoot.get_geometry                      src/models.py:170-190   (geometry in registers)
-//   voxel_pooling: quantise, mask, rank, argsort     src/models.py:212-231   (no sort: runs + per-voxel counts)
+//   voxel_pooling: quantise, mask, rank, argsort     src/models.py:212-231   (no sort: runs + per-voxel lists)
 //   the lift outer product + QuickCumsum + griddify  src/models.py:59, :234-244, src/tools.py:193-209
 //
 // A RUN is the fH image rows of one (camera, feature column, depth bin): consecutive points of the camera-column-major
 // order cm = ((bn*fW + w)*D + d)*fH + h.  A warp owns 32/fH whole runs, lane = image row.  The points of a run that share
 // a voxel form a SUB-RUN; its first lane is the leader.  With the BEV in channels_last a voxel is one contiguous C-float
 // row, so whoever owns a voxel writes it directly: no tile-owner store pass, no compact rows, and nothing to sort --
-//   k_run_index     voxel row per point (bit-exact arithmetic of geom.cuh) -> prow; every leader pushes its sub-run on the
-//                   voxel's list (one atomicExch: sub[leader] = {previous head, row mask}) and adds its size to cnt[voxel]
-//   k_run_classify  no atomics on the common path, no fences: a leader that pushed FIRST (previous head empty) and is still
-//                   the head owns the whole voxel (EXCLUSIVE, emask[leader] = its row mask); a first pusher that is no
-//                   longer the head appends the voxel to the queue of shared voxels {list head, points, row, batch}
-//   k_fwd_gather_cl one CTA per camera column sums its exclusive sub-runs out of staged operands (8-lane groups, lane =
-//                   C/8 channels); queue CTAs walk the short lists of the shared voxels, sort their few points by flat
-//                   index and sum them from global operands; voxels with >= 64 points are summed by a whole CTA
+//   index role (k_prologue)   voxel row per point (bit-exact arithmetic of geom.cuh) -> prow; every leader pushes its sub-run
+//                   on the voxel's list with ONE 64-bit atomicExch on head[voxel] = {build epoch, leader + 1} and records
+//                   sub[leader] = {previous head of this build (0: it pushed first), row mask}.  Heads of older builds carry
+//                   an older epoch and read as empty: nothing is cleared between builds and the forward only READS the plan.
+//   k_fwd_columns   one CTA per camera column stages its operands, finds its first pushers and looks at their voxels' heads:
+//                   still the head = the sub-run is alone = EXCLUSIVE, summed from the staged operands by an 8-lane group
+//                   (lane = C/8 channels) and written as one voxel row.  Voxels shared by several sub-runs (about 5 %) are
+//                   queued; the CTAs at the END of the same grid take one per warp: walk the short list, sort the few points
+//                   by flat index, fetch weights and context rows in one go, add in key order; >= 64 points: a whole CTA.
+//   zero-fill       cp.async.bulk from a zeroed shared-memory chunk, sample by sample, with a progress counter per sample that
+//                   the writers of voxel rows wait for: as the first CTAs of k_fwd_columns (lss_liftsplat_fwd_cl) or as its own
+//                   small grid in front of prologue and columns (lss_liftsplat_forward: three launches running side by side,
+//                   the columns polling a READY flag instead of waiting for the grids before them to complete).
 // Per voxel the result is acc = 0; for p ascending in flat (b,n,d,h,w) index: acc = fl32(acc + fl32(prob[p]*ctx[p])) --
 // the definition of LSS_SPLAT_SORTED (the reference's stable argsort order), bit for bit.
 #include "common.cuh"
@@ -32,9 +37,9 @@
 #define GCL_SORT_CAP 1024          // long voxels up to this many points are sorted in shared memory
 
 // Profiling aid, compiled in with -DLSS_RP_TIMELINE only (scripts/bench_runplan_quick.py): earliest start / latest end
-// (globaltimer ns) of the zero role (0), the index role (1), k_run_classify (2) and the column CTAs of the gather (3).
+// (globaltimer ns) of the zero CTAs (0), the index role (1), the lift role (2), the column CTAs (3) and k_fwd_shared (4).
 #ifdef LSS_RP_TIMELINE
-__device__ unsigned long long g_rp_tl[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+__device__ unsigned long long g_rp_tl[10] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
 __device__ int g_rp_tl_on = 0;
 __device__ __forceinline__ void tl_stamp(int k, bool end) {
     if (!g_rp_tl_on || threadIdx.x != 0) return;
@@ -42,15 +47,27 @@ __device__ __forceinline__ void tl_stamp(int k, bool end) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     if (end) atomicMax(g_rp_tl + 2 * k + 1, t); else atomicMin(g_rp_tl + 2 * k, t);
 }
+#define TL_MARKS 8
+__device__ unsigned long long g_rp_marks[4096 * TL_MARKS];
+__device__ __forceinline__ void tl_mark(int cta, int phase) {      // per-CTA phase stamps of the forward's column CTAs
+    if (!g_rp_tl_on || threadIdx.x != 0 || cta >= 4096) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_rp_marks[cta * TL_MARKS + phase] = t;
+}
+extern "C" int lss_debug_runplan_marks(unsigned long long *out_host, int n_cta) {
+    return cudaMemcpyFromSymbol(out_host, g_rp_marks, sizeof(unsigned long long) * TL_MARKS * n_cta) == cudaSuccess ? 0 : -4;
+}
 extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) {
-    unsigned long long h[8];
-    if (out_host) { if (cudaMemcpyFromSymbol(h, g_rp_tl, sizeof(h)) != cudaSuccess) return -4; for (int i = 0; i < 8; ++i) out_host[i] = h[i]; }
-    const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+    unsigned long long h[10];
+    if (out_host) { if (cudaMemcpyFromSymbol(h, g_rp_tl, sizeof(h)) != cudaSuccess) return -4; for (int i = 0; i < 10; ++i) out_host[i] = h[i]; }
+    const unsigned long long init[10] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
     if (cudaMemcpyToSymbol(g_rp_tl, init, sizeof(init)) != cudaSuccess) return -4;
     return cudaMemcpyToSymbol(g_rp_tl_on, &on, sizeof(on)) == cudaSuccess ? 0 : -4;
 }
 #else
 #define tl_stamp(k, end) ((void)0)
+#define tl_mark(cta, phase) ((void)0)
 #endif
 
 // Bounds / invariant checks of the run-plan kernels, compiled in with -DLSS_DEVICE_ASSERTS only (scripts/run_with_asserts.py:
@@ -63,7 +80,20 @@ extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) 
 #define LSS_DASSERT(cond) ((void)0)
 #endif
 
-// thread -> point mapping shared by k_run_index and k_run_classify (they must agree on what a sub-run is)
+// counters[] of the workspace (int32[64])
+#define RPC_EPOCH 0        // epoch of the last completed build (the plan the forward reads)
+#define RPC_PRO_DONE 1     // lift / index CTAs of the running prologue that have finished (the last one publishes epoch + READY)
+#define RPC_FWD_DONE 2     // shared-voxel CTAs of the running forward that have finished (the last one sums the long voxels and resets the scratch)
+#define RPC_POOL 3         // pool cursor of the running forward
+#define RPC_NREC 4         // shared voxels queued by the column CTAs of the running forward
+#define RPC_NLONG 5        // ... of which k_fwd_shared found >= 64 points (re-queued from the end of the record array)
+#define RPC_STAT 6         // [6], [7]: shared / long voxels of the last completed forward
+#define RPC_PUB 9          // column CTAs of the running forward that have queued their shared voxels
+#define RP_FLAG_STRIDE 32  // ints between two polled flags: every flag has its own 128-byte line (and L2 slice)
+#define RP_READY_LINES 32  // copies of READY (lss_liftsplat_forward: 1 once the plan and the lift operands of the step are
+                           // complete); column CTA i polls copy i % 32, so that a thousand pollers do not queue on one L2 line
+
+// thread -> point mapping of the index pass
 struct RunDims {
     int fH, RPW;        // runs per warp = 32 / fH
     int R;              // runs = B*N*fW*D
@@ -86,28 +116,31 @@ __device__ __forceinline__ RunLane run_lane(const RunDims &rd, int cta, int u) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// plan kernels
+// plan kernel
 // ------------------------------------------------------------------------------------------------
 
-// The work of one CTA of the index pass (RP_THREADS threads); `cta` in [0, ceil(R / runs per CTA)).
+// The work of one CTA of the index pass (RP_THREADS threads); `cta` in [0, n_index).
 template <bool RAW>
 __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, const CalibPtrs &c, int32_t *__restrict__ prow,
-                                              int32_t *__restrict__ cnt, int32_t *__restrict__ head, int2 *__restrict__ sub,
-                                              int32_t *__restrict__ counters, int cta) {
+                                              unsigned long long *__restrict__ head, int2 *__restrict__ sub, int2 *__restrict__ sub2,
+                                              const int32_t *__restrict__ counters, int cta) {
     tl_stamp(1, false);
-    if (cta == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
+    __shared__ unsigned s_epoch;
     const int cam0 = (int)(((long long)cta * RP_WARPS * RP_U * rd.RPW) / rd.fWD);
+    if (threadIdx.x == 32) s_epoch = (unsigned)__ldcg(counters + RPC_EPOCH) + 1u;     // this build's epoch (published by prologue_cta_done)
     if (RAW) {      // the calibration matrices of the few cameras this CTA touches, made on the fly (no extra launch)
         const int cam = cam0 + (int)threadIdx.x;
         if (threadIdx.x < LSS_RAW_CAMS && cam < d.B * d.N) calib_matrices_of(c.rots, c.intrins, c.post_rots, cam, s_m[threadIdx.x], s_m[threadIdx.x] + 9);
-        __syncthreads();
     }
+    __syncthreads();
+    const unsigned long long tag = (unsigned long long)s_epoch << 32;
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int u = 0; u < RP_U; ++u) {
         const RunLane q = run_lane(rd, cta, u);
         int row = -1;
+        const size_t cm = (size_t)q.r * d.fH + q.h;
         if (q.valid) {
             const int bn = q.r / rd.fWD, rem = q.r - bn * rd.fWD;
             const int w = rem / d.D, dd = rem - w * d.D;
@@ -119,252 +152,363 @@ __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, 
             const int b = bn / d.N;
             if (voxel_of_point(d, b, g, ii) >= 0)
                 row = ((b * d.nx + (int)ii[0]) * d.ny + (int)ii[1]) * d.nz + (int)ii[2];
-            prow[(size_t)q.r * d.fH + q.h] = row;
+            prow[cm] = row;
+            sub2[cm] = make_int2(bn * d.HW + q.h * d.fW + w, (bn - b * d.N) * d.DHW + in_cam);      // {pixel = context row, flat index in the sample}
         }
         const unsigned peers = __match_any_sync(LSS_FULL_MASK, row >= 0 ? row : -1 - lane) & q.run_mask;
-        if (row >= 0 && lane == __ffs(peers) - 1) {      // sub-run leader: push on the voxel's list, count its points
-            const size_t cm = (size_t)q.r * d.fH + q.h;
+        int2 node = make_int2(0, 0);
+        if (row >= 0 && lane == __ffs(peers) - 1) {      // sub-run leader: push on the voxel's list
             LSS_DASSERT(row < d.B * d.nx * d.ny * d.nz && cm < (size_t)d.n_points);
-            const int old = atomicExch(head + row, (int)cm + 1);
-            LSS_DASSERT(old >= 0 && old <= d.n_points && old != (int)cm + 1);
-            atomicAdd(cnt + row, __popc(peers));         // result unused: red.global
-            sub[cm] = make_int2(old, (int)(peers >> lane));
+            const unsigned long long old = atomicExch(head + row, tag | (unsigned long long)(cm + 1));
+            const int prev = (old >> 32) == (tag >> 32) ? (int)(unsigned)old : 0;      // heads of older builds read as empty
+            LSS_DASSERT(prev >= 0 && prev <= d.n_points && prev != (int)cm + 1);
+            node = make_int2(prev, (int)(peers >> lane));
         }
+        if (q.valid) sub[cm] = node;                      // {0, 0} wherever no sub-run starts
     }
     tl_stamp(1, true);
 }
 
-// Expand a sub-run (leader `cm` in camera-column-major order incl. the batch part, row mask relative to the leader) into
-// the point-in-sample flat indices ((n*D + d)*fH + h)*fW + w of its points.  `nl` (a power of two) lanes cooperate: lane
-// `jl` writes points jl, jl+nl, ...  Returns the number of points.
-__device__ __forceinline__ int expand_subrun(const Dims &d, int fWD, int cm, unsigned mask, uint32_t *out, int jl, int nl) {
-    const int r = cm / d.fH, h0 = cm - r * d.fH;
-    const int bn = r / fWD, rem = r - bn * fWD;
-    const int w = rem / d.D, dd = rem - w * d.D;
-    const int n = bn % d.N;
-    const unsigned base = (unsigned)((n * d.D + dd) * d.fH + h0) * (unsigned)d.fW + (unsigned)w;
+// Expand a sub-run into the flat point-in-sample indices ((n*D + d)*fH + h)*fW + w of its points, given the flat index `key0`
+// of its leader and its row mask (bit j = image row h0 + j): point j goes to out[at + j] if that is below `cap`.
+__device__ __forceinline__ int expand_keys(unsigned key0, unsigned mask, int fW, uint32_t *out, int at, int cap) {
     int j = 0;
     for (unsigned m = mask; m; m &= m - 1, ++j)
-        if ((j & (nl - 1)) == jl) out[j] = base + (unsigned)(__ffs(m) - 1) * (unsigned)d.fW;
+        if (at + j < cap) out[at + j] = key0 + (unsigned)(__ffs(m) - 1) * (unsigned)fW;
     return j;
-}
-
-__global__ void __launch_bounds__(RP_THREADS)
-k_run_classify(Dims d, RunDims rd, const int32_t *__restrict__ prow, uint32_t *__restrict__ emask, int32_t *__restrict__ cnt,
-               int32_t *__restrict__ head, const int2 *__restrict__ sub, uint32_t *__restrict__ pool,
-               int4 *__restrict__ mixed_recs, int32_t *__restrict__ counters, long long n_mixed_cap) {
-    lss_pdl_trigger();
-    lss_pdl_wait();                                       // prow, cnt, head, sub and the cleared counters come from k_run_index
-    tl_stamp(2, false);
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int u = 0; u < RP_U; ++u) {
-        const RunLane q = run_lane(rd, (int)blockIdx.x, u);
-        const size_t cm = (size_t)q.r * d.fH + q.h;
-        const int row = q.valid ? __ldg(prow + cm) : -1;
-        const unsigned peers = __match_any_sync(LSS_FULL_MASK, row >= 0 ? row : -1 - lane) & q.run_mask;
-        unsigned em = 0u;
-        if (row >= 0 && lane == __ffs(peers) - 1) {
-            const int2 node = __ldcg(sub + cm);            // {previous head of the voxel's list, row mask}
-            if (node.x == 0) {                            // this sub-run pushed first: it answers for the voxel
-                const int hd = __ldcg(head + row);
-                if (hd == (int)cm + 1) {                  // ... and nobody pushed after it: the voxel is this sub-run alone
-                    em = (unsigned)node.y;
-                } else {                                  // shared voxel: one queue record, made by the tail of its list
-                    const int c = __ldcg(cnt + row);
-                    const int b = row / (d.nx * d.ny * d.nz);
-                    if (c >= GCL_SHORT_CAP) {             // long voxel: its point set is written out for the CTA path
-                        const int pos = atomicAdd(counters + 1, c);
-                        LSS_DASSERT(pos >= 0 && pos + c <= d.n_points);
-                        int i = 0;
-                        for (int cur = hd; cur != 0;) {
-                            LSS_DASSERT(cur >= 1 && cur <= d.n_points);
-                            const int2 nd = __ldcg(sub + (cur - 1));
-                            LSS_DASSERT(nd.y != 0 && __ldg(prow + (cur - 1)) == row && i + __popc((unsigned)nd.y) <= c);
-                            i += expand_subrun(d, rd.fWD, cur - 1, (unsigned)nd.y, pool + pos + i, 0, 1);
-                            cur = nd.x;
-                        }
-                        LSS_DASSERT(i == c);
-                        mixed_recs[n_mixed_cap - 1 - atomicAdd(counters + 2, 1)] = make_int4(pos, c, row, b);
-                    } else {
-                        LSS_DASSERT(c >= 2 && hd >= 1 && hd <= d.n_points && hd != (int)cm + 1);
-                        const int slot = atomicAdd(counters, 1);
-                        LSS_DASSERT(slot + __ldcg(counters + 2) < n_mixed_cap);
-                        mixed_recs[slot] = make_int4(hd, c, row, b);
-                    }
-                }
-                head[row] = 0;                            // scratch grids are left clean for the next build: only the
-                cnt[row] = 0;                             // first pusher of a voxel reads them here
-            }
-        }
-        if (q.valid) emask[cm] = em;
-    }
-    tl_stamp(2, true);
 }
 
 // ------------------------------------------------------------------------------------------------
 // zero-fill through the bulk-copy engine
 // ------------------------------------------------------------------------------------------------
 
-// Zero role of one CTA: thread 0 streams its share of [dst, dst + bytes) out of a zeroed shared-memory chunk with bulk copies
+// Zero role of one CTA: thread 0 streams its share of the tensor out of a zeroed shared-memory chunk with bulk copies
 // (cp.async.bulk shared -> global: the copies need no registers and no issue slots, the source is read-only, so all of them
-// stay in flight).  With `evict_first` the lines are marked evict-first in L2: 82 MB of zeros should not push the plan and the
-// lift operands, which the gather is about to read, out of the cache.
+// stay in flight).  The lines are marked evict-first in L2: 82 MB of zeros should not push the plan and the lift operands,
+// which the gather reads, out of the cache.
 #define ZERO_CHUNK (16 * 1024)
-__device__ __forceinline__ void zero_role(float *__restrict__ dst, size_t bytes, int cta, int n_cta, float *s_zero, int evict_first) {
-    tl_stamp(0, false);
+#define ZERO_DEPTH 3               // segments whose copies may be in flight behind the one being issued
+
+__device__ __forceinline__ void zero_smem_init(float *s_zero) {
     for (int i = threadIdx.x; i < ZERO_CHUNK / 16; i += blockDim.x) reinterpret_cast<float4 *>(s_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy
     __syncthreads();
-    if (threadIdx.x != 0) return;
+}
+
+__device__ __forceinline__ void zero_issue(char *dst, size_t bytes, int cta, int n_cta, unsigned src, unsigned long long pol) {
     const size_t n_chunks = (bytes + ZERO_CHUNK - 1) / ZERO_CHUNK;
-    const unsigned src = (unsigned)__cvta_generic_to_shared(s_zero);
-    unsigned long long pol = 0;
-    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     for (size_t ch = cta; ch < n_chunks; ch += n_cta) {
         const size_t off = ch * ZERO_CHUNK;
         const unsigned sz = (unsigned)min((size_t)ZERO_CHUNK, bytes - off);
-        if (evict_first)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                         :: "l"(reinterpret_cast<char *>(dst) + off), "r"(src), "r"(sz), "l"(pol) : "memory");
-        else
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                         :: "l"(reinterpret_cast<char *>(dst) + off), "r"(src), "r"(sz) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(dst + off), "r"(src), "r"(sz), "l"(pol) : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// whole tensor, no progress flags (k_prologue, lss_bev_zero)
+__device__ __forceinline__ void zero_role(float *__restrict__ dst, size_t bytes, int cta, int n_cta, float *s_zero) {
+    tl_stamp(0, false);
+    zero_smem_init(s_zero);
+    if (threadIdx.x != 0) return;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    zero_issue(reinterpret_cast<char *>(dst), bytes, cta, n_cta, (unsigned)__cvta_generic_to_shared(s_zero), pol);
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tl_stamp(0, true);
 }
 
+__device__ __forceinline__ int ld_acquire(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Poll until *p >= target.  The producers are CTAs that are already running (zero CTAs of this or of the preceding grid, the
+// prologue's last CTA), so the wait is bounded by their work; after 2 s something is wrong with the calling sequence (e.g.
+// lss_liftsplat_fwd_cl on a workspace whose counters were overwritten) and the kernel traps instead of hanging the GPU.
+__device__ __forceinline__ void spin_until(const int32_t *p, int target, unsigned sleep_ns) {
+    if (ld_acquire(p) >= target) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire(p) < target) {
+        __nanosleep(sleep_ns);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 2000000000ull) __trap();
+    }
+}
+
+// The zeros of segment `seg` issued by this CTA have landed: make them visible device-wide, then count the CTA in.
+__device__ __forceinline__ void zero_publish(int32_t *zero_done, int seg) {
+    asm volatile("fence.proxy.async;" ::: "memory");      // async-proxy writes before the generic-proxy release below
+    __threadfence();
+    atomicAdd(zero_done + seg * RP_FLAG_STRIDE, 1);
+}
+
+// Segment by segment (one segment = the BEV slab of one sample) with a progress counter per segment: the column CTAs of
+// sample b write their voxel rows as soon as zero_done[b] == n_cta, while the zeros of the later samples are still in flight.
+// The chunk a CTA starts with rotates from segment to segment, so that every CTA issues the same number of chunks (+-1).
+// At most `window` chunks of `chunk` bytes are in flight per CTA: the copies of all CTAs together should cover the
+// bandwidth-delay product of the memory system and no more -- a deeper queue of zeros only delays the loads and atomics of
+// the latency-bound CTAs that run next to the zero-fill.
+__device__ __forceinline__ void zero_wait(int pending_allowed) {
+    switch (pending_allowed) {
+        case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+    }
+}
+
+__device__ __forceinline__ void zero_role_segments(float *__restrict__ dst, size_t seg_bytes, int n_seg, int cta, int n_cta, float *s_zero,
+                                                   int32_t *__restrict__ zero_done, int chunk, int window) {
+    tl_stamp(0, false);
+    zero_smem_init(s_zero);
+    if (threadIdx.x != 0) return;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    const unsigned src = (unsigned)__cvta_generic_to_shared(s_zero);
+    const size_t cps = (seg_bytes + chunk - 1) / chunk;   // chunks per segment
+    const int rot = (int)(cps % (size_t)n_cta);           // chunks of the last, partial round
+    const int pend = window > 4 ? 7 : window - 1;         // groups that may stay pending behind the newest one
+    int first = cta, issued = 0, pub = 0;                 // pub: next segment to publish
+    int end_at[8];                                        // chunks issued up to the end of segment s, ring over s & 7 (every
+                                                          // segment holds a chunk of this CTA, so at most pend + 1 <= 8 are open)
+    for (int sgm = 0; sgm < n_seg; ++sgm) {
+        char *base = reinterpret_cast<char *>(dst) + (size_t)sgm * seg_bytes;
+        for (size_t ch = first; ch < cps; ch += n_cta) {
+            const size_t off = ch * chunk;
+            const unsigned sz = (unsigned)min((size_t)chunk, seg_bytes - off);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         :: "l"(base + off), "r"(src), "r"(sz), "l"(pol) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++issued;
+            zero_wait(pend);                              // the first issued - pend chunks are down
+            while (pub < sgm && end_at[pub & 7] <= issued - pend) zero_publish(zero_done, pub++);
+        }
+        end_at[sgm & 7] = issued;
+        while (pub <= sgm && end_at[pub & 7] <= issued - pend) zero_publish(zero_done, pub++);
+        first -= rot;                                     // the CTAs right behind those of the partial round take the next one
+        if (first < 0) first += n_cta;
+    }
+    zero_wait(0);
+    while (pub < n_seg) zero_publish(zero_done, pub++);
+    tl_stamp(0, true);
+}
+
 // Fused prologue of a step: ONE launch whose CTAs take one of three independent roles --
-//   [0, n_zero)                    zero-fill of the BEV tensor (models.py:240), the only bandwidth-bound piece of the path
+//   [0, n_zero)                    zero-fill of the BEV tensor (models.py:240) for lss_liftsplat_prologue(bev) (lss_liftsplat_forward
+//                                  zero-fills with k_zero_flags)
 //   [n_zero, n_zero + n_lift)      lift operands: depth softmax + pixel-major context (models.py:49-61)
 //   [.., + n_index)                run index: geometry + voxel rows + list pushes (models.py:170-190, :212-221)
 // (measured at cfg 2: lift before index 61.0 us per step, index before lift 63.1 -- the grid is a little more than one wave)
-// The index and lift roles are chains of memory latencies that would otherwise queue behind the zero-fill on other streams
-// (measured: on separate graph branches each of them ends when the zero-fill ends, plus ~10 us of fork / join overhead);
-// inside one grid they share the SMs with the zero role's single issuing thread and finish within its shadow.
+// The last lift / index CTA to finish publishes the build's epoch and, with `ready`, READY = 1 for the column CTAs of
+// k_fwd_columns, which are launched programmatically behind this grid and poll the flag.
 struct PrologueArgs {
-    float *bev; size_t bev_bytes; int n_zero, evict_first;            // zero role (n_zero = 0: off)
+    float *bev; size_t bev_bytes; int n_zero;                         // zero role (n_zero = 0: off)
     int n_index; RunDims rd; CalibPtrs c;                             // index role (n_index = 0: off)
-    int32_t *prow, *cnt, *head, *counters; int2 *sub;
+    int32_t *prow, *counters; unsigned long long *head; int2 *sub, *sub2;
     int n_lift; const float *dn; float *prob, *ctx_t, *prob_col;      // lift role (n_lift = 0: off)
+    int32_t *ready;                                                   // != null: raise READY when lift + index are complete
 };
 
+__device__ __forceinline__ void prologue_cta_done(const PrologueArgs &a) {
+    if (a.counters == nullptr) return;
+    __syncthreads();                                      // the CTA's writes are done ...
+    if (threadIdx.x != 0) return;
+    __threadfence();                                      // ... and ordered before the count
+    if (atomicAdd(a.counters + RPC_PRO_DONE, 1) != a.n_index + a.n_lift - 1) return;
+    __threadfence();
+    a.counters[RPC_PRO_DONE] = 0;
+    if (a.n_index) a.counters[RPC_EPOCH] += 1;            // every index CTA has read the old epoch
+    if (a.ready) {
+        __threadfence();
+        for (int i = 0; i < RP_READY_LINES; ++i) atomicExch(a.ready + i * RP_FLAG_STRIDE, 1);
+    }
+}
+
 template <bool RAW>
-__global__ void __launch_bounds__(RP_THREADS)
+__global__ void __launch_bounds__(RP_THREADS, 2048 / RP_THREADS)      // 32 registers: 8 CTAs per SM
 k_prologue(Dims d, PrologueArgs a) {
     extern __shared__ __align__(128) float s_pro[];
-    lss_pdl_trigger();                                    // k_run_classify may be scheduled while this grid drains
+    lss_pdl_trigger();                                    // k_fwd_columns may be scheduled while this grid runs
     int cta = (int)blockIdx.x;
-    if (cta < a.n_zero) { zero_role(a.bev, a.bev_bytes, cta, a.n_zero, s_pro, a.evict_first); return; }
+    if (cta < a.n_zero) { zero_role(a.bev, a.bev_bytes, cta, a.n_zero, s_pro); return; }
     cta -= a.n_zero;
-    if (cta < a.n_lift) { lift_prepare_cta<float>(d, a.dn, a.prob, a.ctx_t, a.prob_col, cta, s_pro); return; }
-    cta -= a.n_lift;
-    run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.cnt, a.head, a.sub, a.counters, cta);
+    if (cta < a.n_lift) {
+        tl_stamp(2, false);
+        lift_prepare_cta<float>(d, a.dn, a.prob, a.ctx_t, a.prob_col, cta, s_pro);
+        tl_stamp(2, true);
+    } else {
+        run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.head, a.sub, a.sub2, a.counters, cta - a.n_lift);
+    }
+    prologue_cta_done(a);
+}
+
+// The zero-fill of lss_liftsplat_forward: one warp per CTA, two CTAs per SM, launched FIRST so that they are spread evenly over
+// the SMs (a grid that is launched programmatically into a busy GPU gets its CTAs wherever room appears; several zero CTAs on
+// one SM make its bulk-copy engine the bottleneck: 57 us instead of 15 measured).  It lets its successors start at once.
+__global__ void __launch_bounds__(32)
+k_zero_flags(float *bev, size_t seg_bytes, int n_seg, int32_t *zero_done, int chunk, int window) {
+    extern __shared__ __align__(128) float s_z[];
+    lss_pdl_trigger();
+    zero_role_segments(bev, seg_bytes, n_seg, (int)blockIdx.x, (int)gridDim.x, s_z, zero_done, chunk, window);
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward gather
+// forward: zero-fill + classify + gather in one launch
 // ------------------------------------------------------------------------------------------------
 
+struct FwdArgs {
+    int n_zero, z_chunk, z_window;   // zero CTAs of the column grid (LSS_ZERO_ORDERED), their chunk size and window
+    int zero_target;                 // a sample's slab is clear when zero_done[b] reaches this (0: pre-cleared, no waiting)
+    int wait_ready;                  // lss_liftsplat_forward: poll READY instead of waiting for the preceding grid to complete
+    size_t seg_bytes;                // bytes of one sample's BEV slab
+    int32_t *zero_done, *ready;      // [B][32], [32][32]
+    int n_keys, fWD, n_cons;         // camera columns B*N*fW; fW*D; shared-voxel CTAs at the end of the grid
+    unsigned long long mfH;
+    const int32_t *prow; const int2 *sub, *sub2; const unsigned long long *head;
+    int32_t *counters; uint32_t *pool;
+    int4 *recs; long long n_rec_cap; // queue of shared voxels {list head, voxel row, first pusher (both: point index + 1), its row mask}
+    const float *prob_col, *ctx_t; float *bev;
+};
+
+
+#define GCL_ROWS 16                // context rows a warp has in flight for a shared voxel (cp.async into shared memory)
+
+// fl32(acc + fl32(w * v)) on two channels: scalar products, ONE packed add (sm_100 FADD2) -- the same two roundings per channel
+// as __fmul_rn + __fadd_rn with three instructions instead of four.  A packed product feeding the packed add (__fmul2_rn into
+// __fadd2_rn, or mul.rn.f32x2 into add.rn.f32x2 in PTX, with or without --fmad=false) is contracted by ptxas 12.9 into one
+// FFMA2, i.e. a fused multiply-add with a single rounding (measured: 1-ulp differences against the sequential definition;
+// profiles/r02_sass_excerpt.txt); FMUL + FADD2 is not.
+__device__ __forceinline__ void mul_add2(float &a0, float &a1, float w, float v0, float v1) {
+    const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(__fmul_rn(w, v0), __fmul_rn(w, v1)));
+    a0 = r.x; a1 = r.y;
+}
+
+// Shared voxels (several sub-runs on the voxel's list, about 5 % of the voxels: neighbouring columns at close range, the
+// overlap of neighbouring cameras), spread evenly over the last `n_cons` CTAs of the forward grid: one warp per voxel.  The
+// warp walks the voxel's short list from its head to the first pusher (known from the queue record: no load for the tail),
+// lane j takes point j of a node; it rank-sorts the few keys by flat point index, fetches the weights (lane = point) and up to
+// GCL_ROWS context rows at once (cp.async: all of them in flight, no registers), then adds the products in key order, lane =
+// C/32 channels: the same sequence of float32 operations per channel as everywhere else.  Voxels with >= 64 points are
+// re-queued and summed, one at a time, by the last of these CTAs to finish, which also leaves the scratch of the forward clean.
 template <int CPL>
-__global__ void __launch_bounds__(GCL_THREADS, 1024 / GCL_THREADS)
-k_fwd_gather_cl(Dims d, int n_keys, unsigned long long mfH, const int32_t *__restrict__ prow, const uint32_t *__restrict__ emask,
-                const int32_t *__restrict__ counters, const int4 *__restrict__ mixed_recs, long long n_mixed_cap,
-                uint32_t *__restrict__ pool, const int2 *__restrict__ sub, int fWD, const float *__restrict__ prob_col,
-                const float *__restrict__ ctx_t, float *__restrict__ bev) {
-    extern __shared__ __align__(16) float s_dyn[];
+__device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &a, int cons, float *s_dyn) {
     constexpr int C = 8 * CPL;
-    constexpr int LF = CPL <= 8 ? 4 : 2;                  // context rows in flight per group (shared voxels)
-    lss_pdl_wait();
-    tl_stamp(3, false);
-    const int n_queue = (int)gridDim.x - n_keys;          // the FIRST CTAs drain the queue of shared voxels (they form no tail)
-    const bool column = (int)blockIdx.x >= n_queue;
-    const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
-    const int per = d.D * d.fH;
-    if (column) {
-        const int key = (int)blockIdx.x - n_queue;        // (bn, w)
-        const int bn = key / d.fW, w0 = key - bn * d.fW;
-        float *s_ctx = s_dyn;                             // [fH][C]
-        float *s_prob = s_dyn + d.fH * C;                 // [D][fH]
-        int *s_row = reinterpret_cast<int *>(s_prob + per);
-        unsigned *s_em = reinterpret_cast<unsigned *>(s_row + per);
-        unsigned short *s_list = reinterpret_cast<unsigned short *>(s_em + per);
-        __shared__ int s_n;
-        if (threadIdx.x == 0) s_n = 0;
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(ctx_t + ((size_t)bn * d.HW + w0) * C);
-            constexpr int c4 = C >> 2;
-            for (int i = threadIdx.x; i < d.fH * c4; i += GCL_THREADS) {
-                const int h = i / c4, q = i - h * c4;
-                reinterpret_cast<float4 *>(s_ctx)[i] = __ldg(src + (size_t)h * d.fW * c4 + q);
+    constexpr int CH = C / 32;                            // channels per lane
+    constexpr int PR = C / 4;                             // 16-byte pieces per context row
+    constexpr int NW = GCL_THREADS / 32;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, gl = lane & 7, g = threadIdx.x >> 3;
+    const int HWC = d.HW * C;
+    const int vps = d.nx * d.ny * d.nz;                   // voxels per sample
+    if (threadIdx.x == 0) spin_until(a.counters + RPC_PUB, a.n_keys, 200);      // every column CTA has queued its shared voxels
+    __syncthreads();
+    tl_stamp(4, false);
+    const int n_rec = __ldcg(a.counters + RPC_NREC);
+    {
+        // per warp: keys, context-row numbers and weight indices of the voxel's points in list order [3][64], their order
+        // by key [64], then the context rows [GCL_ROWS][C]
+        uint32_t *w_key = reinterpret_cast<uint32_t *>(s_dyn) + wp * (4 * GCL_SHORT_CAP);
+        uint32_t *w_pix = w_key + GCL_SHORT_CAP, *w_widx = w_pix + GCL_SHORT_CAP, *w_ord = w_widx + GCL_SHORT_CAP;
+        float *w_rows = s_dyn + NW * 4 * GCL_SHORT_CAP + wp * (GCL_ROWS * C);
+        const int n_warps = a.n_cons * NW;
+        for (int r = cons * NW + wp; r < n_rec; r += n_warps) {
+            const int4 rec = __ldcg(a.recs + r);          // {list head, voxel row, first pusher, its row mask}
+            int len = 0;
+            const int2 first2 = __ldcg(a.sub2 + (rec.z - 1));
+            for (int cur = rec.x; ;) {                    // sub2 of a node is requested together with the node itself
+                int2 nd, nd2;
+                if (cur == rec.z) { nd = make_int2(0, rec.w); nd2 = first2; }
+                else {
+                    LSS_DASSERT(cur >= 1 && cur <= d.n_points);
+                    nd = __ldcg(a.sub + (cur - 1)); nd2 = __ldcg(a.sub2 + (cur - 1));
+                    LSS_DASSERT(nd.y != 0 && nd.x != 0 && __ldcg(a.prow + (cur - 1)) == rec.y);
+                }
+                const unsigned m = (unsigned)nd.y;
+                const int cnt = __popc(m);
+                if (lane < cnt && len + lane < GCL_SHORT_CAP) {
+                    const unsigned k = __fns(m, 0, lane + 1);     // image-row offset of this lane's point
+                    w_key[len + lane] = (unsigned)nd2.y + k * (unsigned)d.fW;
+                    w_pix[len + lane] = (unsigned)nd2.x + k * (unsigned)d.fW;
+                    w_widx[len + lane] = (unsigned)(cur - 1) + k;
+                }
+                len += cnt;
+                if (cur == rec.z) break;
+                cur = nd.x;
             }
-        }
-        __syncthreads();
-        const size_t base = (size_t)key * per;
-        for (int i0 = 0; i0 < per; i0 += GCL_THREADS) {   // stage the column's plan + weights, compact its leaders
-            const int i = i0 + threadIdx.x;
-            unsigned em = 0u;
-            if (i < per) {
-                em = __ldg(emask + base + i);
-                s_em[i] = em;
-                s_row[i] = __ldg(prow + base + i);
-                s_prob[i] = __ldg(prob_col + base + i);
+            if (len >= GCL_SHORT_CAP) {                   // long voxel: left to the last CTA
+                if (lane == 0) a.recs[a.n_rec_cap - 1 - atomicAdd(a.counters + RPC_NLONG, 1)] = rec;
+                continue;
             }
-            const unsigned hb = __ballot_sync(LSS_FULL_MASK, em != 0u);
-            int wbase = 0;
-            if (lane == 0 && hb) wbase = atomicAdd(&s_n, __popc(hb));
-            wbase = __shfl_sync(LSS_FULL_MASK, wbase, 0);
-            LSS_DASSERT(em == 0u || wbase + __popc(hb) <= per);
-            if (em != 0u) s_list[wbase + __popc(hb & ((1u << lane) - 1u))] = (unsigned short)i;
-        }
-        __syncthreads();
-        const int n_list = s_n;
-        const float *my_ctx = s_ctx + gl * 4;
-        for (int i = g; __any_sync(LSS_FULL_MASK, i < n_list); i += GCL_NG) {
-            const bool live = i < n_list;
-            const int s = live ? (int)s_list[i] : 0;
-            const unsigned m = live ? s_em[s] : 0u;
-            const int h0 = s - (int)lss_div20((unsigned)s, mfH) * d.fH;
-            float acc[CPL];
+            __syncwarp();
+            for (int i = lane; i < len; i += 32) {        // rank sort by flat point index (keys unique, len < 64)
+                const uint32_t e = w_key[i];
+                int rank = 0;
+                for (int j = 0; j < len; ++j) rank += w_key[j] < e ? 1 : 0;
+                w_ord[rank] = (uint32_t)i;
+            }
+            __syncwarp();
+            float acc[CH];
 #pragma unroll
-            for (int a = 0; a < CPL; ++a) acc[a] = 0.f;
-            const float *wp = s_prob + s;
-            const float *rowp0 = my_ctx + h0 * C;
-            for (int j = 0; j < d.fH; ++j) {
-                if ((m >> j) & 1u) {                      // bit j set => image row h0 + j < fH of the same run
-                    const float wj = wp[j];
-                    const float4 *rowp = reinterpret_cast<const float4 *>(rowp0 + j * C);
-#pragma unroll
-                    for (int q = 0; q < CPL / 4; ++q) {
-                        const float4 v = rowp[8 * q];
-                        acc[4 * q] = __fadd_rn(acc[4 * q], __fmul_rn(wj, v.x));
-                        acc[4 * q + 1] = __fadd_rn(acc[4 * q + 1], __fmul_rn(wj, v.y));
-                        acc[4 * q + 2] = __fadd_rn(acc[4 * q + 2], __fmul_rn(wj, v.z));
-                        acc[4 * q + 3] = __fadd_rn(acc[4 * q + 3], __fmul_rn(wj, v.w));
+            for (int k = 0; k < CH; ++k) acc[k] = 0.f;
+            for (int p0 = 0; p0 < len; p0 += GCL_ROWS) {
+                const int n = min(GCL_ROWS, len - p0);
+                float w = 0.f;
+                unsigned pix = 0u;
+                if (lane < n) {
+                    const uint32_t i = w_ord[p0 + lane];
+                    pix = w_pix[i];
+                    w = __ldcg(a.prob_col + w_widx[i]);
+                }
+                for (int k0 = 0; k0 < n; k0 += 32 / PR) { // 32 / PR rows per instruction, lane = (row, 16-byte piece)
+                    const int k = k0 + lane / PR, piece = lane % PR;
+                    const unsigned pix_k = __shfl_sync(LSS_FULL_MASK, pix, k & 31);
+                    if (k < n) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(w_rows + k * C + piece * 4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(a.ctx_t + (size_t)pix_k * C + piece * 4) : "memory");
                     }
                 }
-            }
-            if (live) {
-                LSS_DASSERT(s_row[s] >= 0 && s_row[s] < d.B * d.nx * d.ny * d.nz && (m >> (d.fH - h0)) == 0u);
-                float4 *dst = reinterpret_cast<float4 *>(bev + (size_t)s_row[s] * C) + gl;
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                for (int k = 0; k < n; ++k) {
+                    const float wk = __shfl_sync(LSS_FULL_MASK, w, k);
+                    const float *rp = w_rows + k * C + lane * CH;
+                    if (CH >= 2) {
 #pragma unroll
-                for (int q = 0; q < CPL / 4; ++q) dst[8 * q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                        for (int c = 0; c < CH; c += 2) mul_add2(acc[c], acc[c + (CH >= 2 ? 1 : 0)], wk, rp[c], rp[c + (CH >= 2 ? 1 : 0)]);
+                    } else {
+                        acc[0] = __fadd_rn(acc[0], __fmul_rn(wk, rp[0]));
+                    }
+                }
+                __syncwarp();
             }
+            LSS_DASSERT(len >= 2 && rec.y >= 0 && rec.y < d.B * vps);
+            if (a.zero_target && lane == 0) spin_until(a.zero_done + (rec.y / vps) * RP_FLAG_STRIDE, a.zero_target, 200);
+            __syncwarp();
+            float *dst = a.bev + (size_t)rec.y * C + lane * CH;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) dst[c] = acc[c];
         }
-        tl_stamp(3, true);
-        return;
     }
-
-    // ---- queue CTAs: shared voxels.  Shared-memory layout: [NG][64] unsorted, [NG][64] sorted, [SORT_CAP] keys, [NG][C] products
-    uint32_t *s_un = reinterpret_cast<uint32_t *>(s_dyn) + g * GCL_SHORT_CAP;
-    uint32_t *s_so = reinterpret_cast<uint32_t *>(s_dyn) + (GCL_NG + g) * GCL_SHORT_CAP;
-    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn) + 2 * GCL_NG * GCL_SHORT_CAP;
-    float *s_prod = s_dyn + 2 * GCL_NG * GCL_SHORT_CAP + GCL_SORT_CAP;
-    const int qid = (int)blockIdx.x;
-    const int HWC = d.HW * C;
-    auto decode = [&](unsigned pidx, int b, int &ro, size_t &wi) {   // context row offset (floats) and prob_col index of a point
+    tl_stamp(4, true);
+    // ---- the last CTA to finish: long voxels, then the scratch of the forward is left clean for the next one
+    __shared__ int s_last, s_len, s_pos;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.counters + RPC_FWD_DONE, 1) == a.n_cons - 1;
+        if (s_last) __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // Long voxels (>= 64 points), one at a time by the whole CTA.  Scratch: [SORT_CAP] keys, [NG][C] products.  Keys are sorted
+    // by the CTA (shared memory up to SORT_CAP points, else in the pool), then NG points per pass: every group fetches one
+    // point's context row and writes float32(prob*ctx) to shared memory (all loads in flight together); thread c adds the NG
+    // products of channel c in ascending point order -- the same sequence of float32 additions as everywhere else.
+    auto decode = [&](unsigned pidx, int b, int &ro, size_t &wi) {   // context row offset (floats) in the sample and prob_col index of a point
         const unsigned cam = lss_div20(pidx, d.mDHW);
         const unsigned rr = pidx - cam * d.DHW;
         const unsigned dd = lss_div20(rr, d.mHW);
@@ -374,122 +518,228 @@ k_fwd_gather_cl(Dims d, int n_keys, unsigned long long mfH, const int32_t *__res
         ro = (int)(cam * HWC + hw * C);
         wi = ((size_t)(bnn * d.fW + ww) * d.D + dd) * d.fH + h;
     };
-    {   // long voxels (>= 64 points): one at a time by the whole CTA.  Keys are sorted by the CTA (shared memory up to SORT_CAP
-        // points, else in place in the pool), then NG points per pass: every group fetches one point's context row and writes
-        // float32(prob*ctx) to shared memory (all loads in flight together); thread c adds the NG products of channel c in
-        // ascending point order -- the same sequence of float32 additions as everywhere else, without the serial load chain.
-        const int n_long = __ldg(counters + 2);
-        for (int rl = qid; rl < n_long; rl += n_queue) {
-            const int4 rec = __ldg(mixed_recs + (n_mixed_cap - 1 - rl));
-            uint32_t *gk = pool + rec.x;
-            const bool in_smem = rec.y <= GCL_SORT_CAP;
-            if (in_smem) {
-                for (int i = threadIdx.x; i < rec.y; i += GCL_THREADS) s_keys[i] = __ldcg(gk + i);
-                __syncthreads();
-                bitonic_sort_block(s_keys, rec.y);
-            } else {
-                bitonic_sort_block((volatile uint32_t *)gk, rec.y);
-            }
-            __syncthreads();
-            const float *ctx_b = ctx_t + (size_t)rec.w * d.N * HWC + gl * 4;
-            float accc = 0.f;
-            for (int base = 0; base < rec.y; base += GCL_NG) {
-                const int cntp = min(GCL_NG, rec.y - base);
-                if (g < cntp) {
-                    const unsigned pidx = in_smem ? s_keys[base + g] : ((volatile uint32_t *)gk)[base + g];
-                    int ro; size_t wi;
-                    decode(pidx, rec.w, ro, wi);
-                    const float w = __ldg(prob_col + wi);
-                    const float4 *rowp = reinterpret_cast<const float4 *>(ctx_b + ro);
-                    float4 *dst = reinterpret_cast<float4 *>(s_prod + g * C) + gl;
-#pragma unroll
-                    for (int q = 0; q < CPL / 4; ++q) {
-                        const float4 v = __ldg(rowp + 8 * q);
-                        dst[8 * q] = make_float4(__fmul_rn(w, v.x), __fmul_rn(w, v.y), __fmul_rn(w, v.z), __fmul_rn(w, v.w));
-                    }
-                }
-                __syncthreads();
-                if ((int)threadIdx.x < C)
-                    for (int jj = 0; jj < cntp; ++jj) accc = __fadd_rn(accc, s_prod[jj * C + threadIdx.x]);
-                __syncthreads();
-            }
-            if ((int)threadIdx.x < C) bev[(size_t)rec.z * C + threadIdx.x] = accc;
+    const int n_long = __ldcg(a.counters + RPC_NLONG);
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn);
+    float *s_prod = s_dyn + GCL_SORT_CAP;
+    for (int l = 0; l < n_long; ++l) {
+        const int4 rec = __ldcg(a.recs + (a.n_rec_cap - 1 - l));
+        const int b = rec.y / vps;
+        if (threadIdx.x == 0) {                           // points of the voxel; room in the pool if they do not fit shared memory
+            int c = __popc((unsigned)rec.w);
+            for (int cur = rec.x; cur != rec.z;) { const int2 nd = __ldcg(a.sub + (cur - 1)); c += __popc((unsigned)nd.y); cur = nd.x; }
+            s_len = c;
+            s_pos = c > GCL_SORT_CAP ? atomicAdd(a.counters + RPC_POOL, c) : 0;
+            LSS_DASSERT(c >= GCL_SHORT_CAP && s_pos >= 0 && s_pos + c <= d.n_points);
+            if (a.zero_target) spin_until(a.zero_done + b * RP_FLAG_STRIDE, a.zero_target, 200);
         }
-    }
-    const int n_rec = __ldg(counters);
-    for (int r = GCL_NG * qid + g; __any_sync(LSS_FULL_MASK, r < n_rec); r += GCL_NG * n_queue) {
-        const bool live = r < n_rec;
-        int4 rec = make_int4(0, 0, 0, 0);                 // {head of the voxel's list, points, voxel row, batch}
-        if (live) rec = __ldg(mixed_recs + r);
-        const int len = rec.y;
-        const int maxlen = __reduce_max_sync(LSS_FULL_MASK, len);
-        {   // walk the voxel's list (a few sub-runs), the groups of the warp in lockstep; the 8 lanes expand each node together
-            int cur = rec.x, filled = 0;
-            while (__any_sync(LSS_FULL_MASK, cur != 0)) {
-                int2 nd = make_int2(0, 0);
-                if (cur != 0) {
-                    LSS_DASSERT(cur >= 1 && cur <= d.n_points);
-                    nd = __ldcg(sub + (cur - 1));
-                    LSS_DASSERT(filled + __popc((unsigned)nd.y) <= len && len < GCL_SHORT_CAP);
-                    filled += expand_subrun(d, fWD, cur - 1, (unsigned)nd.y, s_un + filled, gl, 8);
-                }
+        __syncthreads();
+        const int npt = s_len;
+        const bool in_smem = npt <= GCL_SORT_CAP;
+        uint32_t *gk = a.pool + s_pos;
+        if (threadIdx.x == 0) {
+            uint32_t *out = in_smem ? s_keys : gk;
+            int i = expand_keys((unsigned)__ldcg(a.sub2 + (rec.z - 1)).y, (unsigned)rec.w, d.fW, out, 0, npt);
+            for (int cur = rec.x; cur != rec.z;) {
+                const int2 nd = __ldcg(a.sub + (cur - 1));
+                i += expand_keys((unsigned)__ldcg(a.sub2 + (cur - 1)).y, (unsigned)nd.y, d.fW, out, i, npt);
                 cur = nd.x;
             }
         }
-        __syncwarp();
-        for (int i = gl; i < maxlen; i += 8) {            // rank sort by flat point index (keys unique, len < 64)
-            const uint32_t e = i < len ? s_un[i] : 0u;
-            int rank = 0;
-            for (int j = 0; j < maxlen; ++j) rank += (j < len && s_un[j] < e) ? 1 : 0;
-            if (i < len) s_so[rank] = e;
-        }
-        __syncwarp();
-        const float *ctx_b = ctx_t + (size_t)rec.w * d.N * HWC + gl * 4;
-        float acc[CPL];
+        __syncthreads();
+        if (in_smem) bitonic_sort_block(s_keys, npt);
+        else bitonic_sort_block((volatile uint32_t *)gk, npt);
+        __syncthreads();
+        const float *ctx_s = a.ctx_t + (size_t)b * d.N * HWC;
+        float accc = 0.f;
+        for (int p0 = 0; p0 < npt; p0 += GCL_NG) {
+            const int cntp = min(GCL_NG, npt - p0);
+            if (g < cntp) {
+                const unsigned pidx = in_smem ? s_keys[p0 + g] : ((volatile uint32_t *)gk)[p0 + g];
+                int ro; size_t wi;
+                decode(pidx, b, ro, wi);
+                const float w = __ldcg(a.prob_col + wi);
+                const float4 *rowp = reinterpret_cast<const float4 *>(ctx_s + ro + gl * 4);
+                float4 *dst = reinterpret_cast<float4 *>(s_prod + g * C) + gl;
 #pragma unroll
-        for (int a = 0; a < CPL; ++a) acc[a] = 0.f;
-        for (int base = 0; base < maxlen; base += 8) {    // the groups of the warp in lockstep, 8 points per step
-            const int cntp = min(8, len - base);          // <= 0 for a group that has nothing (more) to do
-            const int maxcnt = min(8, maxlen - base);
-            float w = 0.f;
-            int ro = 0;
-            if (gl < cntp) {
-                size_t wi;
-                decode(s_so[base + gl], rec.w, ro, wi);
-                w = __ldg(prob_col + wi);
+                for (int q = 0; q < CPL / 4; ++q) {
+                    const float4 v = __ldcg(rowp + 8 * q);
+                    dst[8 * q] = make_float4(__fmul_rn(w, v.x), __fmul_rn(w, v.y), __fmul_rn(w, v.z), __fmul_rn(w, v.w));
+                }
             }
+            __syncthreads();
+            if ((int)threadIdx.x < C)
+                for (int jj = 0; jj < cntp; ++jj) accc = __fadd_rn(accc, s_prod[jj * C + threadIdx.x]);
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < C) a.bev[(size_t)rec.y * C + threadIdx.x] = accc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {                               // every progress counter has been seen complete by a column CTA by now
+        a.counters[RPC_STAT] = n_rec; a.counters[RPC_STAT + 1] = n_long;
+        a.counters[RPC_NREC] = 0; a.counters[RPC_NLONG] = 0; a.counters[RPC_POOL] = 0; a.counters[RPC_FWD_DONE] = 0; a.counters[RPC_PUB] = 0;
+        if (a.wait_ready) for (int i = 0; i < RP_READY_LINES; ++i) a.ready[i * RP_FLAG_STRIDE] = 0;
+        if (a.zero_target) for (int i = 0; i < d.B; ++i) a.zero_done[i * RP_FLAG_STRIDE] = 0;
+    }
+}
+
+// The forward grid.  [0, n_zero): zero CTAs (LSS_ZERO_ORDERED only).  [.., + n_keys): one CTA per camera column (bn, w): stage
+// the column's operands and plan, classify its sub-runs, queue the voxels it shares with other sub-runs, sum the EXCLUSIVE
+// ones from the staged operands and write their voxel rows.  [.., + n_cons): the shared voxels (shared_voxels_cta); these CTAs
+// come last in the grid, so everything they wait for is running or done when they start.
+template <int CPL>
+__global__ void __launch_bounds__(GCL_THREADS, 9)        // <= 56 registers: 8 column CTAs per SM next to the two zero CTAs
+k_fwd_columns(Dims d, FwdArgs a) {
+    extern __shared__ __align__(128) float s_dyn[];
+    constexpr int C = 8 * CPL;
+    if ((int)blockIdx.x < a.n_zero) {                     // ---- zero CTAs (scheduled first: nobody they depend on comes later)
+        lss_pdl_wait();
+        zero_role_segments(a.bev, a.seg_bytes, d.B, (int)blockIdx.x, a.n_zero, s_dyn, a.zero_done, a.z_chunk, a.z_window);
+        return;
+    }
+    if (a.wait_ready) {                                   // the zero-fill grid is still streaming: only the plan + lift grid counts
+        if (threadIdx.x == 0) spin_until(a.ready + (blockIdx.x % RP_READY_LINES) * RP_FLAG_STRIDE, 1, 100);
+        __syncthreads();
+    } else {
+        lss_pdl_wait();                                   // plan and lift operands come from the preceding kernel(s)
+    }
+    if ((int)blockIdx.x >= a.n_zero + a.n_keys) { shared_voxels_cta<CPL>(d, a, (int)blockIdx.x - a.n_zero - a.n_keys, s_dyn); return; }
+    tl_stamp(3, false);
+    const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
+    const int per = d.D * d.fH;
+    const int key = (int)blockIdx.x - a.n_zero;           // camera column (bn, w)
+    const int bn = key / d.fW, w0 = key - bn * d.fW;
+    const int b = bn / d.N;
+    tl_mark(key, 0);
+    float *s_ctx = s_dyn;                                 // [fH][C]
+    float *s_prob = s_dyn + d.fH * C;                     // [D][fH]
+    int *s_row = reinterpret_cast<int *>(s_prob + per);   // [per] voxel row
+    unsigned *s_aux = reinterpret_cast<unsigned *>(s_row + per);     // [per] row mask of an EXCLUSIVE leader / list head of a shared voxel's first pusher / 0
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_aux + per);      // [per] slots of the EXCLUSIVE leaders
+    unsigned short *s_shared = s_list + per;              // [per] slots of the first pushers of shared voxels ...
+    unsigned *s_shmask = reinterpret_cast<unsigned *>(s_shared + per + (per & 1));    // [per] ... and their row masks
+    __shared__ int s_n, s_nshared;
+    if (threadIdx.x == 0) { s_n = 0; s_nshared = 0; }
+    const unsigned long long tag = (unsigned long long)(unsigned)__ldcg(a.counters + RPC_EPOCH) << 32;
+    const size_t base = (size_t)key * per;
+    constexpr int SU = 3;                                 // slots per thread and round: their loads are all in flight together
+    constexpr int c4 = C >> 2;
+    const float4 *ctx_src = reinterpret_cast<const float4 *>(a.ctx_t + ((size_t)bn * d.HW + w0) * C);
+    const int n_c4 = d.fH * c4;
+    float4 cv[2];                                         // the column's context rows (<= 2 pieces per thread: requested first, stored last)
 #pragma unroll
-            for (int j0 = 0; j0 < 8; j0 += LF) {
-                if (j0 >= maxcnt) break;
-                float x[LF][CPL];
+    for (int u = 0; u < 2; ++u) {
+        const int i = threadIdx.x + u * GCL_THREADS;
+        if (i < n_c4) { const int h = i / c4, q = i - h * c4; cv[u] = __ldcg(ctx_src + (size_t)h * d.fW * c4 + q); }
+    }
+    __syncthreads();                                      // s_n, s_nshared
+    for (int i0 = 0; i0 < per; i0 += SU * GCL_THREADS) {  // stage the column's plan + weights, classify and compact its leaders
+        int2 node[SU]; int row[SU]; float pw[SU]; unsigned long long hd[SU];
 #pragma unroll
-                for (int u = 0; u < LF; ++u) {            // LF rows in flight (idle slots re-read row 0 of the sample: finite, unused)
-                    const int oj = __shfl_sync(LSS_FULL_MASK, ro, j0 + u, 8);
-                    const float4 *rowp = reinterpret_cast<const float4 *>(ctx_b + oj);
+        for (int u = 0; u < SU; ++u) {
+            const int i = i0 + u * GCL_THREADS + threadIdx.x;
+            node[u] = make_int2(0, 0); row[u] = -1; pw[u] = 0.f;
+            if (i < per) {
+                node[u] = __ldcg(a.sub + base + i);       // {previous head of the voxel's list, row mask}
+                row[u] = __ldcg(a.prow + base + i);
+                pw[u] = __ldcg(a.prob_col + base + i);
+            }
+        }
 #pragma unroll
-                    for (int q = 0; q < CPL / 4; ++q) {
-                        const float4 v = __ldg(rowp + 8 * q);
-                        x[u][4 * q] = v.x; x[u][4 * q + 1] = v.y; x[u][4 * q + 2] = v.z; x[u][4 * q + 3] = v.w;
+        for (int u = 0; u < SU; ++u) {                    // a sub-run that pushed first answers for its voxel: is it still the head?
+            hd[u] = 0ull;
+            if (node[u].y != 0 && node[u].x == 0) {
+                LSS_DASSERT(row[u] >= 0 && row[u] < d.B * d.nx * d.ny * d.nz);
+                hd[u] = __ldcg(a.head + row[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int i = i0 + u * GCL_THREADS + threadIdx.x;
+            unsigned em = 0u;
+            if (i < per) {
+                s_row[i] = row[u];
+                s_prob[i] = pw[u];
+                unsigned aux = 0u;
+                if (hd[u] != 0ull) {
+                    LSS_DASSERT((hd[u] >> 32) == (tag >> 32) && (unsigned)hd[u] >= 1u && (unsigned)hd[u] <= (unsigned)d.n_points);
+                    if (hd[u] == (tag | (unsigned long long)(base + i + 1))) aux = em = (unsigned)node[u].y;   // nobody pushed after it: EXCLUSIVE
+                    else {
+                        aux = (unsigned)hd[u];
+                        const int pos = atomicAdd(&s_nshared, 1);
+                        s_shared[pos] = (unsigned short)i; s_shmask[pos] = (unsigned)node[u].y;
                     }
                 }
+                s_aux[i] = aux;
+            }
+            const unsigned hb = __ballot_sync(LSS_FULL_MASK, em != 0u);
+            int wbase = 0;
+            if (lane == 0 && hb) wbase = atomicAdd(&s_n, __popc(hb));
+            wbase = __shfl_sync(LSS_FULL_MASK, wbase, 0);
+            LSS_DASSERT(em == 0u || wbase + __popc(hb) <= per);
+            if (em != 0u) s_list[wbase + __popc(hb & ((1u << lane) - 1u))] = (unsigned short)i;
+        }
+    }
 #pragma unroll
-                for (int u = 0; u < LF; ++u) {
-                    const float wj = __shfl_sync(LSS_FULL_MASK, w, j0 + u, 8);
-                    if (j0 + u < cntp) {
+    for (int u = 0; u < 2; ++u) {
+        const int i = threadIdx.x + u * GCL_THREADS;
+        if (i < n_c4) reinterpret_cast<float4 *>(s_ctx)[i] = cv[u];
+    }
+    for (int i = threadIdx.x + 2 * GCL_THREADS; i < n_c4; i += GCL_THREADS) {      // (tall feature maps: the rest of the rows)
+        const int h = i / c4, q = i - h * c4;
+        reinterpret_cast<float4 *>(s_ctx)[i] = __ldcg(ctx_src + (size_t)h * d.fW * c4 + q);
+    }
+    tl_mark(key, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {                               // queue the shared voxels (one reservation per CTA), count the CTA in
+        const int n = s_nshared;
+        if (n) {
+            const int q0 = atomicAdd(a.counters + RPC_NREC, n);
+            LSS_DASSERT(q0 >= 0 && q0 + n <= a.n_rec_cap);
+            for (int r = 0; r < n; ++r) {
+                const int slot = (int)s_shared[r];
+                a.recs[q0 + r] = make_int4((int)s_aux[slot], s_row[slot], (int)(base + slot) + 1, (int)s_shmask[r]);
+            }
+            __threadfence();
+        }
+        atomicAdd(a.counters + RPC_PUB, 1);
+        if (a.zero_target)                                // the zeros of this sample's slab must be down before any row is written
+            spin_until(a.zero_done + b * RP_FLAG_STRIDE, a.zero_target, 400);
+    }
+    __syncthreads();
+    tl_mark(key, 2);
+    const int n_list = s_n;
+    const float *my_ctx = s_ctx + gl * 4;
+    for (int i = g; __any_sync(LSS_FULL_MASK, i < n_list); i += GCL_NG) {
+        const bool live = i < n_list;
+        const int s = live ? (int)s_list[i] : 0;
+        const unsigned m = live ? s_aux[s] : 0u;
+        const int h0 = s - (int)lss_div20((unsigned)s, a.mfH) * d.fH;
+        float acc[CPL];
 #pragma unroll
-                        for (int a = 0; a < CPL; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(wj, x[u][a]));
-                    }
+        for (int k = 0; k < CPL; ++k) acc[k] = 0.f;
+        const float *wp_ = s_prob + s;
+        const float *rowp0 = my_ctx + h0 * C;
+        for (int j = 0; j < d.fH; ++j) {
+            if ((m >> j) & 1u) {                          // bit j set => image row h0 + j < fH of the same run
+                const float wj = wp_[j];
+                const float4 *rowp = reinterpret_cast<const float4 *>(rowp0 + j * C);
+#pragma unroll
+                for (int q = 0; q < CPL / 4; ++q) {
+                    const float4 v = rowp[8 * q];
+                    mul_add2(acc[4 * q], acc[4 * q + 1], wj, v.x, v.y);
+                    mul_add2(acc[4 * q + 2], acc[4 * q + 3], wj, v.z, v.w);
                 }
             }
         }
         if (live) {
-            LSS_DASSERT(rec.z >= 0 && rec.z < d.B * d.nx * d.ny * d.nz && rec.w == rec.z / (d.nx * d.ny * d.nz));
-            float4 *dst = reinterpret_cast<float4 *>(bev + (size_t)rec.z * C) + gl;
+            LSS_DASSERT(s_row[s] >= 0 && s_row[s] < d.B * d.nx * d.ny * d.nz && (m >> (d.fH - h0)) == 0u);
+            float4 *dst = reinterpret_cast<float4 *>(a.bev + (size_t)s_row[s] * C) + gl;
 #pragma unroll
             for (int q = 0; q < CPL / 4; ++q) dst[8 * q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         }
-        __syncwarp();
     }
+    tl_mark(key, 3);
+    tl_stamp(3, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,49 +779,73 @@ extern "C" int lss_runplan_layout_init(const lss_problem *p, lss_runplan_layout 
     out->n_points = d.n_points;
     out->n_runs = (int64_t)p->B * p->N * p->fW * p->D;
     out->n_voxels = (int64_t)p->B * p->nx * p->ny * p->nz;
-    out->n_mixed_cap = (int64_t)d.n_points / 2 + 2;       // a shared voxel holds at least two points
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t off = 0;
     out->off_prow = off;       off += up((size_t)d.n_points * 4);
-    out->off_emask = off;      off += up((size_t)d.n_points * 4);
     out->off_sub = off;        off += up((size_t)d.n_points * 8);
+    out->off_sub2 = off;       off += up((size_t)d.n_points * 8);
     out->off_pool = off;       off += up((size_t)d.n_points * 4);
-    out->off_mixed_recs = off; off += up((size_t)out->n_mixed_cap * 16);
+    out->n_rec_cap = (int64_t)d.n_points / 2 + 2;         // a shared voxel holds at least two points
+    out->off_recs = off;       off += up((size_t)out->n_rec_cap * 16);
     out->off_counters = off;   off += up(64 * 4);
-    out->off_cnt = off;        off += up((size_t)out->n_voxels * 4);
-    out->off_head = off;       off += up((size_t)out->n_voxels * 4);
+    out->off_zero_done = off;  off += up((size_t)p->B * RP_FLAG_STRIDE * 4);
+    out->off_ready = off;      off += up((size_t)RP_READY_LINES * RP_FLAG_STRIDE * 4);
+    out->off_head = off;       off += up((size_t)out->n_voxels * 8);
     out->bytes = off;
     return LSS_OK;
 }
 
 extern "C" int lss_runplan_reset(const lss_runplan_layout *L, void *ws, void *stream) {
     LSS_REQUIRE(L && ws, LSS_ERR_WORKSPACE);
-    char *w = (char *)ws;    // counters, cnt and head are contiguous
+    char *w = (char *)ws;    // counters, zero_done and head are contiguous
     if (cudaMemsetAsync(w + L->off_counters, 0, L->bytes - L->off_counters, (cudaStream_t)stream) != cudaSuccess) return LSS_ERR_CUDA;
     return LSS_OK;
 }
 
+// cameras one index CTA may span when it makes the calibration inverses itself
+static bool raw_build_fits(const lss_problem *p) {
+    const RunDims rd = make_run_dims(p);
+    return (RP_WARPS * RP_U * rd.RPW) / rd.fWD + 2 <= LSS_RAW_CAMS;
+}
+
+extern "C" int lss_runplan_raw_supported(const lss_problem *p) {
+    int st = runplan_supported(p);
+    if (st != LSS_OK) return st;
+    return raw_build_fits(p) ? LSS_OK : LSS_ERR_UNSUPPORTED;
+}
+
+// Pacing of the zero-fill with progress counters: CTAs, bytes per bulk copy, copies in flight per CTA.  Measured at cfg 2 next to
+// the other kernels of the forward: 148 .. 592 CTAs, 4 .. 16 KB copies, 1 .. 8 in flight all end within
+// +-1.5 us of each other; fewer CTAs or shallower windows stretch the zero-fill, deeper ones delay the latency-bound CTAs.
+struct ZeroTune { int n_cta, chunk, window; };
+static ZeroTune zero_tune(size_t seg_bytes) {
+    ZeroTune t = {2 * rp_num_sms(), ZERO_CHUNK, 4};
+    const size_t cps = (seg_bytes + t.chunk - 1) / t.chunk;
+    if ((size_t)t.n_cta > cps) t.n_cta = (int)cps;
+    return t;
+}
+
+// `ready`: launched programmatically behind k_zero_flags (no dependence on it); the last lift / index CTA raises READY
 static int launch_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, bool index, const CalibPtrs &c, bool raw,
-                           const float *dn, float *prob, float *ctx_t, float *prob_col, float *bev, size_t bev_bytes,
+                           const float *dn, float *prob, float *ctx_t, float *prob_col, float *bev, size_t bev_bytes, bool ready,
                            cudaStream_t s) {
     const Dims d = make_dims(p);
     PrologueArgs a = {};
     a.rd = make_run_dims(p);
     char *w = (char *)workspace;
-    if (bev != nullptr && bev_bytes > 0) {
-        // two issuing CTAs per SM (one: 67.5 us per step at cfg 2 against 63); evict-first lines: the zeros should not push
-        // the plan and the lift operands out of L2 (measured neutral to slightly better)
-        const size_t n_chunks = (bev_bytes + ZERO_CHUNK - 1) / ZERO_CHUNK;
-        a.bev = bev; a.bev_bytes = bev_bytes; a.evict_first = 1;
-        a.n_zero = (int)min((size_t)2 * rp_num_sms(), n_chunks);
+    if (w != nullptr) a.counters = (int32_t *)(w + L->off_counters);
+    if (bev != nullptr && bev_bytes > 0) {      // two issuing CTAs per SM (one: 67.5 us per step at cfg 2 against 63)
+        a.bev = bev; a.bev_bytes = bev_bytes;
+        a.n_zero = (int)min((size_t)2 * rp_num_sms(), (bev_bytes + ZERO_CHUNK - 1) / ZERO_CHUNK);
     }
+    if (ready) a.ready = (int32_t *)(w + L->off_ready);
     if (index) {
         const int runs_per_cta = RP_WARPS * RP_U * a.rd.RPW;
-        if (raw) LSS_REQUIRE(runs_per_cta / a.rd.fWD + 2 <= LSS_RAW_CAMS, LSS_ERR_UNSUPPORTED);   // cameras one CTA may span
+        if (raw) LSS_REQUIRE(raw_build_fits(p), LSS_ERR_UNSUPPORTED);
         a.n_index = (a.rd.R + runs_per_cta - 1) / runs_per_cta;
         a.c = c;
-        a.prow = (int32_t *)(w + L->off_prow); a.cnt = (int32_t *)(w + L->off_cnt); a.head = (int32_t *)(w + L->off_head);
-        a.counters = (int32_t *)(w + L->off_counters); a.sub = (int2 *)(w + L->off_sub);
+        a.prow = (int32_t *)(w + L->off_prow); a.head = (unsigned long long *)(w + L->off_head);
+        a.sub = (int2 *)(w + L->off_sub); a.sub2 = (int2 *)(w + L->off_sub2);
     }
     size_t smem = a.n_zero ? ZERO_CHUNK : 0;
     if (dn != nullptr) {
@@ -581,17 +855,12 @@ static int launch_prologue(const lss_problem *p, const lss_runplan_layout *L, vo
     }
     const int grid = a.n_zero + a.n_index + a.n_lift;
     if (grid == 0) return LSS_OK;
+    if (ready) LSS_REQUIRE(a.n_index + a.n_lift > 0, LSS_ERR_BAD_ARG);      // somebody has to raise READY
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
     auto kern = raw ? k_prologue<true> : k_prologue<false>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LSS_ERR_CUDA;
-    kern<<<grid, RP_THREADS, smem, s>>>(d, a);
+    if (lss_launch(kern, dim3(grid), dim3(RP_THREADS), smem, s, ready, d, a) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
-    if (index) {
-        if (lss_launch(k_run_classify, dim3(a.n_index), dim3(RP_THREADS), 0, s, true, d, a.rd, (const int32_t *)a.prow,
-                       (uint32_t *)(w + L->off_emask), a.cnt, a.head, (const int2 *)a.sub, (uint32_t *)(w + L->off_pool),
-                       (int4 *)(w + L->off_mixed_recs), a.counters, (long long)L->n_mixed_cap) != cudaSuccess) return LSS_ERR_CUDA;
-        LSS_CHECK_LAUNCH();
-    }
     return LSS_OK;
 }
 
@@ -602,25 +871,51 @@ extern "C" int lss_runplan_build(const lss_problem *p, const lss_runplan_layout 
                                   nullptr, nullptr, nullptr, stream);
 }
 
-extern "C" int lss_liftsplat_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
-                                      const float *post_trans, const float *M1, const float *M2, const float *trans,
-                                      const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
-                                      float *prob, float *ctx_t, float *prob_col, float *bev, void *stream) {
+static int prologue_validate(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                             const float *post_trans, const float *M1, const float *M2, const float *trans, const float *rots,
+                             const float *intrins, const float *post_rots, const float *depthnet_out, float *prob, float *ctx_t,
+                             float *prob_col, float *bev, bool ready) {
     int st = runplan_supported(p);
     if (st != LSS_OK) return st;
     const bool index = frustum != nullptr;
     const bool raw = M1 == nullptr || M2 == nullptr;
-    if (index) {
+    if (index || ready) {
         LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
-        LSS_REQUIRE(post_trans && trans, LSS_ERR_BAD_ARG);
-        LSS_REQUIRE(!raw || (rots && intrins && post_rots), LSS_ERR_BAD_ARG);
         LSS_REQUIRE(L->n_points == (int64_t)p->B * p->N * p->D * p->fH * p->fW, LSS_ERR_WORKSPACE);
     }
+    if (index) {
+        LSS_REQUIRE(post_trans && trans, LSS_ERR_BAD_ARG);
+        LSS_REQUIRE(!raw || (rots && intrins && post_rots), LSS_ERR_BAD_ARG);
+        if (raw) LSS_REQUIRE(raw_build_fits(p), LSS_ERR_UNSUPPORTED);
+    }
     if (depthnet_out != nullptr) LSS_REQUIRE(prob && ctx_t && prob_col, LSS_ERR_BAD_ARG);
+    if (ready) LSS_REQUIRE(index || depthnet_out != nullptr, LSS_ERR_BAD_ARG);      // somebody has to raise READY
+    if ((size_t)(p->D + p->C) * (LIFT_PX + 1) * sizeof(float) > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    if (bev != nullptr) LSS_REQUIRE(lss_aligned(bev, 16), LSS_ERR_ALIGN);
+    return LSS_OK;
+}
+
+static int prologue_checked(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                            const float *post_trans, const float *M1, const float *M2, const float *trans,
+                            const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
+                            float *prob, float *ctx_t, float *prob_col, float *bev, bool ready, void *stream) {
+    int st = prologue_validate(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,
+                               prob_col, bev, ready);
+    if (st != LSS_OK) return st;
+    const bool index = frustum != nullptr;
+    const bool raw = M1 == nullptr || M2 == nullptr;
     const size_t bytes = (size_t)p->B * p->nz * p->C * p->nx * p->ny * 4;
-    if (bev != nullptr) LSS_REQUIRE(lss_aligned(bev, 16) && bytes % 16 == 0, LSS_ERR_ALIGN);
     const CalibPtrs c{frustum, post_trans, M1, M2, trans, rots, intrins, post_rots};
-    return launch_prologue(p, L, workspace, index, c, index && raw, depthnet_out, prob, ctx_t, prob_col, bev, bytes, (cudaStream_t)stream);
+    return launch_prologue(p, L, (L && workspace) ? workspace : nullptr, index, c, index && raw, depthnet_out, prob, ctx_t, prob_col, bev,
+                           bytes, ready, (cudaStream_t)stream);
+}
+
+extern "C" int lss_liftsplat_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                                      const float *post_trans, const float *M1, const float *M2, const float *trans,
+                                      const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
+                                      float *prob, float *ctx_t, float *prob_col, float *bev, void *stream) {
+    return prologue_checked(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,
+                            prob_col, bev, false, stream);
 }
 
 static int launch_bev_zero(float *bev, size_t bytes, cudaStream_t s) {
@@ -629,7 +924,7 @@ static int launch_bev_zero(float *bev, size_t bytes, cudaStream_t s) {
     lss_problem dummy = {};
     dummy.B = dummy.N = dummy.D = dummy.fH = dummy.fW = 1; dummy.C = 32; dummy.nx = dummy.ny = dummy.nz = 1;
     dummy.dx[0] = dummy.dx[1] = dummy.dx[2] = 1.f;
-    return launch_prologue(&dummy, nullptr, nullptr, false, CalibPtrs{}, false, nullptr, nullptr, nullptr, nullptr, bev, bytes, s);
+    return launch_prologue(&dummy, nullptr, nullptr, false, CalibPtrs{}, false, nullptr, nullptr, nullptr, nullptr, bev, bytes, false, s);
 }
 
 extern "C" int lss_bev_zero(const lss_problem *p, float *bev, int part, int n_parts, void *stream) {
@@ -642,44 +937,93 @@ extern "C" int lss_bev_zero(const lss_problem *p, float *bev, int part, int n_pa
     return launch_bev_zero(reinterpret_cast<float *>(reinterpret_cast<char *>(bev) + r0 * row_bytes), (r1 - r0) * row_bytes, (cudaStream_t)stream);
 }
 
-static size_t gather_cl_smem(const lss_problem *p) {
+static size_t fwd_columns_smem(const lss_problem *p, bool zero) {
     const size_t per = (size_t)p->D * p->fH;
-    const size_t col = ((size_t)p->fH * p->C + 3 * per) * 4 + per * 2 + 16;
-    const size_t que = ((size_t)2 * GCL_NG * GCL_SHORT_CAP + GCL_SORT_CAP + (size_t)GCL_NG * p->C) * 4;
-    return col > que ? col : que;
+    const size_t col = ((size_t)p->fH * p->C + 4 * per) * 4 + 2 * (per + 1) * 2 + 16;
+    const size_t shr = (size_t)(GCL_THREADS / 32) * (4 * GCL_SHORT_CAP + (size_t)GCL_ROWS * p->C) * 4;
+    const size_t lng = ((size_t)GCL_SORT_CAP + (size_t)GCL_NG * p->C) * 4;
+    size_t total = col > shr ? col : shr;
+    if (lng > total) total = lng;
+    return zero && total < ZERO_CHUNK ? (size_t)ZERO_CHUNK : total;
 }
 
-extern "C" int lss_liftsplat_fwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,
-                                    const float *prob_col, const float *ctx_t, float *bev, int precleared, void *stream) {
+template <int CPL>
+static int launch_fwd_kernel(const Dims &d, const FwdArgs &a, size_t smem, bool pdl, cudaStream_t s) {
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(k_fwd_columns<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LSS_ERR_CUDA;
+    if (lss_launch(k_fwd_columns<CPL>, dim3(a.n_zero + a.n_keys + a.n_cons), dim3(GCL_THREADS), smem, s, pdl, d, a) != cudaSuccess) return LSS_ERR_CUDA;
+    LSS_CHECK_LAUNCH();
+    return LSS_OK;
+}
+
+// zero_target: 0 = pre-cleared; > 0 with in_kernel = zero CTAs inside the column grid; > 0 without = the CTAs of k_zero_flags
+static int launch_fwd_grid(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *prob_col,
+                            const float *ctx_t, float *bev, int zero_target, bool in_kernel, bool wait_ready, cudaStream_t s) {
+    const Dims d = make_dims(p);
+    char *w = (char *)workspace;
+    FwdArgs a = {};
+    a.seg_bytes = (size_t)p->nx * p->ny * p->nz * p->C * 4;
+    a.n_zero = in_kernel ? zero_target : 0;
+    a.zero_target = zero_target;
+    { const ZeroTune t = zero_tune(a.seg_bytes); a.z_chunk = t.chunk; a.z_window = t.window; }
+    a.wait_ready = wait_ready ? 1 : 0;
+    a.zero_done = (int32_t *)(w + L->off_zero_done); a.ready = (int32_t *)(w + L->off_ready);
+    a.n_keys = p->B * p->N * p->fW; a.fWD = p->fW * p->D;
+    a.mfH = ((1ull << 40) + (unsigned)p->fH - 1) / (unsigned)p->fH;
+    a.prow = (const int32_t *)(w + L->off_prow); a.sub = (const int2 *)(w + L->off_sub); a.sub2 = (const int2 *)(w + L->off_sub2);
+    a.head = (const unsigned long long *)(w + L->off_head);
+    a.counters = (int32_t *)(w + L->off_counters); a.pool = (uint32_t *)(w + L->off_pool);
+    a.recs = (int4 *)(w + L->off_recs); a.n_rec_cap = (long long)L->n_rec_cap;
+    a.prob_col = prob_col; a.ctx_t = ctx_t; a.bev = bev;
+    a.n_cons = 4 * rp_num_sms();                          // one warp per shared voxel, 4 warps per CTA
+    const size_t smem = fwd_columns_smem(p, a.n_zero > 0);
+    if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
+    // The grid is launched programmatically only behind the prologue of the same call (wait_ready): a grid that starts while
+    // SMs are still full gets its first CTAs -- zero CTAs, in the one-launch form -- wherever room appears.
+    if (p->C == 32) return launch_fwd_kernel<4>(d, a, smem, wait_ready, s);
+    if (p->C == 64) return launch_fwd_kernel<8>(d, a, smem, wait_ready, s);
+    return launch_fwd_kernel<16>(d, a, smem, wait_ready, s);
+}
+
+static int fwd_args_ok(const lss_problem *p, const lss_runplan_layout *L, const void *workspace, const float *prob_col,
+                       const float *ctx_t, const float *bev) {
     int st = runplan_supported(p);
     if (st != LSS_OK) return st;
     LSS_REQUIRE(L && workspace, LSS_ERR_WORKSPACE);
     LSS_REQUIRE(prob_col && ctx_t && bev, LSS_ERR_BAD_ARG);
     LSS_REQUIRE(lss_aligned(ctx_t, 16) && lss_aligned(bev, 16), LSS_ERR_ALIGN);
-    const Dims d = make_dims(p);
-    LSS_REQUIRE(L->n_points == d.n_points, LSS_ERR_WORKSPACE);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!precleared) {
-        st = launch_bev_zero(bev, (size_t)L->n_voxels * p->C * 4, s);
-        if (st != LSS_OK) return st;
-    }
-    const size_t smem = gather_cl_smem(p);
-    if (smem > 48 * 1024) return LSS_ERR_UNSUPPORTED;
-    const char *w = (const char *)workspace;
-    const int n_keys = p->B * p->N * p->fW;
-    const int grid = n_keys + 2 * rp_num_sms();
-    const unsigned long long mfH = ((1ull << 40) + (unsigned)p->fH - 1) / (unsigned)p->fH;
-#define GCL_ARGS d, n_keys, mfH, (const int32_t *)(w + L->off_prow), (const uint32_t *)(w + L->off_emask),                \
-                 (const int32_t *)(w + L->off_counters), (const int4 *)(w + L->off_mixed_recs), (long long)L->n_mixed_cap, \
-                 (uint32_t *)(const_cast<char *>(w) + L->off_pool), (const int2 *)(w + L->off_sub), p->fW * p->D, prob_col, ctx_t, bev
-    cudaError_t e;
-    if (p->C == 32) e = lss_launch(k_fwd_gather_cl<4>, dim3(grid), dim3(GCL_THREADS), smem, s, false, GCL_ARGS);
-    else if (p->C == 64) e = lss_launch(k_fwd_gather_cl<8>, dim3(grid), dim3(GCL_THREADS), smem, s, false, GCL_ARGS);
-    else e = lss_launch(k_fwd_gather_cl<16>, dim3(grid), dim3(GCL_THREADS), smem, s, false, GCL_ARGS);
-#undef GCL_ARGS
-    if (e != cudaSuccess) return LSS_ERR_CUDA;
-    LSS_CHECK_LAUNCH();
+    LSS_REQUIRE(L->n_points == (int64_t)p->B * p->N * p->D * p->fH * p->fW, LSS_ERR_WORKSPACE);
     return LSS_OK;
+}
+
+extern "C" int lss_liftsplat_fwd_cl(const lss_problem *p, const lss_runplan_layout *L, void *workspace,
+                                    const float *prob_col, const float *ctx_t, float *bev, int zero_mode, void *stream) {
+    int st = fwd_args_ok(p, L, workspace, prob_col, ctx_t, bev);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(zero_mode == LSS_ZERO_ORDERED || zero_mode == LSS_ZERO_PRECLEARED, LSS_ERR_BAD_ARG);
+    int n_zero = 0;
+    if (zero_mode == LSS_ZERO_ORDERED) n_zero = zero_tune((size_t)p->nx * p->ny * p->nz * p->C * 4).n_cta;
+    return launch_fwd_grid(p, L, workspace, prob_col, ctx_t, bev, n_zero, true, false, (cudaStream_t)stream);
+}
+
+extern "C" int lss_liftsplat_forward(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                                     const float *post_trans, const float *M1, const float *M2, const float *trans,
+                                     const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
+                                     float *prob, float *ctx_t, float *prob_col, float *bev, void *stream) {
+    int st = fwd_args_ok(p, L, workspace, prob_col, ctx_t, bev);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(depthnet_out != nullptr, LSS_ERR_BAD_ARG);
+    st = prologue_validate(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,
+                           prob_col, nullptr, true);      // before anything is launched: a zero-fill without its consumer
+    if (st != LSS_OK) return st;                          // would leave the progress counters raised
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t seg_bytes = (size_t)p->nx * p->ny * p->nz * p->C * 4;
+    const ZeroTune t = zero_tune(seg_bytes);
+    k_zero_flags<<<t.n_cta, 32, ZERO_CHUNK, s>>>(bev, seg_bytes, p->B, (int32_t *)((char *)workspace + L->off_zero_done), t.chunk, t.window);
+    LSS_CHECK_LAUNCH();
+    st = prologue_checked(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,
+                          prob_col, nullptr, true, stream);
+    if (st != LSS_OK) return st;
+    return launch_fwd_grid(p, L, workspace, prob_col, ctx_t, bev, t.n_cta, false, true, s);
 }
 
 extern "C" int lss_liftsplat_bwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,

@@ -39,23 +39,18 @@ def _fused_get_voxels(self, x, rots, trans, intrins, post_rots, post_trans):
 def lift_splat_from_depthnet(model, depthnet_out, rots, trans, intrins, post_rots, post_trans, plan=None):
     """Geometry + lift + splat for a depthnet output [B*N, D+C, fH, fW] -> BEV [B, nz*C, nx, ny].
 
-    `bev_channels_last` + `splat_mode="sorted"` take the run-plan path (ops.RunPlan): the BEV is zero-filled by the
-    bulk-copy kernel on a side stream while the plan is built, then every non-empty voxel row is written once."""
+    `bev_channels_last` + `splat_mode="sorted"` take the run-plan path (ops.RunPlan, ops.liftsplat_forward): the BEV is
+    zero-filled by the bulk-copy engine while the plan is built and the voxels are summed; every non-empty voxel row is
+    written once."""
     B, N = trans.shape[:2]
     fH, fW = depthnet_out.shape[-2:]
     C = depthnet_out.shape[1] - model.D
     prob = _problem_for(model, B, N, fH, fW, C)
     mode = getattr(model, "splat_mode", "sorted")
     if plan is None and _use_runplan(model, prob):
-        dev = depthnet_out.device
-        cur, side = torch.cuda.current_stream(dev), _side_stream(model, dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            bev = ops.bev_zero(prob, dev)
-        plan = runplan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans)
-        cur.wait_stream(side)
-        bev.record_stream(cur)
-        return ops.lift_splat(depthnet_out, prob, plan, mode, True, bev_out=bev)
+        ws = _cached_plan(model, prob, depthnet_out.device, run=True)
+        build = runplan_build_args(model, prob, rots, trans, intrins, post_rots, post_trans)
+        return ops.lift_splat(depthnet_out, prob, ws, mode, True, build=build)     # ops.liftsplat_forward: plan + lift + forward
     if plan is None:
         plan = plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans)
     return ops.lift_splat(depthnet_out, prob, plan, mode, getattr(model, "bev_channels_last", False))
@@ -66,32 +61,24 @@ def _use_runplan(model, prob):
             and ops.runplan_supported(prob))
 
 
-def _side_stream(model, device):
-    streams = model.__dict__.setdefault("_lss_side_streams", {})
-    key = str(device)
-    if key not in streams:
-        streams[key] = torch.cuda.Stream(device=device)
-    return streams[key]
+def runplan_build_args(model, prob, rots, trans, intrins, post_rots, post_trans):
+    """Calibration arguments of ops.build_runplan / ops.liftsplat_prologue for the batch of `forward` (models.py:256).
+    inverse_mode "reference": M1/M2 from the reference's own torch calls (bit-identical geometry); "device": closed-form
+    inverses inside the kernel, no host round trip (tiny cameras, where a CTA would span too many of them: separate kernel)."""
+    args = dict(frustum=model.frustum.detach(), trans=trans.reshape(-1, 3), post_trans=post_trans.reshape(-1, 3))
+    if getattr(model, "inverse_mode", "reference") == "device":
+        if ops.runplan_raw_supported(prob):
+            return dict(args, rots=rots, intrins=intrins, post_rots=post_rots)
+        M1, M2 = ops.calib_matrices_device(rots, intrins, post_rots)
+    else:
+        M1, M2 = ops.calib_matrices_reference(rots, intrins, post_rots)
+    return dict(args, M1=M1.reshape(-1, 3, 3), M2=M2.reshape(-1, 3, 3))
 
 
 def runplan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans):
-    """Run plan (voxel row per point, exclusive runs, shared-voxel queue) from the calibration of `forward`
-    (models.py:256).  inverse_mode "reference": M1/M2 from the reference's own torch calls (bit-identical geometry);
-    "device": closed-form inverses inside the kernel, no host round trip."""
+    """Run plan (voxel row per point, sub-run lists per voxel) from the calibration of `forward` (models.py:256)."""
     ws = _cached_plan(model, prob, rots.device, run=True)
-    frustum = model.frustum.detach()
-    if getattr(model, "inverse_mode", "reference") == "device":
-        try:
-            return ops.build_runplan(prob, frustum, trans.reshape(-1, 3), post_trans.reshape(-1, 3), rots=rots, intrins=intrins,
-                                     post_rots=post_rots, plan=ws)
-        except RuntimeError as e:                  # tiny cameras: a CTA would span too many of them for the fused inverses
-            if "status -3" not in str(e):
-                raise
-            M1, M2 = ops.calib_matrices_device(rots, intrins, post_rots)
-    else:
-        M1, M2 = ops.calib_matrices_reference(rots, intrins, post_rots)
-    return ops.build_runplan(prob, frustum, trans.reshape(-1, 3), post_trans.reshape(-1, 3), M1=M1.reshape(-1, 3, 3),
-                             M2=M2.reshape(-1, 3, 3), plan=ws)
+    return ops.build_runplan(prob, plan=ws, **runplan_build_args(model, prob, rots, trans, intrins, post_rots, post_trans))
 
 
 def plan_from_calibration(model, prob, rots, trans, intrins, post_rots, post_trans):

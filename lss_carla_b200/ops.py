@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 
-from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, VARIANTS, LssPlanLayout, LssProblem, LssRunplanLayout, check,
+from ._lib import (LAYOUT_CHANNELS_LAST, LAYOUT_NCHW, SPLAT_MODES, VARIANTS, ZERO_ORDERED, ZERO_PRECLEARED, LssPlanLayout, LssProblem, LssRunplanLayout, check,
                    lib)
 
 
@@ -363,14 +363,20 @@ def runplan_supported(prob: Problem) -> bool:
     return lib().lss_runplan_layout_init(C.byref(prob.c), C.byref(lay)) == 0
 
 
+def runplan_raw_supported(prob: Problem) -> bool:
+    """Whether build_runplan / liftsplat_prologue take the raw calibration (closed-form inverses inside the index kernel)."""
+    return lib().lss_runplan_raw_supported(C.byref(prob.c)) == 0
+
+
 class RunPlan:
-    """Per-batch index structures of the channels_last path: voxel row per point, exclusive-run masks, shared-voxel queue."""
+    """Per-batch index structures of the channels_last path: voxel row per point, sub-run nodes, per-voxel list heads.
+    The forward only reads them (its scratch -- progress counters, pool -- is left clean), so a built plan can be kept."""
 
     def __init__(self, prob: Problem, device):
         self.prob = prob
         self.layout = LssRunplanLayout()
         check(lib().lss_runplan_layout_init(C.byref(prob.c), C.byref(self.layout)), "lss_runplan_layout_init")
-        self.ws = torch.zeros(self.layout.bytes, dtype=torch.uint8, device=device)   # scratch grids start at 0
+        self.ws = torch.zeros(self.layout.bytes, dtype=torch.uint8, device=device)   # epoch 0, empty lists
         self.built = False
         self.busy = False
         self.generation = 0
@@ -386,26 +392,54 @@ class RunPlan:
         return self._view(self.layout.off_prow, p.n_points, torch.int32).view(p.B, p.N, p.fW, p.D, p.fH)
 
     @property
-    def emask(self):
+    def sub(self):
+        """int32[B, N, fW, D, fH, 2]: at the first point of a sub-run {previous sub-run on the voxel's list (flat
+        camera-column-major point index + 1, 0 = none), image-row mask}; {0, 0} elsewhere."""
         p = self.prob
-        return self._view(self.layout.off_emask, p.n_points, torch.int32).view(p.B, p.N, p.fW, p.D, p.fH)
+        return self._view(self.layout.off_sub, 2 * p.n_points, torch.int32).view(p.B, p.N, p.fW, p.D, p.fH, 2)
+
+    @property
+    def head(self):
+        """int64[n_voxels]: (build epoch << 32) | (point index + 1) of the last sub-run pushed on the voxel's list."""
+        return self._view(self.layout.off_head, self.layout.n_voxels, torch.int64)
 
     @property
     def counters(self):
-        """int32[3]: shared voxels below 64 points, pool slots in use, shared voxels with >= 64 points."""
-        return self._view(self.layout.off_counters, 3, torch.int32)
-
-    def shared_voxels(self):
-        """int32[n, 4] records {list head or pool slot, points, voxel row, batch} of the voxels that hold points of several
-        sub-runs (short ones first, then the >= 64-point ones); reads the counters (synchronises)."""
-        n_short, _, n_long = self.counters.cpu().tolist()
-        recs = self._view(self.layout.off_mixed_recs, self.layout.n_mixed_cap * 4, torch.int32).view(-1, 4)
-        return torch.cat((recs[:n_short], recs[recs.shape[0] - n_long:]))
+        """int32[8]: [0] epoch of the last build, [1..5] scratch (zero between launches), [6] / [7] voxels shared by several
+        sub-runs / voxels with >= 64 points met by the last forward."""
+        return self._view(self.layout.off_counters, 8, torch.int32)
 
     @property
     def scratch(self):
-        """The per-voxel scratch grids (all-zero between builds)."""
-        return self.ws[self.layout.off_cnt:]
+        """What a forward uses as scratch (all-zero between launches): counters [1..5], the zero-fill progress counters and
+        the READY flags."""
+        n = (self.layout.off_head - self.layout.off_zero_done) // 4
+        return torch.cat((self.counters[1:6], self._view(self.layout.off_zero_done, n, torch.int32)))
+
+    def lists(self):
+        """The per-voxel lists of the current build as numpy arrays (synchronises; tests): (rows, points) -- for every
+        sub-run on a list of this epoch, the voxel row it belongs to and its number of points -- plus the number of voxels
+        whose list holds more than one sub-run."""
+        import numpy as np
+        sub = self.sub.reshape(-1, 2).cpu().numpy()
+        prow = self.prow.reshape(-1).cpu().numpy()
+        head = self.head.cpu().numpy()
+        epoch = int(self.counters[0])
+        live = np.flatnonzero((head >> 32) == epoch)
+        cur = (head[live] & 0xFFFFFFFF).astype(np.int64)
+        rows, pts, nodes = [], [], np.zeros(live.size, dtype=np.int64)
+        voxel = live.copy()
+        while cur.size:
+            node = sub[cur - 1]
+            assert (node[:, 1] != 0).all() and (prow[cur - 1] == voxel).all()
+            rows.append(voxel)
+            pts.append(np.array([bin(int(m) & 0xFFFFFFFF).count("1") for m in node[:, 1]], dtype=np.int64))
+            keep = node[:, 0] != 0
+            cur, voxel = node[keep, 0].astype(np.int64), voxel[keep]
+        rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+        pts = np.concatenate(pts) if pts else np.zeros(0, np.int64)
+        n_shared = int((np.bincount(rows, minlength=1) > 1).sum()) if rows.size else 0
+        return rows, pts, n_shared
 
     def reset(self):
         check(lib().lss_runplan_reset(C.byref(self.layout), _ptr(self.ws), _stream()), "lss_runplan_reset")
@@ -432,12 +466,8 @@ def build_runplan(prob: Problem, frustum, trans, post_trans, M1=None, M2=None, r
     return plan
 
 
-@_nvtx("lss:prologue(zero+lift+index)")
-def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None, plan: RunPlan | None = None, frustum=None, trans=None,
-                       post_trans=None, M1=None, M2=None, rots=None, intrins=None, post_rots=None):
-    """Fused prologue of a step in ONE launch (+ classify): zero-fill of `bev` (channels_last; None: off), run plan from the
-    calibration (`plan` and `frustum` given; arguments as build_runplan) and lift operands of `depthnet_out` (float32; None: off)
-    as independent CTA roles of one grid.  Returns (pr, ct) of the lift (or None).  Then: splat_fwd_cl(..., out=bev, precleared=True)."""
+def _prologue_args(prob: Problem, depthnet_out, lift_out, plan, frustum, trans, post_trans, M1, M2, rots, intrins, post_rots):
+    """ctypes arguments shared by lss_liftsplat_prologue / lss_liftsplat_forward: (calibration x8, lift x4), (pr, ct), keepalive."""
     null = C.c_void_p(0)
     build = plan is not None and frustum is not None
     cal = [null] * 8
@@ -461,15 +491,46 @@ def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None
             torch.empty((BN, HW, prob.C), dtype=torch.float32, device=x.device))
         lift_args, res = [_ptr(x), _ptr(both[0]), _ptr(ct), _ptr(both[1])], (both[0], ct)
         keep.append(x)
+    return build, cal + lift_args, res, keep
+
+
+@_nvtx("lss:prologue(lift+index)")
+def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None, plan: RunPlan | None = None, frustum=None, trans=None,
+                       post_trans=None, M1=None, M2=None, rots=None, intrins=None, post_rots=None):
+    """Fused prologue in ONE launch: run plan from the calibration (`plan` and `frustum` given; arguments as build_runplan),
+    lift operands of `depthnet_out` (float32; None: off) and, optionally, a zero-fill of `bev` (channels_last; None: off) as
+    independent CTA roles of one grid.  Returns (pr, ct) of the lift (or None).
+    Then: splat_fwd_cl(..., out=bev), with precleared=True if `bev` was zero-filled here.  (liftsplat_forward does it all.)"""
+    build, args, res, keep = _prologue_args(prob, depthnet_out, lift_out, plan, frustum, trans, post_trans, M1, M2, rots, intrins, post_rots)
     if bev is not None and not bev.is_contiguous(memory_format=torch.channels_last):
         raise RuntimeError("liftsplat_prologue zero-fills channels_last tensors only")
     lay = C.byref(plan.layout) if plan is not None else None
-    check(lib().lss_liftsplat_prologue(C.byref(prob.c), lay, _ptr(plan.ws) if plan is not None else null, *cal, *lift_args,
+    check(lib().lss_liftsplat_prologue(C.byref(prob.c), lay, _ptr(plan.ws) if plan is not None else C.c_void_p(0), *args,
                                        _ptr(bev), _stream()), "lss_liftsplat_prologue")
     if build:
         plan.built, plan._keepalive = True, keep
         plan.generation += 1
     return res
+
+
+@_nvtx("lss:forward(zero || lift+index || classify+gather)")
+def liftsplat_forward(prob: Problem, plan: RunPlan, depthnet_out, lift_out=None, out=None, frustum=None, trans=None, post_trans=None,
+                      M1=None, M2=None, rots=None, intrins=None, post_rots=None):
+    """The whole forward of a step (lss_liftsplat_forward): three launches that run side by side -- zero-fill with progress
+    counters, lift || plan build, classify + gather polling both.  `frustum` None: the plan in `plan` is kept (static calibration).
+    Returns (bev, pr, ct); `bev` is channels_last, the same bits as splat_fwd(mode="sorted")."""
+    build, args, res, keep = _prologue_args(prob, depthnet_out, lift_out, plan, frustum, trans, post_trans, M1, M2, rots, intrins, post_rots)
+    if not build and not plan.built:
+        raise RuntimeError("liftsplat_forward without calibration needs a built plan")
+    bev = out if out is not None else _empty_bev(prob, depthnet_out.device, True)
+    if not bev.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("liftsplat_forward writes channels_last tensors only")
+    check(lib().lss_liftsplat_forward(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), *args, _ptr(bev), _stream()),
+          "lss_liftsplat_forward")
+    if build:
+        plan.built, plan._keepalive = True, keep
+        plan.generation += 1
+    return bev, res[0], res[1]
 
 
 @_nvtx("lss:bev_zero")
@@ -481,9 +542,10 @@ def bev_zero(prob: Problem, device, out=None, part=0, n_parts=1):
     return bev
 
 
-@_nvtx("lss:splat_fwd_cl")
+@_nvtx("lss:splat_fwd_cl(zero+classify+gather)")
 def splat_fwd_cl(prob: Problem, plan: RunPlan, pr, ct, out=None, precleared=False):
-    """Deterministic forward into a channels_last BEV tensor: same bits as splat_fwd(mode="sorted")."""
+    """Deterministic forward into a channels_last BEV tensor from an existing plan and existing lift operands, ONE launch
+    (zero-fill + classify + gather): same bits as splat_fwd(mode="sorted").  `precleared`: `out` is already all-zero."""
     pc = _prob_col(pr)
     if pc is None:
         raise RuntimeError("splat_fwd_cl needs the (prob, ctx) pair of lift_prepare (column-major weights)")
@@ -491,7 +553,7 @@ def splat_fwd_cl(prob: Problem, plan: RunPlan, pr, ct, out=None, precleared=Fals
     if not bev.is_contiguous(memory_format=torch.channels_last):
         raise RuntimeError("splat_fwd_cl writes channels_last tensors only")
     check(lib().lss_liftsplat_fwd_cl(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pc), _ptr(ct), _ptr(bev),
-                                     1 if precleared else 0, _stream()), "lss_liftsplat_fwd_cl")
+                                     ZERO_PRECLEARED if precleared else ZERO_ORDERED, _stream()), "lss_liftsplat_fwd_cl")
     return bev
 
 
@@ -523,11 +585,17 @@ class _LiftSplatFn(torch.autograd.Function):
     """depthnet output [B*N, D+C, fH, fW] -> BEV [B, nz*C, nx, ny]; backward = fused gather."""
 
     @staticmethod
-    def forward(ctx, depthnet_out, prob, plan, mode, channels_last, bev_out):
-        pr, ct = lift_prepare(prob, depthnet_out)
+    def forward(ctx, depthnet_out, prob, plan, mode, channels_last, bev_out, build):
         if isinstance(plan, RunPlan):
-            bev = splat_fwd_cl(prob, plan, pr, ct, out=bev_out, precleared=bev_out is not None)
+            if depthnet_out.dtype == torch.float32 and bev_out is None:    # the whole forward, plan build included
+                bev, pr, ct = liftsplat_forward(prob, plan, depthnet_out, **(build or {}))
+            else:
+                if build:
+                    build_runplan(prob, plan=plan, **build)
+                pr, ct = lift_prepare(prob, depthnet_out)
+                bev = splat_fwd_cl(prob, plan, pr, ct, out=bev_out, precleared=bev_out is not None)
         else:
+            pr, ct = lift_prepare(prob, depthnet_out)
             bev = splat_fwd(prob, plan, pr, ct, mode, channels_last)
         ctx.prob, ctx.plan, ctx.in_dtype, ctx.generation = prob, plan, depthnet_out.dtype, plan.generation
         ctx.save_for_backward(pr, ct, _prob_col(pr))
@@ -549,14 +617,18 @@ class _LiftSplatFn(torch.autograd.Function):
         ctx.plan.busy = False
         if ctx.in_dtype != torch.float32:          # bfloat16 input: the float32 gradient is rounded once, at the very end
             out = out.to(ctx.in_dtype)
-        return out, None, None, None, None, None
+        return out, None, None, None, None, None, None
 
 
-def lift_splat(depthnet_out, prob: Problem, plan, mode="sorted", channels_last=False, bev_out=None):
+def lift_splat(depthnet_out, prob: Problem, plan, mode="sorted", channels_last=False, bev_out=None, build=None):
     """Fused lift + splat of the depthnet output through an existing plan (differentiable w.r.t.
     `depthnet_out`; geometry carries no gradient, tools.py:207).  `plan`: a tile `Plan`, or a `RunPlan`
-    (deterministic, channels_last output; `bev_out`: optional pre-zeroed output from `bev_zero`)."""
-    return _LiftSplatFn.apply(depthnet_out, prob, plan, mode, channels_last, bev_out)
+    (deterministic, channels_last output; `bev_out`: optional pre-zeroed output from `bev_zero`; `build`: the
+    calibration arguments of `build_runplan` as a dict -- the plan is then (re)built in the same launch as the lift
+    operands; None: `plan` is used as it is)."""
+    if build is not None and not isinstance(plan, RunPlan):
+        raise RuntimeError("lift_splat(build=...) needs a RunPlan")
+    return _LiftSplatFn.apply(depthnet_out, prob, plan, mode, channels_last, bev_out, build)
 
 
 class _VoxelPoolingFn(torch.autograd.Function):

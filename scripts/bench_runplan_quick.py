@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Quick per-kernel and whole-step timing of the run-plan path at one workload (development aid; bench.py is the record).
 
-    python scripts/bench_runplan_quick.py [cfg2] [iters]
+    [LSS_TIMELINE=1] python scripts/bench_runplan_quick.py [cfg2] [iters]
 Each item is captured as one CUDA graph per rotating buffer set (4 sets > L2) and replayed back to back."""
 import json
 import os
@@ -11,7 +11,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from lss_carla_b200 import ops  # noqa: E402
+from lss_carla_b200 import _lib, ops  # noqa: E402
+
+if os.environ.get("LSS_TIMELINE"):      # a second build with globaltimer stamps inside the kernels
+    _lib.SO_PATH = _lib.build_library(out=os.path.join(ROOT, "lss_carla_b200", "liblss_b200_timeline.so"), defines=("LSS_RP_TIMELINE",))
+    _lib._lib = None
 from lss_carla_b200.synthetic import CONFIGS, make_batch, make_bev_grad  # noqa: E402
 from lss_carla_b200.tools import gen_dx_bx  # noqa: E402
 
@@ -44,12 +48,13 @@ def main():
         s.bev = torch.empty(prob.bev_shape, device=dev).contiguous(memory_format=torch.channels_last)
         s.grad = torch.empty_like(s.dn)
         s.lift = (torch.empty((2, prob.B * prob.N, prob.D, fH, fW), device=dev), torch.empty((prob.B * prob.N, fH * fW, prob.C), device=dev))
-        s.s1, s.s2 = torch.cuda.Stream(), torch.cuda.Stream()
         sets.append(s)
 
+    cal_args = lambda s: dict(trans=s.cal["trans"].reshape(-1, 3), post_trans=s.cal["post_trans"].reshape(-1, 3), rots=s.cal["rots"],  # noqa: E731
+                              intrins=s.cal["intrins"], post_rots=s.cal["post_rots"])
+
     def plan(s):
-        ops.build_runplan(prob, fr, s.cal["trans"].reshape(-1, 3), s.cal["post_trans"].reshape(-1, 3), rots=s.cal["rots"],
-                          intrins=s.cal["intrins"], post_rots=s.cal["post_rots"], plan=s.rp)
+        ops.build_runplan(prob, fr, plan=s.rp, **cal_args(s))
 
     def lift(s):
         s.pr, s.ct = ops.lift_prepare(prob, s.dn, out=s.lift)
@@ -57,95 +62,39 @@ def main():
     def zero(s):
         ops.bev_zero(prob, dev, out=s.bev)
 
-    def gather(s):
+    def fwd_precleared(s):       # classify + gather alone (timing only: the tensor is not cleared)
         ops.splat_fwd_cl(prob, s.rp, s.pr, s.ct, out=s.bev, precleared=True)
 
-    def fwd_serial(s):
-        ops.splat_fwd_cl(prob, s.rp, s.pr, s.ct, out=s.bev, precleared=False)
+    def fwd_ordered(s):          # one launch from an existing plan: zero CTAs + classify + gather
+        ops.splat_fwd_cl(prob, s.rp, s.pr, s.ct, out=s.bev)
 
     def bwd(s):
         ops.splat_bwd_cl(prob, s.rp, s.gb, s.pr, s.ct, out=s.grad)
 
-    def fwd_op(s):            # zero || lift, then gather (plan cached)
-        cur = torch.cuda.current_stream()
-        s.s1.wait_stream(cur)
-        with torch.cuda.stream(s.s1):
-            zero(s)
-        lift(s)
-        cur.wait_stream(s.s1)
-        gather(s)
+    def prologue(s):             # lift + plan, no zero-fill
+        s.pr, s.ct = ops.liftsplat_prologue(prob, s.dn, s.lift, None, s.rp, fr, **cal_args(s))
 
-    def step(s, upto=3):
-        cur = torch.cuda.current_stream()
-        s.s1.wait_stream(cur)
-        s.s2.wait_stream(cur)
-        with torch.cuda.stream(s.s1):
-            zero(s)
-        with torch.cuda.stream(s.s2):
-            lift(s)
-        plan(s)
-        cur.wait_stream(s.s1)
-        cur.wait_stream(s.s2)
+    def forward(s):              # lss_liftsplat_forward: zero-fill || lift || plan -> classify + gather
+        if os.environ.get("QUICK_NOZERO"):       # measurement: the same chain without any zero-fill traffic
+            prologue(s)
+            fwd_precleared(s)
+            return
+        _, s.pr, s.ct = ops.liftsplat_forward(prob, s.rp, s.dn, s.lift, s.bev, fr, **cal_args(s))
+
+    def forward_kept(s):
+        _, s.pr, s.ct = ops.liftsplat_forward(prob, s.rp, s.dn, s.lift, s.bev)
+
+    if os.environ.get("QUICK_PDL") == "0":
+        ops.set_option("pdl", 0)
+
+    def step(s, upto=2):
+        forward(s)
         if upto >= 2:
-            gather(s)
-        if upto >= 3:
             bwd(s)
 
-    NP = int(os.environ.get("ZPARTS", "2"))
-
-    def step_split(s, upto=3):
-        """zero slices chained on a side stream; slice k+1 starts when slice k AND the k-th plan kernel are done"""
-        cur = torch.cuda.current_stream()
-        s.s1.wait_stream(cur)
-        s.s2.wait_stream(cur)
-        with torch.cuda.stream(s.s2):
-            lift(s)
-        with torch.cuda.stream(s.s1):
-            ops.bev_zero(prob, dev, out=s.bev, part=0, n_parts=NP)
-        plan(s)
-        with torch.cuda.stream(s.s1):
-            for k in range(1, NP):
-                ops.bev_zero(prob, dev, out=s.bev, part=k, n_parts=NP)
-        cur.wait_stream(s.s1)
-        cur.wait_stream(s.s2)
-        if upto >= 2:
-            gather(s)
-        if upto >= 3:
-            bwd(s)
-
-    def prologue(s):
-        s.pr, s.ct = ops.liftsplat_prologue(prob, s.dn, s.lift, s.bev, s.rp, fr, s.cal["trans"].reshape(-1, 3), s.cal["post_trans"].reshape(-1, 3),
-                                            rots=s.cal["rots"], intrins=s.cal["intrins"], post_rots=s.cal["post_rots"])
-
-    def prologue_cached(s):      # plan cached: zero + lift only
-        s.pr, s.ct = ops.liftsplat_prologue(prob, s.dn, s.lift, s.bev)
-
-    def fused_step(s, upto=3):
-        prologue(s)
-        if upto >= 2:
-            gather(s)
-        if upto >= 3:
-            bwd(s)
-
-    def fused_fwd_cached(s):
-        prologue_cached(s)
-        gather(s)
-
-    def pair(a, b=None, c=None):
-        def f(s):
-            cur = torch.cuda.current_stream()
-            s.s1.wait_stream(cur)
-            with torch.cuda.stream(s.s1):
-                a(s)
-            if c is not None:
-                s.s2.wait_stream(cur)
-                with torch.cuda.stream(s.s2):
-                    c(s)
-                cur.wait_stream(s.s2)
-            if b is not None:
-                b(s)
-            cur.wait_stream(s.s1)
-        return f
+    def step_kept(s):
+        forward_kept(s)
+        bwd(s)
 
     def timeit(fn):
         for s in sets:
@@ -174,16 +123,14 @@ def main():
         step(s)
     torch.cuda.synchronize()
     res = {"workload": name}
-    for nm, fn in (("plan", plan), ("lift", lift), ("zero", zero), ("gather", gather), ("fwd_serial(zero+gather)", fwd_serial),
-                   ("fwd_op(zero||lift->gather)", fwd_op), ("bwd", bwd), ("zero||plan", pair(zero, plan)), ("zero||lift", pair(zero, lift)),
-                   ("lift||plan", pair(lift, plan)), ("zero||gather", pair(zero, gather)), ("zero||bwd", pair(zero, bwd)), ("zero_side_only", pair(zero)), ("step_upto_plan", lambda s: step(s, 1)),
-                   ("step_upto_fwd", lambda s: step(s, 2)), ("step", step), ("prologue", prologue), ("prologue_cached(zero+lift)", prologue_cached), ("fused_upto_fwd", lambda s: fused_step(s, 2)),
-                   ("fused_fwd_cached", fused_fwd_cached), ("fused_step", fused_step)):
+    for nm, fn in (("plan", plan), ("lift", lift), ("zero", zero), ("prologue(lift+plan)", prologue), ("fwd_precleared", fwd_precleared),
+                   ("fwd_ordered", fwd_ordered), ("bwd", bwd), ("forward", forward), ("forward_kept_plan", forward_kept), ("step", step),
+                   ("step_kept_plan", step_kept)):
         res[nm + "_us"] = round(timeit(fn), 2)
-    res["mpoints_per_s"] = round(cfg.points / res["fused_step_us"], 1)
+    res["mpoints_per_s"] = round(cfg.points / res["step_us"], 1)
+    res["counters"] = sets[0].rp.counters.cpu().tolist()
     # timeline of one step in the rotating (L2-cold) regime: globaltimer stamps inside the kernels
     import ctypes as C
-    from lss_carla_b200 import _lib
     L = _lib.lib()
     if not hasattr(L, "lss_debug_runplan_timeline"):          # library built without -DLSS_RP_TIMELINE
         print(json.dumps(res))
@@ -195,7 +142,7 @@ def main():
     for s in sets:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            fused_step(s)
+            step(s)
         graphs.append(g)
     for i in range(12):
         graphs[i % 4].replay()
@@ -203,11 +150,22 @@ def main():
     L.lss_debug_runplan_timeline(1, None)
     graphs[0].replay()
     torch.cuda.synchronize()
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 10)()
     L.lss_debug_runplan_timeline(0, out)
-    t0 = min(out[0], out[2])
-    res["timeline_us"] = {nm: [round((out[2 * k] - t0) / 1e3, 1), round((out[2 * k + 1] - t0) / 1e3, 1)] for k, nm in enumerate(("zero", "index", "classify", "gather_col"))}
-    res["counters"] = sets[0].rp.counters.cpu().tolist()
+    t0 = min(out[2], out[4])
+    res["timeline_us"] = {nm: [round((out[2 * k] - t0) / 1e3, 1), round((out[2 * k + 1] - t0) / 1e3, 1)]
+                          for k, nm in enumerate(("zero", "index", "lift", "fwd_columns", "fwd_shared"))}
+    if hasattr(L, "lss_debug_runplan_marks"):    # phase stamps of the forward's column CTAs (thread 0): after READY, staged, after the
+        n = prob.B * prob.N * prob.fW            # zero wait, exclusive loop done, barrier, shared voxels done
+        m = (C.c_ulonglong * (8 * n))()
+        L.lss_debug_runplan_marks.argtypes = [C.c_void_p, C.c_int]
+        L.lss_debug_runplan_marks(m, n)
+        import numpy as np
+        mk = (np.array(m, dtype=np.float64).reshape(n, 8)[:, :4] - float(t0)) / 1e3
+        names = ("start", "staged", "zero_ok", "excl_done")
+        res["column_cta_marks_us"] = {nm: [round(float(np.percentile(mk[:, k], q)), 1) for q in (0, 50, 90, 100)] for k, nm in enumerate(names)}
+        dur = np.diff(mk, axis=1)
+        res["column_cta_phase_us"] = {f"{names[k]}->{names[k + 1]}": [round(float(np.percentile(dur[:, k], q)), 1) for q in (50, 90, 100)] for k in range(3)}
     print(json.dumps(res))
 
 

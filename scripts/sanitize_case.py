@@ -35,12 +35,18 @@ for pdl in (1, 0):
             cal = {k: b[k].to(dev) for k in ("rots", "trans", "intrins", "post_rots", "post_trans")}
             dn = b["depthnet_out"].to(dev)
             gb = make_bev_grad(cfg, seed).to(dev)
-            # run plan: fused prologue, classify, gather, backward
-            bev = torch.empty(prob.bev_shape, device=dev).contiguous(memory_format=torch.channels_last)
-            pr, ct = ops.liftsplat_prologue(prob, dn, None, bev, rp, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3),
-                                            rots=cal["rots"], intrins=cal["intrins"], post_rots=cal["post_rots"])
-            ops.splat_fwd_cl(prob, rp, pr, ct, out=bev, precleared=True)
+            # run plan: two-launch forward (zero-fill || lift || index -> classify + gather), backward
+            bev = torch.full(prob.bev_shape, float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
+            _, pr, ct = ops.liftsplat_forward(prob, rp, dn, None, bev, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3),
+                                              rots=cal["rots"], intrins=cal["intrins"], post_rots=cal["post_rots"])
             g1 = ops.splat_bwd_cl(prob, rp, gb.contiguous(memory_format=torch.channels_last), pr, ct)
+            # ... and with the prologue's own zero role + a pre-cleared forward
+            bev1 = torch.full(prob.bev_shape, float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
+            ops.liftsplat_prologue(prob, None, None, bev1)
+            ops.splat_fwd_cl(prob, rp, pr, ct, out=bev1, precleared=True)
+            bev2 = torch.full(prob.bev_shape, float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
+            ops.splat_fwd_cl(prob, rp, pr, ct, out=bev2)           # zero CTAs inside the forward kernel
+            assert torch.equal(bev, bev1) and torch.equal(bev, bev2)
             # tile plan: voxel index, scatter, sort, lift, gather + store, gradient rows + gather; atomic and red modes
             ops.build_plan_raw(prob, fr, cal["rots"], cal["trans"], cal["intrins"], cal["post_rots"], cal["post_trans"], sorted=True, plan=tp)
             pr2, ct2 = ops.lift_prepare(prob, dn)

@@ -57,8 +57,10 @@ def test_runplan_layout_and_options_host_only(L):
     assert lay.n_points == cfg.points and lay.n_runs == cfg.points // cfg.fHW[0] and lay.n_voxels == 8 * 200 * 200
     offs = [getattr(lay, f[0]) for f in _lib.LssRunplanLayout._fields_ if f[0].startswith("off_")]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and offs[-1] < lay.bytes
-    assert lay.bytes - lay.off_counters >= 2 * 4 * lay.n_voxels       # the scratch grids sit at the end (lss_runplan_reset)
-    assert ops.runplan_supported(p)
+    assert lay.bytes - lay.off_head >= 8 * lay.n_voxels and lay.off_zero_done > lay.off_counters   # counters, progress, heads: the tail lss_runplan_reset clears
+    assert ops.runplan_supported(p) and ops.runplan_raw_supported(p)
+    tiny_cam = ops.Problem.from_grid(8, 6, 2, 4, 2, 64, *gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound))   # an index CTA would span 16 cameras
+    assert ops.runplan_supported(tiny_cam) and not ops.runplan_raw_supported(tiny_cam)
     odd = ops.Problem.from_grid(1, 1, 8, 40, 4, 64, *gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound))   # a run must fit a warp
     assert L.lss_runplan_layout_init(C.byref(odd.c), C.byref(lay)) == -3 and not ops.runplan_supported(odd)
     c48 = ops.Problem.from_grid(1, 1, 8, 8, 4, 48, *gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound))
@@ -69,6 +71,7 @@ def test_runplan_layout_and_options_host_only(L):
     assert L.lss_set_option(0, 1) == 0 and L.lss_set_option(7, 1) == -1
     null = C.c_void_p(0)
     assert L.lss_liftsplat_fwd_cl(C.byref(p.c), None, null, null, null, null, 0, null) == -5
+    assert L.lss_liftsplat_fwd_cl(C.byref(p.c), C.byref(lay), C.c_void_p(256), C.c_void_p(256), C.c_void_p(256), C.c_void_p(256), 3, null) == -1
     assert L.lss_bev_zero(C.byref(p.c), null, 0, 1, null) == -1
 
 

@@ -71,13 +71,13 @@ def test_runplan_whole_tensor_parity(case):
     vox = oracle_vox(g, cfg.B)
     # ---- integer results: voxel row of every point, exact
     assert np.array_equal(rp.prow.cpu().numpy(), rows_of_vox(vox, prob))
-    assert not rp.scratch.any()                                   # scratch grids clean themselves
-    # every kept point is covered exactly once: exclusive masks + shared-voxel pool
+    # every kept point sits on exactly one list (the voxel's), and the lists are as long as the oracle's voxel populations
     n_kept = int((vox >= 0).sum())
-    em = rp.emask.cpu().numpy().view(np.uint32)
-    n_excl = int(sum(bin(int(x)).count("1") for x in em[em != 0]))
-    shared = rp.shared_voxels().cpu().numpy()
-    assert n_excl + int(shared[:, 1].sum()) == n_kept and np.unique(shared[:, 2]).size == shared.shape[0]
+    rows, pts, n_shared = rp.lists()
+    assert int(pts.sum()) == n_kept
+    want_rows = rows_of_vox(vox, prob).reshape(-1)
+    want_cnt = np.bincount(want_rows[want_rows >= 0], minlength=prob.n_voxels)
+    assert np.array_equal(np.bincount(rows, weights=pts, minlength=prob.n_voxels).astype(np.int64), want_cnt)
     # ---- forward: whole tensor, bit-exact against the sequential definition and against the tile-plan path
     dn = (torch.from_numpy(g["depthnet_out"]) if "depthnet_out" in g else make_depthnet_out(cfg, seed)).to(dev())
     pr, ct = ops.lift_prepare(prob, dn)
@@ -89,9 +89,17 @@ def test_runplan_whole_tensor_parity(case):
                                       cu(g["M2"]).reshape(-1, 3, 3), cu(g["trans"]).reshape(-1, 3)), sorted=True)
     assert torch.equal(bev.contiguous(), ops.splat_fwd(prob, tp, pr, ct, "sorted", False))
     # pre-zeroed output issued separately (what the model path does on a side stream)
+    assert not rp.scratch.any()                                   # the forward leaves its scratch clean
+    assert int(rp.counters[6]) == n_shared                        # voxels that went through the list walk
     z = ops.bev_zero(prob, dev())
     assert not z.any()
     assert torch.equal(ops.splat_fwd_cl(prob, rp, pr, ct, out=z, precleared=True), bev)
+    z.fill_(float("nan"))                                         # the two-launch forward on the kept plan, then with a rebuild
+    assert torch.equal(ops.liftsplat_forward(prob, rp, dn, out=z)[0], bev)
+    z.fill_(float("nan"))
+    out, pr2, ct2 = ops.liftsplat_forward(prob, rp, dn, None, z, cu(g["frustum"]), cu(g["trans"]).reshape(-1, 3),
+                                          cu(g["post_trans"]).reshape(-1, 3), M1=cu(g["M1"]).reshape(-1, 3, 3), M2=cu(g["M2"]).reshape(-1, 3, 3))
+    assert torch.equal(out, bev) and torch.equal(pr2, pr) and torch.equal(ct2, ct) and not rp.scratch.any()
     # ---- backward: whole tensor vs the float64 analytic gradient; same bits as the tile-plan kernels
     gb = make_bev_grad(cfg, seed).to(dev())
     gr = ops.splat_bwd_cl(prob, rp, gb.contiguous(memory_format=torch.channels_last), pr, ct)
@@ -102,10 +110,14 @@ def test_runplan_whole_tensor_parity(case):
     if "grad_in" in g:
         np.testing.assert_allclose(gr.cpu().numpy(), g["grad_in"], rtol=RTOL, atol=ATOL)   # the reference's autograd
     # ---- rebuilding into the same workspace gives the same plan and the same bits
-    p0, e0 = rp.prow.clone(), rp.emask.clone()
+    p0, epoch = rp.prow.clone(), int(rp.counters[0])
+    assert epoch == 2                                             # built twice so far
     runplan_from_golden(prob, g, plan=rp)
-    assert torch.equal(p0, rp.prow) and torch.equal(e0, rp.emask) and not rp.scratch.any()
+    assert torch.equal(p0, rp.prow) and int(rp.counters[0]) == epoch + 1 and not rp.scratch.any()
+    rows2, pts2, n_shared2 = rp.lists()
+    assert int(pts2.sum()) == n_kept and n_shared2 == n_shared
     assert torch.equal(ops.splat_fwd_cl(prob, rp, pr, ct), bev)
+    assert torch.equal(ops.splat_fwd_cl(prob, rp, pr, ct), bev)                      # the forward only reads the plan
 
 
 @pytest.mark.parametrize("name,aug", [("tiny", "train"), ("tiny", "full"), ("cfg1", "eval"), ("cfg2", "full")])
@@ -122,8 +134,9 @@ def test_runplan_raw_build_equals_matrix_build(name, aug):
     a = ops.build_runplan(prob, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3), M1=M1, M2=M2)
     r = ops.build_runplan(prob, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3), rots=cal["rots"],
                           intrins=cal["intrins"], post_rots=cal["post_rots"])
-    assert torch.equal(a.prow, r.prow) and torch.equal(a.emask, r.emask)
-    assert torch.equal(a.counters, r.counters)
+    assert torch.equal(a.prow, r.prow)
+    (ra, pa, sa), (rr, pr_, sr) = a.lists(), r.lists()
+    assert sa == sr and np.array_equal(np.bincount(ra, weights=pa), np.bincount(rr, weights=pr_))
 
 
 def test_runplan_long_voxels_and_all_dropped():
@@ -149,11 +162,12 @@ def test_runplan_long_voxels_and_all_dropped():
         want = O.splat_from_prob(pr.cpu().numpy(), ct.cpu().numpy(), vox, case_cfg.B, case_cfg.C, nx)
         assert np.array_equal(bev.cpu().numpy(), want)
         cnt = rp.counters.cpu().numpy()
+        assert not rp.scratch.any()
         if expect_hits:
-            assert cnt[2] >= 1 and np.bincount(vox[vox >= 0]).max() > 1024      # long voxels beyond the shared-memory sort
-            assert torch.equal(ops.splat_fwd_cl(prob, rp, pr, ct), bev)           # (in-place pool sort is idempotent)
+            assert cnt[7] >= 1 and np.bincount(vox[vox >= 0]).max() > 1024      # long voxels beyond the shared-memory sort
+            assert torch.equal(ops.splat_fwd_cl(prob, rp, pr, ct), bev)
         else:
-            assert not kept.any() and not bev.any() and cnt[0] == 0 and cnt[2] == 0
+            assert not kept.any() and not bev.any() and cnt[6] == 0 and cnt[7] == 0
         gb = make_bev_grad(case_cfg, 1).to(dev())
         gr = ops.splat_bwd_cl(prob, rp, gb, pr, ct)
         want_g = O.liftsplat_backward(gb.cpu().numpy(), b["depthnet_out"].numpy(), pr.cpu().numpy(), vox, case_cfg.B,
@@ -224,10 +238,11 @@ def test_runplan_autograd_and_model_path():
     assert torch.equal(x2.grad, x.grad)
 
 
-def test_runplan_graph_replay_with_changing_calibration():
-    """One captured step (zero-fill || lift || plan build -> gather -> backward, programmatic launch inside the plan build)
+@pytest.mark.parametrize("cfg_name", ["tiny", "cfg1"])
+def test_runplan_graph_replay_with_changing_calibration(cfg_name):
+    """One captured step (lift || plan build -> zero-fill || classify + gather, launched programmatically -> backward)
     replayed with a different calibration every time: no stale plan data may leak from one replay into the next."""
-    cfg = CONFIGS["tiny"]
+    cfg = CONFIGS[cfg_name]
     dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
     prob = problem_of(cfg, {"dx": dx, "bx": bx, "nx": nx})
     fr = cu(O.create_frustum(cfg.final_dim, list(cfg.dbound)))
@@ -239,23 +254,13 @@ def test_runplan_graph_replay_with_changing_calibration():
     rp = ops.RunPlan(prob, dev())
     bev = torch.empty(prob.bev_shape, device=dev()).contiguous(memory_format=torch.channels_last)
     grad = torch.empty_like(dn)
-    s_main, s_zero, s_lift = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    s_main = torch.cuda.Stream()
     lift_out = (torch.empty((2, prob.B * prob.N, prob.D, prob.fH, prob.fW), device=dev()),
                 torch.empty((prob.B * prob.N, prob.fH * prob.fW, prob.C), device=dev()))
 
-    def step():
-        cur = torch.cuda.current_stream()
-        s_zero.wait_stream(cur)
-        s_lift.wait_stream(cur)
-        with torch.cuda.stream(s_zero):
-            ops.bev_zero(prob, dev(), out=bev)
-        with torch.cuda.stream(s_lift):
-            pr, ct = ops.lift_prepare(prob, dn, out=lift_out)
-        ops.build_runplan(prob, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3), rots=cal["rots"],
-                          intrins=cal["intrins"], post_rots=cal["post_rots"], plan=rp)
-        cur.wait_stream(s_zero)
-        cur.wait_stream(s_lift)
-        ops.splat_fwd_cl(prob, rp, pr, ct, out=bev, precleared=True)
+    def step():      # the step of bench.py / api.StepPipeline: zero-fill || lift || index -> classify + gather -> backward
+        _, pr, ct = ops.liftsplat_forward(prob, rp, dn, lift_out, bev, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3),
+                                          rots=cal["rots"], intrins=cal["intrins"], post_rots=cal["post_rots"])
         ops.splat_bwd_cl(prob, rp, gb, pr, ct, out=grad)
 
     with torch.cuda.stream(s_main):
@@ -270,6 +275,7 @@ def test_runplan_graph_replay_with_changing_calibration():
         for k in keys:
             cal[k].copy_(b[k])
         dn.copy_(b["depthnet_out"])
+        bev.fill_(float("nan"))
         graph.replay()
         torch.cuda.synchronize()
         ref_rp = ops.build_runplan(prob, fr, cal["trans"].reshape(-1, 3), cal["post_trans"].reshape(-1, 3), rots=cal["rots"],
@@ -277,3 +283,50 @@ def test_runplan_graph_replay_with_changing_calibration():
         pr, ct = ops.lift_prepare(prob, dn)
         assert torch.equal(bev, ops.splat_fwd_cl(prob, ref_rp, pr, ct)), it
         assert torch.equal(grad, ops.splat_bwd_cl(prob, ref_rp, gb, pr, ct)), it
+
+
+@pytest.mark.parametrize("one_launch", [False, True])
+@pytest.mark.parametrize("cfg_name,B", [("cfg2", 8), ("cfg2", 3), ("cfg1", 1)])
+def test_fused_forward_zero_fill_ordering_stress(cfg_name, B, one_launch):
+    """The zero-fill runs NEXT TO the classify + gather CTAs (per-sample progress counters) -- in the prologue grid of
+    liftsplat_forward, whose successor starts on the READY flag, or as the first CTAs of splat_fwd_cl: 40 back-to-back replays over a tensor poisoned with NaN before every step must all give the reference bits --
+    a zero landing after a voxel row, or a row written before its zeros, shows up as a mismatch."""
+    cfg = dataclasses.replace(CONFIGS[cfg_name], B=B)
+    dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    prob = problem_of(cfg, {"dx": dx, "bx": bx, "nx": nx})
+    fr = cu(O.create_frustum(cfg.final_dim, list(cfg.dbound)))
+    b = make_batch(cfg, 5, "train")
+    cal = {k: b[k].to(dev()) for k in ("rots", "trans", "intrins", "post_rots", "post_trans")}
+    dn = b["depthnet_out"].to(dev())
+    args = dict(trans=cal["trans"].reshape(-1, 3), post_trans=cal["post_trans"].reshape(-1, 3), rots=cal["rots"],
+                intrins=cal["intrins"], post_rots=cal["post_rots"])
+    ref_rp = ops.build_runplan(prob, fr, **args)
+    pr0, ct0 = ops.lift_prepare(prob, dn)
+    want = ops.splat_fwd_cl(prob, ref_rp, pr0, ct0, out=ops.bev_zero(prob, dev()), precleared=True)
+    rp = ops.RunPlan(prob, dev())
+    bev = torch.empty(prob.bev_shape, device=dev()).contiguous(memory_format=torch.channels_last)
+    lift_out = (torch.empty((2, prob.B * prob.N, prob.D, prob.fH, prob.fW), device=dev()),
+                torch.empty((prob.B * prob.N, prob.fH * prob.fW, prob.C), device=dev()))
+    bad = torch.zeros((), dtype=torch.int64, device=dev())
+    s_main = torch.cuda.Stream()
+
+    def step():
+        bev.fill_(float("nan"))
+        if one_launch:
+            pr, ct = ops.liftsplat_prologue(prob, dn, lift_out, None, rp, fr, **args)
+            ops.splat_fwd_cl(prob, rp, pr, ct, out=bev)
+        else:
+            ops.liftsplat_forward(prob, rp, dn, lift_out, bev, fr, **args)
+        bad.add_((bev != want).sum())                     # NaN != x counts too
+
+    with torch.cuda.stream(s_main):
+        step()
+    torch.cuda.synchronize()
+    assert int(bad) == 0
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s_main):
+        step()
+    for _ in range(40):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert int(bad) == 0 and not rp.scratch.any()
