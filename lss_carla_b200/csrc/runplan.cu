@@ -89,6 +89,7 @@ extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) 
 #define RPC_NLONG 5        // ... of which k_fwd_shared found >= 64 points (re-queued from the end of the record array)
 #define RPC_STAT 6         // [6], [7]: shared / long voxels of the last completed forward
 #define RPC_PUB 9          // column CTAs of the running forward that have queued their shared voxels
+#define RPC_NLONG_CTA 10   // long voxels summed by the CTA that met them (running forward)
 #define RP_FLAG_STRIDE 32  // ints between two polled flags: every flag has its own 128-byte line (and L2 slice)
 #define RP_READY_LINES 32  // copies of READY (lss_liftsplat_forward: 1 once the plan and the lift operands of the step are
                            // complete); column CTA i polls copy i % 32, so that a thousand pollers do not queue on one L2 line
@@ -227,15 +228,17 @@ __device__ __forceinline__ int ld_acquire(const int32_t *p) {
 // Poll until *p >= target.  The producers are CTAs that are already running (zero CTAs of this or of the preceding grid, the
 // prologue's last CTA), so the wait is bounded by their work; after 2 s something is wrong with the calling sequence (e.g.
 // lss_liftsplat_fwd_cl on a workspace whose counters were overwritten) and the kernel traps instead of hanging the GPU.
-__device__ __forceinline__ void spin_until(const int32_t *p, int target, unsigned sleep_ns) {
-    if (ld_acquire(p) >= target) return;
+__device__ __forceinline__ int spin_until(const int32_t *p, int target, unsigned sleep_ns) {
+    int v = ld_acquire(p);
+    if (v >= target) return v;
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire(p) < target) {
+    while ((v = ld_acquire(p)) < target) {
         __nanosleep(sleep_ns);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         if (t - t0 > 2000000000ull) __trap();
     }
+    return v;
 }
 
 // The zeros of segment `seg` issued by this CTA have landed: make them visible device-wide, then count the CTA in.
@@ -313,19 +316,18 @@ struct PrologueArgs {
     int32_t *ready;                                                   // != null: raise READY when lift + index are complete
 };
 
-__device__ __forceinline__ void prologue_cta_done(const PrologueArgs &a) {
+// `epoch0` (thread 0): the epoch of the plan in the workspace when this CTA started.
+__device__ __forceinline__ void prologue_cta_done(const PrologueArgs &a, int epoch0) {
     if (a.counters == nullptr) return;
     __syncthreads();                                      // the CTA's writes are done ...
     if (threadIdx.x != 0) return;
     __threadfence();                                      // ... and ordered before the count
     if (atomicAdd(a.counters + RPC_PRO_DONE, 1) != a.n_index + a.n_lift - 1) return;
-    __threadfence();
+    __threadfence();                                      // the last CTA: everybody's writes are visible to it, and through
+    const int epoch = epoch0 + (a.n_index ? 1 : 0);       // READY (which carries the epoch of the plan to use) to the forward grid
+    if (a.ready) for (int i = 0; i < RP_READY_LINES; ++i) atomicExch(a.ready + i * RP_FLAG_STRIDE, epoch);
     a.counters[RPC_PRO_DONE] = 0;
-    if (a.n_index) a.counters[RPC_EPOCH] += 1;            // every index CTA has read the old epoch
-    if (a.ready) {
-        __threadfence();
-        for (int i = 0; i < RP_READY_LINES; ++i) atomicExch(a.ready + i * RP_FLAG_STRIDE, 1);
-    }
+    a.counters[RPC_EPOCH] = epoch;                        // every index CTA has read the old epoch
 }
 
 template <bool RAW>
@@ -335,6 +337,7 @@ k_prologue(Dims d, PrologueArgs a) {
     lss_pdl_trigger();                                    // k_fwd_columns may be scheduled while this grid runs
     int cta = (int)blockIdx.x;
     if (cta < a.n_zero) { zero_role(a.bev, a.bev_bytes, cta, a.n_zero, s_pro); return; }
+    const int epoch0 = (threadIdx.x == 0 && a.counters != nullptr) ? __ldcg(a.counters + RPC_EPOCH) : 0;
     cta -= a.n_zero;
     if (cta < a.n_lift) {
         tl_stamp(2, false);
@@ -343,7 +346,7 @@ k_prologue(Dims d, PrologueArgs a) {
     } else {
         run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.head, a.sub, a.sub2, a.counters, cta - a.n_lift);
     }
-    prologue_cta_done(a);
+    prologue_cta_done(a, epoch0);
 }
 
 // The zero-fill of lss_liftsplat_forward: one warp per CTA, two CTAs per SM, launched FIRST so that they are spread evenly over
@@ -375,6 +378,7 @@ struct FwdArgs {
 };
 
 
+#define GCL_LONG_CAP 64            // long voxels a shared-voxel CTA keeps for itself (more: the last CTA of the grid takes them)
 #define GCL_ROWS 16                // context rows a warp has in flight for a shared voxel (cp.async into shared memory)
 
 // fl32(acc + fl32(w * v)) on two channels: scalar products, ONE packed add (sm_100 FADD2) -- the same two roundings per channel
@@ -403,7 +407,9 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, gl = lane & 7, g = threadIdx.x >> 3;
     const int HWC = d.HW * C;
     const int vps = d.nx * d.ny * d.nz;                   // voxels per sample
-    if (threadIdx.x == 0) spin_until(a.counters + RPC_PUB, a.n_keys, 200);      // every column CTA has queued its shared voxels
+    __shared__ int s_nlong, s_last, s_len, s_pos;
+    __shared__ int4 s_longrec[GCL_LONG_CAP];
+    if (threadIdx.x == 0) { s_nlong = 0; spin_until(a.counters + RPC_PUB, a.n_keys, 200); }      // every column CTA has queued its shared voxels
     __syncthreads();
     tl_stamp(4, false);
     const int n_rec = __ldcg(a.counters + RPC_NREC);
@@ -438,8 +444,12 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
                 if (cur == rec.z) break;
                 cur = nd.x;
             }
-            if (len >= GCL_SHORT_CAP) {                   // long voxel: left to the last CTA
-                if (lane == 0) a.recs[a.n_rec_cap - 1 - atomicAdd(a.counters + RPC_NLONG, 1)] = rec;
+            if (len >= GCL_SHORT_CAP) {                   // long voxel: for the whole CTA, after its warps are through
+                if (lane == 0) {
+                    const int pos = atomicAdd(&s_nlong, 1);
+                    if (pos < GCL_LONG_CAP) s_longrec[pos] = rec;
+                    else a.recs[a.n_rec_cap - 1 - atomicAdd(a.counters + RPC_NLONG, 1)] = rec;      // (overflow: the last CTA)
+                }
                 continue;
             }
             __syncwarp();
@@ -494,20 +504,11 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
         }
     }
     tl_stamp(4, true);
-    // ---- the last CTA to finish: long voxels, then the scratch of the forward is left clean for the next one
-    __shared__ int s_last, s_len, s_pos;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(a.counters + RPC_FWD_DONE, 1) == a.n_cons - 1;
-        if (s_last) __threadfence();
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // Long voxels (>= 64 points), one at a time by the whole CTA.  Scratch: [SORT_CAP] keys, [NG][C] products.  Keys are sorted
-    // by the CTA (shared memory up to SORT_CAP points, else in the pool), then NG points per pass: every group fetches one
-    // point's context row and writes float32(prob*ctx) to shared memory (all loads in flight together); thread c adds the NG
-    // products of channel c in ascending point order -- the same sequence of float32 additions as everywhere else.
+    // ---- long voxels (>= 64 points) met by this CTA's warps, one at a time by the whole CTA.  Scratch: [SORT_CAP] keys, [NG][C]
+    // products.  Keys are sorted by the CTA (shared memory up to SORT_CAP points, else in the pool), then NG points per pass:
+    // every group fetches one point's context row and writes float32(prob*ctx) to shared memory (all loads in flight
+    // together); thread c adds the NG products of channel c in ascending point order -- the same sequence of float32
+    // additions as everywhere else.
     auto decode = [&](unsigned pidx, int b, int &ro, size_t &wi) {   // context row offset (floats) in the sample and prob_col index of a point
         const unsigned cam = lss_div20(pidx, d.mDHW);
         const unsigned rr = pidx - cam * d.DHW;
@@ -518,11 +519,9 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
         ro = (int)(cam * HWC + hw * C);
         wi = ((size_t)(bnn * d.fW + ww) * d.D + dd) * d.fH + h;
     };
-    const int n_long = __ldcg(a.counters + RPC_NLONG);
     uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn);
     float *s_prod = s_dyn + GCL_SORT_CAP;
-    for (int l = 0; l < n_long; ++l) {
-        const int4 rec = __ldcg(a.recs + (a.n_rec_cap - 1 - l));
+    auto sum_long = [&](const int4 rec) {
         const int b = rec.y / vps;
         if (threadIdx.x == 0) {                           // points of the voxel; room in the pool if they do not fit shared memory
             int c = __popc((unsigned)rec.w);
@@ -573,9 +572,23 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
         }
         if ((int)threadIdx.x < C) a.bev[(size_t)rec.y * C + threadIdx.x] = accc;
         __syncthreads();
+    };
+    __syncthreads();
+    const int n_long_cta = min(s_nlong, GCL_LONG_CAP);
+    for (int l = 0; l < n_long_cta; ++l) sum_long(s_longrec[l]);
+    // ---- the last CTA to finish: the long voxels that did not fit a CTA's list, then the scratch of the forward is left clean
+    if (threadIdx.x == 0) {
+        if (n_long_cta) atomicAdd(a.counters + RPC_NLONG_CTA, n_long_cta);
+        __threadfence();
+        s_last = atomicAdd(a.counters + RPC_FWD_DONE, 1) == a.n_cons - 1;
+        if (s_last) __threadfence();
     }
+    __syncthreads();
+    if (!s_last) return;
+    const int n_long = __ldcg(a.counters + RPC_NLONG);
+    for (int l = 0; l < n_long; ++l) sum_long(__ldcg(a.recs + (a.n_rec_cap - 1 - l)));
     if (threadIdx.x == 0) {                               // every progress counter has been seen complete by a column CTA by now
-        a.counters[RPC_STAT] = n_rec; a.counters[RPC_STAT + 1] = n_long;
+        a.counters[RPC_STAT] = n_rec; a.counters[RPC_STAT + 1] = n_long + atomicExch(a.counters + RPC_NLONG_CTA, 0);
         a.counters[RPC_NREC] = 0; a.counters[RPC_NLONG] = 0; a.counters[RPC_POOL] = 0; a.counters[RPC_FWD_DONE] = 0; a.counters[RPC_PUB] = 0;
         if (a.wait_ready) for (int i = 0; i < RP_READY_LINES; ++i) a.ready[i * RP_FLAG_STRIDE] = 0;
         if (a.zero_target) for (int i = 0; i < d.B; ++i) a.zero_done[i * RP_FLAG_STRIDE] = 0;
@@ -596,12 +609,14 @@ k_fwd_columns(Dims d, FwdArgs a) {
         zero_role_segments(a.bev, a.seg_bytes, d.B, (int)blockIdx.x, a.n_zero, s_dyn, a.zero_done, a.z_chunk, a.z_window);
         return;
     }
+    __shared__ int s_epoch;
     if (a.wait_ready) {                                   // the zero-fill grid is still streaming: only the plan + lift grid counts
-        if (threadIdx.x == 0) spin_until(a.ready + (blockIdx.x % RP_READY_LINES) * RP_FLAG_STRIDE, 1, 100);
-        __syncthreads();
+        if (threadIdx.x == 0) s_epoch = spin_until(a.ready + (blockIdx.x % RP_READY_LINES) * RP_FLAG_STRIDE, 1, 100);   // READY = the plan's epoch
     } else {
         lss_pdl_wait();                                   // plan and lift operands come from the preceding kernel(s)
+        if (threadIdx.x == 0) s_epoch = __ldcg(a.counters + RPC_EPOCH);
     }
+    __syncthreads();
     if ((int)blockIdx.x >= a.n_zero + a.n_keys) { shared_voxels_cta<CPL>(d, a, (int)blockIdx.x - a.n_zero - a.n_keys, s_dyn); return; }
     tl_stamp(3, false);
     const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
@@ -619,7 +634,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
     unsigned *s_shmask = reinterpret_cast<unsigned *>(s_shared + per + (per & 1));    // [per] ... and their row masks
     __shared__ int s_n, s_nshared;
     if (threadIdx.x == 0) { s_n = 0; s_nshared = 0; }
-    const unsigned long long tag = (unsigned long long)(unsigned)__ldcg(a.counters + RPC_EPOCH) << 32;
+    const unsigned long long tag = (unsigned long long)(unsigned)s_epoch << 32;
     const size_t base = (size_t)key * per;
     constexpr int SU = 3;                                 // slots per thread and round: their loads are all in flight together
     constexpr int c4 = C >> 2;

@@ -414,7 +414,8 @@ class RunPlan:
         """What a forward uses as scratch (all-zero between launches): counters [1..5], the zero-fill progress counters and
         the READY flags."""
         n = (self.layout.off_head - self.layout.off_zero_done) // 4
-        return torch.cat((self.counters[1:6], self._view(self.layout.off_zero_done, n, torch.int32)))
+        c = self._view(self.layout.off_counters, 64, torch.int32)
+        return torch.cat((c[1:6], c[8:], self._view(self.layout.off_zero_done, n, torch.int32)))
 
     def lists(self):
         """The per-voxel lists of the current build as numpy arrays (synchronises; tests): (rows, points) -- for every
