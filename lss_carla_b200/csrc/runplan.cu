@@ -244,7 +244,7 @@ __device__ __forceinline__ int spin_until(const int32_t *p, int target, unsigned
 // The zeros of segment `seg` issued by this CTA have landed: make them visible device-wide, then count the CTA in.
 __device__ __forceinline__ void zero_publish(int32_t *zero_done, int seg) {
     asm volatile("fence.proxy.async;" ::: "memory");      // async-proxy writes before the generic-proxy release below
-    __threadfence();
+    __threadfence();                                      // (publishing without the fences was measured 2 us SLOWER per forward)
     atomicAdd(zero_done + seg * RP_FLAG_STRIDE, 1);
 }
 
@@ -830,11 +830,13 @@ extern "C" int lss_runplan_raw_supported(const lss_problem *p) {
 }
 
 // Pacing of the zero-fill with progress counters: CTAs, bytes per bulk copy, copies in flight per CTA.  Measured at cfg 2 next to
-// the other kernels of the forward: 148 .. 592 CTAs, 4 .. 16 KB copies, 1 .. 8 in flight all end within
-// +-1.5 us of each other; fewer CTAs or shallower windows stretch the zero-fill, deeper ones delay the latency-bound CTAs.
+// the other kernels of the forward: between (1 CTA per SM, 2 in flight) and (2 per SM, 4 in flight) the
+// forward is flat within 0.5 us; more in flight (4 per SM, or 8 deep) costs 3-5 us -- a deeper queue of zeros delays the loads
+// and atomics of the latency-bound CTAs next to it -- and half a CTA per SM stretches the zero-fill itself by as much.
+// `own_grid`: k_zero_flags in front of prologue + columns (1 per SM, 4 deep) / the first CTAs of the column grid (2 per SM, 2 deep).
 struct ZeroTune { int n_cta, chunk, window; };
-static ZeroTune zero_tune(size_t seg_bytes) {
-    ZeroTune t = {2 * rp_num_sms(), ZERO_CHUNK, 4};
+static ZeroTune zero_tune(size_t seg_bytes, bool own_grid) {
+    ZeroTune t = {own_grid ? rp_num_sms() : 2 * rp_num_sms(), ZERO_CHUNK, own_grid ? 4 : 2};
     const size_t cps = (seg_bytes + t.chunk - 1) / t.chunk;
     if ((size_t)t.n_cta > cps) t.n_cta = (int)cps;
     return t;
@@ -979,7 +981,7 @@ static int launch_fwd_grid(const lss_problem *p, const lss_runplan_layout *L, vo
     a.seg_bytes = (size_t)p->nx * p->ny * p->nz * p->C * 4;
     a.n_zero = in_kernel ? zero_target : 0;
     a.zero_target = zero_target;
-    { const ZeroTune t = zero_tune(a.seg_bytes); a.z_chunk = t.chunk; a.z_window = t.window; }
+    { const ZeroTune t = zero_tune(a.seg_bytes, false); a.z_chunk = t.chunk; a.z_window = t.window; }
     a.wait_ready = wait_ready ? 1 : 0;
     a.zero_done = (int32_t *)(w + L->off_zero_done); a.ready = (int32_t *)(w + L->off_ready);
     a.n_keys = p->B * p->N * p->fW; a.fWD = p->fW * p->D;
@@ -1016,7 +1018,7 @@ extern "C" int lss_liftsplat_fwd_cl(const lss_problem *p, const lss_runplan_layo
     if (st != LSS_OK) return st;
     LSS_REQUIRE(zero_mode == LSS_ZERO_ORDERED || zero_mode == LSS_ZERO_PRECLEARED, LSS_ERR_BAD_ARG);
     int n_zero = 0;
-    if (zero_mode == LSS_ZERO_ORDERED) n_zero = zero_tune((size_t)p->nx * p->ny * p->nz * p->C * 4).n_cta;
+    if (zero_mode == LSS_ZERO_ORDERED) n_zero = zero_tune((size_t)p->nx * p->ny * p->nz * p->C * 4, false).n_cta;
     return launch_fwd_grid(p, L, workspace, prob_col, ctx_t, bev, n_zero, true, false, (cudaStream_t)stream);
 }
 
@@ -1032,7 +1034,7 @@ extern "C" int lss_liftsplat_forward(const lss_problem *p, const lss_runplan_lay
     if (st != LSS_OK) return st;                          // would leave the progress counters raised
     cudaStream_t s = (cudaStream_t)stream;
     const size_t seg_bytes = (size_t)p->nx * p->ny * p->nz * p->C * 4;
-    const ZeroTune t = zero_tune(seg_bytes);
+    const ZeroTune t = zero_tune(seg_bytes, true);
     k_zero_flags<<<t.n_cta, 32, ZERO_CHUNK, s>>>(bev, seg_bytes, p->B, (int32_t *)((char *)workspace + L->off_zero_done), t.chunk, t.window);
     LSS_CHECK_LAUNCH();
     st = prologue_checked(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,

@@ -96,6 +96,26 @@ def main():
         forward_kept(s)
         bwd(s)
 
+    import ctypes
+    _rt = ctypes.CDLL("libcudart.so.12")
+    _rt.cudaMemsetAsync.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+    side = [torch.cuda.Stream() for _ in sets]
+
+    def forward_fork(kind):      # experiment: the zero-fill as a memset / ATen fill on a forked branch, forward on a pre-cleared tensor
+        def f(s):
+            cur = torch.cuda.current_stream()
+            st = side[sets.index(s)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                if kind == "memset":
+                    _rt.cudaMemsetAsync(s.bev.data_ptr(), 0, s.bev.numel() * 4, ctypes.c_void_p(st.cuda_stream))
+                else:
+                    s.bev.zero_()
+            prologue(s)
+            cur.wait_stream(st)
+            fwd_precleared(s)
+        return f
+
     def timeit(fn):
         for s in sets:
             fn(s)
@@ -124,7 +144,7 @@ def main():
     torch.cuda.synchronize()
     res = {"workload": name}
     for nm, fn in (("plan", plan), ("lift", lift), ("zero", zero), ("prologue(lift+plan)", prologue), ("fwd_precleared", fwd_precleared),
-                   ("fwd_ordered", fwd_ordered), ("bwd", bwd), ("forward", forward), ("forward_kept_plan", forward_kept), ("step", step),
+                   ("fwd_ordered", fwd_ordered), ("bwd", bwd), ("forward", forward), ("forward_fork_memset", forward_fork("memset")), ("forward_fork_fill", forward_fork("fill")), ("forward_kept_plan", forward_kept), ("step", step),
                    ("step_kept_plan", step_kept)):
         res[nm + "_us"] = round(timeit(fn), 2)
     res["mpoints_per_s"] = round(cfg.points / res["step_us"], 1)
@@ -142,7 +162,7 @@ def main():
     for s in sets:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            step(s)
+            (fwd_ordered if os.environ.get("QUICK_TL") == "ordered" else step)(s)
         graphs.append(g)
     for i in range(12):
         graphs[i % 4].replay()
@@ -152,7 +172,7 @@ def main():
     torch.cuda.synchronize()
     out = (C.c_ulonglong * 10)()
     L.lss_debug_runplan_timeline(0, out)
-    t0 = min(out[2], out[4])
+    t0 = min(out[0], out[6]) if os.environ.get("QUICK_TL") == "ordered" else min(out[2], out[4])
     res["timeline_us"] = {nm: [round((out[2 * k] - t0) / 1e3, 1), round((out[2 * k + 1] - t0) / 1e3, 1)]
                           for k, nm in enumerate(("zero", "index", "lift", "fwd_columns", "fwd_shared"))}
     if hasattr(L, "lss_debug_runplan_marks"):    # phase stamps of the forward's column CTAs (thread 0): after READY, staged, after the

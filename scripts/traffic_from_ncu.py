@@ -32,7 +32,7 @@ for name, v in agg.items():
     n = len(v)
     entry[name] = {"launches": n, "dram_read_bytes": round(sum(x[0] for x in v) / n), "dram_write_bytes": round(sum(x[1] for x in v) / n),
                    "duration_us_under_ncu": round(sum(x[2] for x in v) / n, 2)}
-fwd = [k for k in entry if "prologue" in k or "classify" in k or "fwd_gather" in k or "fwd_store" in k or "lift" in k]
+fwd = [k for k in entry if any(t in k for t in ("zero_flags", "prologue", "fwd_columns", "fwd_gather", "fwd_store", "lift"))]
 entry["forward_op_total"] = sum(entry[k]["dram_read_bytes"] + entry[k]["dram_write_bytes"] for k in fwd)
 entry["source"] = os.path.basename(rep)
 try:
