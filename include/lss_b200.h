@@ -196,7 +196,7 @@ int lss_lift_prepare(const lss_problem *p, const float *depthnet_out, float *pro
 /* The same for a bfloat16 depthnet output (autocast training; the reference's AMP-less loop has no counterpart):
  * values are widened on load, everything downstream is the float32 path bit for bit -- the result equals
  * lss_lift_prepare on the widened tensor.  Against float32 inputs that were rounded to bfloat16 the BEV differs by the
- * input rounding only (stated tolerance of the bf16 path: rtol 3e-2 / atol 3e-2, tests/test_cuda_parity.py). */
+ * input rounding only (stated tolerance of the bf16 path: rtol 3e-2 / atol 5e-3, tests/test_cuda_parity.py). */
 int lss_lift_prepare_bf16(const lss_problem *p, const void *depthnet_out_bf16, float *prob, float *ctx_t,
                           float *prob_col, void *stream);
 

@@ -17,16 +17,38 @@ backward 7.8 ms against 11.6 ms from an NCHW input) and the one the sort-free ru
 """
 from __future__ import annotations
 
+import collections
+import hashlib
+
 import torch
 
 from . import models, ops
 from .tools import gen_dx_bx
 
 
+def calibration_key(rots, trans, intrins, post_rots, post_trans):
+    """Key of a batch's calibration for the plan cache: the bytes of the five HOST tensors of LiftSplatShoot.forward
+    (models.py:256) -- 33 floats per camera.  None if any of them lives on the device (hashing would cost a round trip)."""
+    h = hashlib.blake2b(digest_size=16)
+    for t in (rots, trans, intrins, post_rots, post_trans):
+        if t.is_cuda:
+            return None
+        h.update(str(tuple(t.shape)).encode())
+        h.update(t.detach().contiguous().float().numpy().tobytes())
+    return h.digest()
+
+
 class LiftSplat:
+    """`plan_cache`: number of run plans kept, keyed by the bytes of the host calibration (0 = every call rebuilds its plan).
+    The forward only reads a plan, so a batch whose calibration repeats -- evaluation (static resize / crop,
+    src/data_simbev.py:135-143), or a repeated training batch -- skips the plan build; `plan_cache_stats()` reports hits."""
+
     def __init__(self, grid_conf, data_aug_conf, C=64, downsample=16, splat_mode="sorted",
-                 inverse_mode="reference", bev_channels_last=True, device="cuda:0", tile_cols=0, copy_streams=False):
+                 inverse_mode="reference", bev_channels_last=True, device="cuda:0", tile_cols=0, copy_streams=False, plan_cache=0):
         self.device = torch.device(device)
+        self.plan_cache_size = int(plan_cache)
+        self._plans = collections.OrderedDict()
+        self._hits = self._misses = 0
         dx, bx, nx = gen_dx_bx(grid_conf["xbound"], grid_conf["ybound"], grid_conf["zbound"])
         self.dx, self.bx, self.nx = dx, bx, nx
         ogfH, ogfW = data_aug_conf["final_dim"]
@@ -80,6 +102,10 @@ class LiftSplat:
         t.record_stream(self._down)
         return out
 
+    def plan_cache_stats(self):
+        n = self._hits + self._misses
+        return {"hits": self._hits, "misses": self._misses, "hit_rate": (self._hits / n) if n else None, "plans_kept": len(self._plans)}
+
     def sync_downloads(self):
         if self._down is not None:
             self._down.synchronize()
@@ -89,16 +115,31 @@ class LiftSplat:
         fH, fW = depthnet_out.shape[-2:]
         prob = models._problem_for(self, B, N, fH, fW, depthnet_out.shape[1] - self.D)
         if plan is None and models._use_runplan(self, prob):
+            key = calibration_key(rots, trans, intrins, post_rots, post_trans) if self.plan_cache_size > 0 else None
+            if key is not None:
+                key = (key, id(prob))
+                if key in self._plans:                # the calibration repeats: no plan build, lift + forward only
+                    self._plans.move_to_end(key)
+                    self._hits += 1
+                    return ops.lift_splat(self._dev(depthnet_out), prob, self._plans[key], self.splat_mode, True)
+                self._misses += 1
+            # a cached plan is never rebuilt in place (a graph that still needs it may be alive): fresh workspace per entry
+            ws = ops.RunPlan(prob, self.device) if key is not None else models._cached_plan(self, prob, self.device, run=True)
             if self.inverse_mode == "reference":      # host tensors: LAPACK inverse where the data already is
                 M1 = torch.inverse(post_rots.cpu() if post_rots.is_cuda else post_rots)
                 M2h = torch.inverse(intrins.cpu() if intrins.is_cuda else intrins)
                 M1, M2 = self._dev(M1), self._dev(rots).matmul(self._dev(M2h))
-                plan = ops.build_runplan(prob, self.frustum, self._dev(trans).reshape(-1, 3), self._dev(post_trans).reshape(-1, 3),
-                                         M1=M1.reshape(-1, 3, 3), M2=M2.reshape(-1, 3, 3), plan=models._cached_plan(self, prob, self.device, run=True))
+                build = dict(frustum=self.frustum, trans=self._dev(trans).reshape(-1, 3), post_trans=self._dev(post_trans).reshape(-1, 3),
+                             M1=M1.reshape(-1, 3, 3), M2=M2.reshape(-1, 3, 3))
             else:
-                plan = models.runplan_from_calibration(self, prob, self._dev(rots), self._dev(trans), self._dev(intrins),
-                                                       self._dev(post_rots), self._dev(post_trans))
-            return ops.lift_splat(self._dev(depthnet_out), prob, plan, self.splat_mode, True)
+                build = models.runplan_build_args(self, prob, self._dev(rots), self._dev(trans), self._dev(intrins),
+                                                  self._dev(post_rots), self._dev(post_trans))
+            out = ops.lift_splat(self._dev(depthnet_out), prob, ws, self.splat_mode, True, build=build)   # plan build + lift + forward
+            if key is not None:
+                self._plans[key] = ws
+                while len(self._plans) > self.plan_cache_size:
+                    self._plans.popitem(last=False)
+            return out
         if plan is None:
             if self.inverse_mode == "reference":
                 # host tensors: LAPACK inverse where the data already is; device tensors: the reference's round trip

