@@ -274,11 +274,15 @@ typedef struct lss_runplan_layout {
                             /*                      ((n*D + d)*fH + h)*fW + w}: what the sums of shared voxels need        */
     size_t off_pool;        /* uint32[n_points]     forward scratch: point keys of voxels beyond the shared-memory sort */
     int64_t n_rec_cap;      /* capacity (records) of recs                                                    */
-    size_t off_recs;        /* int32 [n_rec_cap,4]  forward scratch: queue of the voxels shared by several sub-runs       */
-                            /*                      {head of the voxel's list, voxel row, first pusher, its row mask}     */
-    size_t off_counters;    /* int32 [64]           [0] epoch of the last build; [1..5] scratch, zero between launches;  */
-                            /*                      [6] voxels shared by several sub-runs and [7] voxels with            */
-                            /*                      >= 64 points, as met by the last forward                             */
+    size_t off_recs;        /* int32 [n_rec_cap,4]  queue of the voxels shared by several sub-runs, filled by the build: every    */
+                            /*                      sub-run that found another one on its voxel's list queued {voxel row,         */
+                            /*                      previous sub-run, itself (both: point index + 1), its row mask}               */
+    size_t off_longs;       /* int32 [n_points/64+2,4] forward scratch: overflow list of voxels with >= 64 points                 */
+    size_t off_counters;    /* int32 [64]           [0] epoch of the last build; [6] voxels shared by several sub-runs   */
+                            /*                      and [7] voxels with >= 64 points, as summed by the last forward;     */
+                            /*                      the rest: scratch, zero between launches                             */
+    size_t off_qcount;      /* uint64[32] (128 bytes apart) (epoch << 32) | records of sub-queue s; record k of sub-queue s */
+                            /*                      sits in recs[k*32 + s]                                               */
     size_t off_zero_done;   /* int32 [B,32]         forward scratch: zero-fill progress per sample ([b][0]; one 128-byte  */
                             /*                      line each), zero between launches                                    */
     size_t off_ready;       /* int32 [32,32]        forward scratch: 32 copies ([i][0]) of the "plan + lift operands     */

@@ -39,7 +39,7 @@ class LssPlanLayout(C.Structure):
 class LssRunplanLayout(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_runs", C.c_int64), ("n_voxels", C.c_int64),
                 ("off_prow", C.c_size_t), ("off_sub", C.c_size_t), ("off_sub2", C.c_size_t), ("off_pool", C.c_size_t),
-                ("n_rec_cap", C.c_int64), ("off_recs", C.c_size_t), ("off_counters", C.c_size_t), ("off_zero_done", C.c_size_t), ("off_ready", C.c_size_t),
+                ("n_rec_cap", C.c_int64), ("off_recs", C.c_size_t), ("off_longs", C.c_size_t), ("off_counters", C.c_size_t), ("off_qcount", C.c_size_t), ("off_zero_done", C.c_size_t), ("off_ready", C.c_size_t),
                 ("off_head", C.c_size_t), ("bytes", C.c_size_t)]
 
 

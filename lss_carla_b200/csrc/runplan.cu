@@ -13,11 +13,13 @@
 //                   on the voxel's list with ONE 64-bit atomicExch on head[voxel] = {build epoch, leader + 1} and records
 //                   sub[leader] = {previous head of this build (0: it pushed first), row mask}.  Heads of older builds carry
 //                   an older epoch and read as empty: nothing is cleared between builds and the forward only READS the plan.
+//                   A pusher that finds a sub-run of this build on the list also queues the voxel {row, previous, itself, mask}.
 //   k_fwd_columns   one CTA per camera column stages its operands, finds its first pushers and looks at their voxels' heads:
 //                   still the head = the sub-run is alone = EXCLUSIVE, summed from the staged operands by an 8-lane group
-//                   (lane = C/8 channels) and written as one voxel row.  Voxels shared by several sub-runs (about 5 %) are
-//                   queued; the CTAs at the END of the same grid take one per warp: walk the short list, sort the few points
-//                   by flat index, fetch weights and context rows in one go, add in key order; >= 64 points: a whole CTA.
+//                   (lane = C/8 channels) and written as one voxel row.  Voxels shared by several sub-runs (about 5 %) come
+//                   from the queue; the CTAs at the END of the same grid take one record per warp: the two sub-runs' nodes and
+//                   the head in one go, the few points sorted by flat index, weights and context rows in one go, added in key
+//                   order; >= 64 points: a whole CTA.
 //   zero-fill       cp.async.bulk from a zeroed shared-memory chunk, sample by sample, with a progress counter per sample that
 //                   the writers of voxel rows wait for: as the first CTAs of k_fwd_columns (lss_liftsplat_fwd_cl) or as its own
 //                   small grid in front of prologue and columns (lss_liftsplat_forward: three launches running side by side,
@@ -85,10 +87,12 @@ extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) 
 #define RPC_PRO_DONE 1     // lift / index CTAs of the running prologue that have finished (the last one publishes epoch + READY)
 #define RPC_FWD_DONE 2     // shared-voxel CTAs of the running forward that have finished (the last one sums the long voxels and resets the scratch)
 #define RPC_POOL 3         // pool cursor of the running forward
-#define RPC_NREC 4         // shared voxels queued by the column CTAs of the running forward
-#define RPC_NLONG 5        // ... of which k_fwd_shared found >= 64 points (re-queued from the end of the record array)
-#define RPC_STAT 6         // [6], [7]: shared / long voxels of the last completed forward
-#define RPC_PUB 9          // column CTAs of the running forward that have queued their shared voxels
+#define RP_QSHARDS 32      // the queue of shared voxels is 32 interleaved sub-queues (record k of shard s sits in slot k*32 + s) with one
+                           // counter each, (build epoch << 32) | count, on its own 128-byte line: index CTA i queues on shard i % 32,
+                           // so that the ~2 000 reservations of a build do not serialise on one L2 address
+#define RPC_NLONG 12       // long voxels (>= 64 points) that did not fit the list of the CTA that met them (running forward)
+#define RPC_STAT 6         // [6], [7]: shared / long voxels summed by the last completed forward
+#define RPC_NSHARED 9      // shared voxels summed by the running forward
 #define RPC_NLONG_CTA 10   // long voxels summed by the CTA that met them (running forward)
 #define RP_FLAG_STRIDE 32  // ints between two polled flags: every flag has its own 128-byte line (and L2 slice)
 #define RP_READY_LINES 32  // copies of READY (lss_liftsplat_forward: 1 once the plan and the lift operands of the step are
@@ -124,6 +128,7 @@ __device__ __forceinline__ RunLane run_lane(const RunDims &rd, int cta, int u) {
 template <bool RAW>
 __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, const CalibPtrs &c, int32_t *__restrict__ prow,
                                               unsigned long long *__restrict__ head, int2 *__restrict__ sub, int2 *__restrict__ sub2,
+                                              int4 *__restrict__ recs, unsigned long long *__restrict__ qcount,
                                               const int32_t *__restrict__ counters, int cta) {
     tl_stamp(1, false);
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
@@ -164,6 +169,14 @@ __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, 
             const int prev = (old >> 32) == (tag >> 32) ? (int)(unsigned)old : 0;      // heads of older builds read as empty
             LSS_DASSERT(prev >= 0 && prev <= d.n_points && prev != (int)cm + 1);
             node = make_int2(prev, (int)(peers >> lane));
+            if (prev != 0) {    // the voxel is shared: queue it for the shared-voxel CTAs of the forward.  Every pusher but the first
+                                // queues one record; only the one made by the SECOND pusher (whose `prev` pushed first) is taken up.
+                const int shard = cta & (RP_QSHARDS - 1);
+                unsigned long long *nrec = qcount + shard * (RP_FLAG_STRIDE / 2);
+                atomicMax(nrec, tag);                     // a count of an older build reads as zero (same-address order)
+                const unsigned k = (unsigned)atomicAdd(nrec, 1ull);
+                recs[(size_t)k * RP_QSHARDS + shard] = make_int4(row, prev, (int)cm + 1, node.y);
+            }
         }
         if (q.valid) sub[cm] = node;                      // {0, 0} wherever no sub-run starts
     }
@@ -311,7 +324,7 @@ __device__ __forceinline__ void zero_role_segments(float *__restrict__ dst, size
 struct PrologueArgs {
     float *bev; size_t bev_bytes; int n_zero;                         // zero role (n_zero = 0: off)
     int n_index; RunDims rd; CalibPtrs c;                             // index role (n_index = 0: off)
-    int32_t *prow, *counters; unsigned long long *head; int2 *sub, *sub2;
+    int32_t *prow, *counters; unsigned long long *head, *qcount; int2 *sub, *sub2; int4 *recs;
     int n_lift; const float *dn; float *prob, *ctx_t, *prob_col;      // lift role (n_lift = 0: off)
     int32_t *ready;                                                   // != null: raise READY when lift + index are complete
 };
@@ -344,7 +357,7 @@ k_prologue(Dims d, PrologueArgs a) {
         lift_prepare_cta<float>(d, a.dn, a.prob, a.ctx_t, a.prob_col, cta, s_pro);
         tl_stamp(2, true);
     } else {
-        run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.head, a.sub, a.sub2, a.counters, cta - a.n_lift);
+        run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.head, a.sub, a.sub2, a.recs, a.qcount, a.counters, cta - a.n_lift);
     }
     prologue_cta_done(a, epoch0);
 }
@@ -373,12 +386,15 @@ struct FwdArgs {
     unsigned long long mfH;
     const int32_t *prow; const int2 *sub, *sub2; const unsigned long long *head;
     int32_t *counters; uint32_t *pool;
-    int4 *recs; long long n_rec_cap; // queue of shared voxels {list head, voxel row, first pusher (both: point index + 1), its row mask}
+    const unsigned long long *qcount; // [32] sub-queue counters, 128 bytes apart
+    const int4 *recs; long long n_rec_cap; // shared voxels queued by the index pass {voxel row, previous pusher, this pusher (point + 1), its row mask}
+    int4 *longs;                     // forward scratch: overflow list of long voxels {voxel row} (end of the record array)
     const float *prob_col, *ctx_t; float *bev;
 };
 
 
 #define GCL_LONG_CAP 64            // long voxels a shared-voxel CTA keeps for itself (more: the last CTA of the grid takes them)
+#define GCL_PRE 3                  // exclusive voxels per 8-lane group summed before the CTA waits for its zeros
 #define GCL_ROWS 16                // context rows a warp has in flight for a shared voxel (cp.async into shared memory)
 
 // fl32(acc + fl32(w * v)) on two channels: scalar products, ONE packed add (sm_100 FADD2) -- the same two roundings per channel
@@ -392,14 +408,17 @@ __device__ __forceinline__ void mul_add2(float &a0, float &a1, float w, float v0
 }
 
 // Shared voxels (several sub-runs on the voxel's list, about 5 % of the voxels: neighbouring columns at close range, the
-// overlap of neighbouring cameras), spread evenly over the last `n_cons` CTAs of the forward grid: one warp per voxel.  The
-// warp walks the voxel's short list from its head to the first pusher (known from the queue record: no load for the tail),
-// lane j takes point j of a node; it rank-sorts the few keys by flat point index, fetches the weights (lane = point) and up to
-// GCL_ROWS context rows at once (cp.async: all of them in flight, no registers), then adds the products in key order, lane =
-// C/32 channels: the same sequence of float32 operations per channel as everywhere else.  Voxels with >= 64 points are
-// re-queued and summed, one at a time, by the last of these CTAs to finish, which also leaves the scratch of the forward clean.
+// overlap of neighbouring cameras), spread evenly over the last `n_cons` CTAs of the forward grid: one warp per voxel, from the
+// queue the index pass made -- every pusher that found a sub-run on the list before it queued {voxel, previous, itself, its row
+// mask}; the record whose `previous` pushed first is the voxel's, the others are skipped (96 % of the shared voxels hold two
+// sub-runs and one record).  The warp requests the previous sub-run's node, the two sub-runs' pixel / key words and the list
+// head together; sub-runs pushed later hang between the head and the record's maker.  Lane j takes point j of a sub-run; the warp
+// rank-sorts the few keys by flat point index, fetches the weights (lane = point) and up to GCL_ROWS context rows at once
+// (cp.async: all of them in flight, no registers), waits for the zeros of the voxel's sample and adds the products in key order,
+// lane = C/32 channels: the same sequence of float32 operations per channel as everywhere else.  Voxels with >= 64 points are
+// summed by the whole CTA afterwards.  The last of these CTAs to finish leaves the scratch of the forward clean.
 template <int CPL>
-__device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &a, int cons, float *s_dyn) {
+__device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &a, int cons, int epoch, float *s_dyn) {
     constexpr int C = 8 * CPL;
     constexpr int CH = C / 32;                            // channels per lane
     constexpr int PR = C / 4;                             // 16-byte pieces per context row
@@ -407,12 +426,15 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, gl = lane & 7, g = threadIdx.x >> 3;
     const int HWC = d.HW * C;
     const int vps = d.nx * d.ny * d.nz;                   // voxels per sample
-    __shared__ int s_nlong, s_last, s_len, s_pos;
-    __shared__ int4 s_longrec[GCL_LONG_CAP];
-    if (threadIdx.x == 0) { s_nlong = 0; spin_until(a.counters + RPC_PUB, a.n_keys, 200); }      // every column CTA has queued its shared voxels
+    __shared__ int s_nlong, s_ndone, s_last, s_len, s_pos;
+    __shared__ int s_longrow[GCL_LONG_CAP];
+    if (threadIdx.x == 0) { s_nlong = 0; s_ndone = 0; }
     __syncthreads();
     tl_stamp(4, false);
-    const int n_rec = __ldcg(a.counters + RPC_NREC);
+    // the sub-queues were filled by the index pass of the build this forward reads: lane s holds the count of shard s
+    const unsigned long long q64 = __ldcg(a.qcount + lane * (RP_FLAG_STRIDE / 2));
+    const int q_cnt = (unsigned)(q64 >> 32) == (unsigned)epoch ? (int)(unsigned)q64 : 0;
+    const int n_rec = __reduce_max_sync(LSS_FULL_MASK, q_cnt) * RP_QSHARDS;      // slots to look at (the tail of a short shard is skipped)
     {
         // per warp: keys, context-row numbers and weight indices of the voxel's points in list order [3][64], their order
         // by key [64], then the context rows [GCL_ROWS][C]
@@ -420,38 +442,43 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
         uint32_t *w_pix = w_key + GCL_SHORT_CAP, *w_widx = w_pix + GCL_SHORT_CAP, *w_ord = w_widx + GCL_SHORT_CAP;
         float *w_rows = s_dyn + NW * 4 * GCL_SHORT_CAP + wp * (GCL_ROWS * C);
         const int n_warps = a.n_cons * NW;
+        auto take = [&](int cm, unsigned m, int2 n2, int len) {      // lane j takes point j of a sub-run (leader cm, row mask m)
+            const int cnt = __popc(m);
+            if (lane < cnt && len + lane < GCL_SHORT_CAP) {
+                const unsigned k = __fns(m, 0, lane + 1);             // image-row offset of this lane's point
+                w_key[len + lane] = (unsigned)n2.y + k * (unsigned)d.fW;
+                w_pix[len + lane] = (unsigned)n2.x + k * (unsigned)d.fW;
+                w_widx[len + lane] = (unsigned)cm + k;
+            }
+            return cnt;
+        };
         for (int r = cons * NW + wp; r < n_rec; r += n_warps) {
-            const int4 rec = __ldcg(a.recs + r);          // {list head, voxel row, first pusher, its row mask}
-            int len = 0;
-            const int2 first2 = __ldcg(a.sub2 + (rec.z - 1));
-            for (int cur = rec.x; ;) {                    // sub2 of a node is requested together with the node itself
-                int2 nd, nd2;
-                if (cur == rec.z) { nd = make_int2(0, rec.w); nd2 = first2; }
-                else {
-                    LSS_DASSERT(cur >= 1 && cur <= d.n_points);
-                    nd = __ldcg(a.sub + (cur - 1)); nd2 = __ldcg(a.sub2 + (cur - 1));
-                    LSS_DASSERT(nd.y != 0 && nd.x != 0 && __ldcg(a.prow + (cur - 1)) == rec.y);
-                }
-                const unsigned m = (unsigned)nd.y;
-                const int cnt = __popc(m);
-                if (lane < cnt && len + lane < GCL_SHORT_CAP) {
-                    const unsigned k = __fns(m, 0, lane + 1);     // image-row offset of this lane's point
-                    w_key[len + lane] = (unsigned)nd2.y + k * (unsigned)d.fW;
-                    w_pix[len + lane] = (unsigned)nd2.x + k * (unsigned)d.fW;
-                    w_widx[len + lane] = (unsigned)(cur - 1) + k;
-                }
-                len += cnt;
-                if (cur == rec.z) break;
+            if ((r >> 5) >= __shfl_sync(LSS_FULL_MASK, q_cnt, r & (RP_QSHARDS - 1))) continue;      // beyond the end of its shard
+            const int4 rec = __ldcg(a.recs + r);          // {voxel row, previous pusher, the pusher that made the record, its row mask}
+            LSS_DASSERT(rec.x >= 0 && rec.x < d.B * vps && rec.y >= 1 && rec.y <= d.n_points && rec.z >= 1 && rec.z <= d.n_points);
+            const int2 nf = __ldcg(a.sub + (rec.y - 1));  // all of these are requested together
+            const int2 nf2 = __ldcg(a.sub2 + (rec.y - 1));
+            const int2 nc2 = __ldcg(a.sub2 + (rec.z - 1));
+            const int hd = (int)(unsigned)__ldcg(a.head + rec.x);
+            if (nf.x != 0) continue;                      // `previous` did not push first: the record of the second pusher covers the voxel
+            int len = take(rec.y - 1, (unsigned)nf.y, nf2, 0);
+            len += take(rec.z - 1, (unsigned)rec.w, nc2, len);
+            for (int cur = hd; cur != rec.z;) {           // sub-runs pushed after the second one (4 % of the shared voxels)
+                LSS_DASSERT(cur >= 1 && cur <= d.n_points);
+                const int2 nd = __ldcg(a.sub + (cur - 1)), nd2 = __ldcg(a.sub2 + (cur - 1));
+                LSS_DASSERT(nd.y != 0 && nd.x != 0 && __ldcg(a.prow + (cur - 1)) == rec.x);
+                len += take(cur - 1, (unsigned)nd.y, nd2, len);
                 cur = nd.x;
             }
             if (len >= GCL_SHORT_CAP) {                   // long voxel: for the whole CTA, after its warps are through
                 if (lane == 0) {
                     const int pos = atomicAdd(&s_nlong, 1);
-                    if (pos < GCL_LONG_CAP) s_longrec[pos] = rec;
-                    else a.recs[a.n_rec_cap - 1 - atomicAdd(a.counters + RPC_NLONG, 1)] = rec;      // (overflow: the last CTA)
+                    if (pos < GCL_LONG_CAP) s_longrow[pos] = rec.x;
+                    else a.longs[atomicAdd(a.counters + RPC_NLONG, 1)] = make_int4(rec.x, 0, 0, 0);      // (overflow: the last CTA)
                 }
                 continue;
             }
+            if (lane == 0) atomicAdd(&s_ndone, 1);
             __syncwarp();
             for (int i = lane; i < len; i += 32) {        // rank sort by flat point index (keys unique, len < 64)
                 const uint32_t e = w_key[i];
@@ -495,10 +522,10 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
                 }
                 __syncwarp();
             }
-            LSS_DASSERT(len >= 2 && rec.y >= 0 && rec.y < d.B * vps);
-            if (a.zero_target && lane == 0) spin_until(a.zero_done + (rec.y / vps) * RP_FLAG_STRIDE, a.zero_target, 200);
+            LSS_DASSERT(len >= 2);
+            if (a.zero_target && lane == 0) spin_until(a.zero_done + (rec.x / vps) * RP_FLAG_STRIDE, a.zero_target, 200);
             __syncwarp();
-            float *dst = a.bev + (size_t)rec.y * C + lane * CH;
+            float *dst = a.bev + (size_t)rec.x * C + lane * CH;
 #pragma unroll
             for (int c = 0; c < CH; ++c) dst[c] = acc[c];
         }
@@ -521,11 +548,12 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
     };
     uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn);
     float *s_prod = s_dyn + GCL_SORT_CAP;
-    auto sum_long = [&](const int4 rec) {
-        const int b = rec.y / vps;
+    auto sum_long = [&](const int row) {
+        const int b = row / vps;
+        const int hd = (int)(unsigned)__ldcg(a.head + row);
         if (threadIdx.x == 0) {                           // points of the voxel; room in the pool if they do not fit shared memory
-            int c = __popc((unsigned)rec.w);
-            for (int cur = rec.x; cur != rec.z;) { const int2 nd = __ldcg(a.sub + (cur - 1)); c += __popc((unsigned)nd.y); cur = nd.x; }
+            int c = 0;
+            for (int cur = hd; cur != 0;) { const int2 nd = __ldcg(a.sub + (cur - 1)); c += __popc((unsigned)nd.y); cur = nd.x; }
             s_len = c;
             s_pos = c > GCL_SORT_CAP ? atomicAdd(a.counters + RPC_POOL, c) : 0;
             LSS_DASSERT(c >= GCL_SHORT_CAP && s_pos >= 0 && s_pos + c <= d.n_points);
@@ -537,8 +565,8 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
         uint32_t *gk = a.pool + s_pos;
         if (threadIdx.x == 0) {
             uint32_t *out = in_smem ? s_keys : gk;
-            int i = expand_keys((unsigned)__ldcg(a.sub2 + (rec.z - 1)).y, (unsigned)rec.w, d.fW, out, 0, npt);
-            for (int cur = rec.x; cur != rec.z;) {
+            int i = 0;
+            for (int cur = hd; cur != 0;) {
                 const int2 nd = __ldcg(a.sub + (cur - 1));
                 i += expand_keys((unsigned)__ldcg(a.sub2 + (cur - 1)).y, (unsigned)nd.y, d.fW, out, i, npt);
                 cur = nd.x;
@@ -570,14 +598,15 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
                 for (int jj = 0; jj < cntp; ++jj) accc = __fadd_rn(accc, s_prod[jj * C + threadIdx.x]);
             __syncthreads();
         }
-        if ((int)threadIdx.x < C) a.bev[(size_t)rec.y * C + threadIdx.x] = accc;
+        if ((int)threadIdx.x < C) a.bev[(size_t)row * C + threadIdx.x] = accc;
         __syncthreads();
     };
     __syncthreads();
     const int n_long_cta = min(s_nlong, GCL_LONG_CAP);
-    for (int l = 0; l < n_long_cta; ++l) sum_long(s_longrec[l]);
+    for (int l = 0; l < n_long_cta; ++l) sum_long(s_longrow[l]);
     // ---- the last CTA to finish: the long voxels that did not fit a CTA's list, then the scratch of the forward is left clean
     if (threadIdx.x == 0) {
+        if (s_ndone) atomicAdd(a.counters + RPC_NSHARED, s_ndone);
         if (n_long_cta) atomicAdd(a.counters + RPC_NLONG_CTA, n_long_cta);
         __threadfence();
         s_last = atomicAdd(a.counters + RPC_FWD_DONE, 1) == a.n_cons - 1;
@@ -586,19 +615,21 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
     __syncthreads();
     if (!s_last) return;
     const int n_long = __ldcg(a.counters + RPC_NLONG);
-    for (int l = 0; l < n_long; ++l) sum_long(__ldcg(a.recs + (a.n_rec_cap - 1 - l)));
+    for (int l = 0; l < n_long; ++l) sum_long(__ldcg(a.longs + l).x);
     if (threadIdx.x == 0) {                               // every progress counter has been seen complete by a column CTA by now
-        a.counters[RPC_STAT] = n_rec; a.counters[RPC_STAT + 1] = n_long + atomicExch(a.counters + RPC_NLONG_CTA, 0);
-        a.counters[RPC_NREC] = 0; a.counters[RPC_NLONG] = 0; a.counters[RPC_POOL] = 0; a.counters[RPC_FWD_DONE] = 0; a.counters[RPC_PUB] = 0;
+        const int n_long_all = n_long + atomicExch(a.counters + RPC_NLONG_CTA, 0);
+        a.counters[RPC_STAT] = atomicExch(a.counters + RPC_NSHARED, 0) + n_long_all;
+        a.counters[RPC_STAT + 1] = n_long_all;
+        a.counters[RPC_NLONG] = 0; a.counters[RPC_POOL] = 0; a.counters[RPC_FWD_DONE] = 0;
         if (a.wait_ready) for (int i = 0; i < RP_READY_LINES; ++i) a.ready[i * RP_FLAG_STRIDE] = 0;
         if (a.zero_target) for (int i = 0; i < d.B; ++i) a.zero_done[i * RP_FLAG_STRIDE] = 0;
     }
 }
 
 // The forward grid.  [0, n_zero): zero CTAs (LSS_ZERO_ORDERED only).  [.., + n_keys): one CTA per camera column (bn, w): stage
-// the column's operands and plan, classify its sub-runs, queue the voxels it shares with other sub-runs, sum the EXCLUSIVE
-// ones from the staged operands and write their voxel rows.  [.., + n_cons): the shared voxels (shared_voxels_cta); these CTAs
-// come last in the grid, so everything they wait for is running or done when they start.
+// the column's operands and plan, find the sub-runs that are alone on their voxel's list (EXCLUSIVE), sum them from the staged
+// operands and write their voxel rows.  [.., + n_cons): the shared voxels, from the queue the index pass made (shared_voxels_cta):
+// they depend on nothing the column CTAs do and run next to them.
 template <int CPL>
 __global__ void __launch_bounds__(GCL_THREADS, 9)        // <= 56 registers: 8 column CTAs per SM next to the two zero CTAs
 k_fwd_columns(Dims d, FwdArgs a) {
@@ -617,7 +648,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
         if (threadIdx.x == 0) s_epoch = __ldcg(a.counters + RPC_EPOCH);
     }
     __syncthreads();
-    if ((int)blockIdx.x >= a.n_zero + a.n_keys) { shared_voxels_cta<CPL>(d, a, (int)blockIdx.x - a.n_zero - a.n_keys, s_dyn); return; }
+    if ((int)blockIdx.x >= a.n_zero + a.n_keys) { shared_voxels_cta<CPL>(d, a, (int)blockIdx.x - a.n_zero - a.n_keys, s_epoch, s_dyn); return; }
     tl_stamp(3, false);
     const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
     const int per = d.D * d.fH;
@@ -628,12 +659,10 @@ k_fwd_columns(Dims d, FwdArgs a) {
     float *s_ctx = s_dyn;                                 // [fH][C]
     float *s_prob = s_dyn + d.fH * C;                     // [D][fH]
     int *s_row = reinterpret_cast<int *>(s_prob + per);   // [per] voxel row
-    unsigned *s_aux = reinterpret_cast<unsigned *>(s_row + per);     // [per] row mask of an EXCLUSIVE leader / list head of a shared voxel's first pusher / 0
+    unsigned *s_aux = reinterpret_cast<unsigned *>(s_row + per);     // [per] row mask of an EXCLUSIVE leader / 0
     unsigned short *s_list = reinterpret_cast<unsigned short *>(s_aux + per);      // [per] slots of the EXCLUSIVE leaders
-    unsigned short *s_shared = s_list + per;              // [per] slots of the first pushers of shared voxels ...
-    unsigned *s_shmask = reinterpret_cast<unsigned *>(s_shared + per + (per & 1));    // [per] ... and their row masks
-    __shared__ int s_n, s_nshared;
-    if (threadIdx.x == 0) { s_n = 0; s_nshared = 0; }
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
     const unsigned long long tag = (unsigned long long)(unsigned)s_epoch << 32;
     const size_t base = (size_t)key * per;
     constexpr int SU = 3;                                 // slots per thread and round: their loads are all in flight together
@@ -646,7 +675,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
         const int i = threadIdx.x + u * GCL_THREADS;
         if (i < n_c4) { const int h = i / c4, q = i - h * c4; cv[u] = __ldcg(ctx_src + (size_t)h * d.fW * c4 + q); }
     }
-    __syncthreads();                                      // s_n, s_nshared
+    __syncthreads();                                      // s_n
     for (int i0 = 0; i0 < per; i0 += SU * GCL_THREADS) {  // stage the column's plan + weights, classify and compact its leaders
         int2 node[SU]; int row[SU]; float pw[SU]; unsigned long long hd[SU];
 #pragma unroll
@@ -677,12 +706,9 @@ k_fwd_columns(Dims d, FwdArgs a) {
                 unsigned aux = 0u;
                 if (hd[u] != 0ull) {
                     LSS_DASSERT((hd[u] >> 32) == (tag >> 32) && (unsigned)hd[u] >= 1u && (unsigned)hd[u] <= (unsigned)d.n_points);
-                    if (hd[u] == (tag | (unsigned long long)(base + i + 1))) aux = em = (unsigned)node[u].y;   // nobody pushed after it: EXCLUSIVE
-                    else {
-                        aux = (unsigned)hd[u];
-                        const int pos = atomicAdd(&s_nshared, 1);
-                        s_shared[pos] = (unsigned short)i; s_shmask[pos] = (unsigned)node[u].y;
-                    }
+                    // nobody pushed after it: EXCLUSIVE.  (Otherwise the voxel is shared: the index pass has queued it for the
+                    // shared-voxel CTAs at the end of this grid.)
+                    if (hd[u] == (tag | (unsigned long long)(base + i + 1))) aux = em = (unsigned)node[u].y;
                 }
                 s_aux[i] = aux;
             }
@@ -705,31 +731,15 @@ k_fwd_columns(Dims d, FwdArgs a) {
     }
     tl_mark(key, 1);
     __syncthreads();
-    if (threadIdx.x == 0) {                               // queue the shared voxels (one reservation per CTA), count the CTA in
-        const int n = s_nshared;
-        if (n) {
-            const int q0 = atomicAdd(a.counters + RPC_NREC, n);
-            LSS_DASSERT(q0 >= 0 && q0 + n <= a.n_rec_cap);
-            for (int r = 0; r < n; ++r) {
-                const int slot = (int)s_shared[r];
-                a.recs[q0 + r] = make_int4((int)s_aux[slot], s_row[slot], (int)(base + slot) + 1, (int)s_shmask[r]);
-            }
-            __threadfence();
-        }
-        atomicAdd(a.counters + RPC_PUB, 1);
-        if (a.zero_target)                                // the zeros of this sample's slab must be down before any row is written
-            spin_until(a.zero_done + b * RP_FLAG_STRIDE, a.zero_target, 400);
-    }
-    __syncthreads();
-    tl_mark(key, 2);
+    // The sums of the first GCL_PRE exclusive voxels of every group are made BEFORE the CTA waits for its sample's zeros: when
+    // the zero-fill is the last thing to finish, only the stores are left behind it.
     const int n_list = s_n;
     const float *my_ctx = s_ctx + gl * 4;
-    for (int i = g; __any_sync(LSS_FULL_MASK, i < n_list); i += GCL_NG) {
+    auto sum_exclusive = [&](int i, float (&acc)[CPL]) -> int {      // voxel row of leader i of the list (or -1), its sum in acc
         const bool live = i < n_list;
         const int s = live ? (int)s_list[i] : 0;
         const unsigned m = live ? s_aux[s] : 0u;
         const int h0 = s - (int)lss_div20((unsigned)s, a.mfH) * d.fH;
-        float acc[CPL];
 #pragma unroll
         for (int k = 0; k < CPL; ++k) acc[k] = 0.f;
         const float *wp_ = s_prob + s;
@@ -746,12 +756,28 @@ k_fwd_columns(Dims d, FwdArgs a) {
                 }
             }
         }
-        if (live) {
-            LSS_DASSERT(s_row[s] >= 0 && s_row[s] < d.B * d.nx * d.ny * d.nz && (m >> (d.fH - h0)) == 0u);
-            float4 *dst = reinterpret_cast<float4 *>(a.bev + (size_t)s_row[s] * C) + gl;
+        LSS_DASSERT(!live || (s_row[s] >= 0 && s_row[s] < d.B * d.nx * d.ny * d.nz && (m >> (d.fH - h0)) == 0u));
+        return live ? s_row[s] : -1;
+    };
+    auto store_row = [&](int row, const float (&acc)[CPL]) {
+        if (row < 0) return;
+        float4 *dst = reinterpret_cast<float4 *>(a.bev + (size_t)row * C) + gl;
 #pragma unroll
-            for (int q = 0; q < CPL / 4; ++q) dst[8 * q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-        }
+        for (int q = 0; q < CPL / 4; ++q) dst[8 * q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    };
+    float pre[GCL_PRE][CPL];
+    int pre_row[GCL_PRE];
+#pragma unroll
+    for (int t = 0; t < GCL_PRE; ++t) pre_row[t] = sum_exclusive(g + t * GCL_NG, pre[t]);
+    if (threadIdx.x == 0 && a.zero_target)                // the zeros of this sample's slab must be down before any row is written
+        spin_until(a.zero_done + b * RP_FLAG_STRIDE, a.zero_target, 400);
+    __syncthreads();
+    tl_mark(key, 2);
+#pragma unroll
+    for (int t = 0; t < GCL_PRE; ++t) store_row(pre_row[t], pre[t]);
+    for (int i = g + GCL_PRE * GCL_NG; __any_sync(LSS_FULL_MASK, i < n_list); i += GCL_NG) {
+        float acc[CPL];
+        store_row(sum_exclusive(i, acc), acc);
     }
     tl_mark(key, 3);
     tl_stamp(3, true);
@@ -800,9 +826,13 @@ extern "C" int lss_runplan_layout_init(const lss_problem *p, lss_runplan_layout 
     out->off_sub = off;        off += up((size_t)d.n_points * 8);
     out->off_sub2 = off;       off += up((size_t)d.n_points * 8);
     out->off_pool = off;       off += up((size_t)d.n_points * 4);
-    out->n_rec_cap = (int64_t)d.n_points / 2 + 2;         // a shared voxel holds at least two points
+    // one record per sub-run that is not the first on its voxel's list, in RP_QSHARDS interleaved sub-queues: room for the
+    // shard that gets one index CTA (<= 512 points) more than its share
+    out->n_rec_cap = (int64_t)d.n_points + RP_QSHARDS * 512 + 2;
     out->off_recs = off;       off += up((size_t)out->n_rec_cap * 16);
+    out->off_longs = off;      off += up(((size_t)d.n_points / GCL_SHORT_CAP + 2) * 16);
     out->off_counters = off;   off += up(64 * 4);
+    out->off_qcount = off;     off += up((size_t)RP_QSHARDS * RP_FLAG_STRIDE * 4);
     out->off_zero_done = off;  off += up((size_t)p->B * RP_FLAG_STRIDE * 4);
     out->off_ready = off;      off += up((size_t)RP_READY_LINES * RP_FLAG_STRIDE * 4);
     out->off_head = off;       off += up((size_t)out->n_voxels * 8);
@@ -862,7 +892,8 @@ static int launch_prologue(const lss_problem *p, const lss_runplan_layout *L, vo
         a.n_index = (a.rd.R + runs_per_cta - 1) / runs_per_cta;
         a.c = c;
         a.prow = (int32_t *)(w + L->off_prow); a.head = (unsigned long long *)(w + L->off_head);
-        a.sub = (int2 *)(w + L->off_sub); a.sub2 = (int2 *)(w + L->off_sub2);
+        a.sub = (int2 *)(w + L->off_sub); a.sub2 = (int2 *)(w + L->off_sub2); a.recs = (int4 *)(w + L->off_recs);
+        a.qcount = (unsigned long long *)(w + L->off_qcount);
     }
     size_t smem = a.n_zero ? ZERO_CHUNK : 0;
     if (dn != nullptr) {
@@ -956,7 +987,7 @@ extern "C" int lss_bev_zero(const lss_problem *p, float *bev, int part, int n_pa
 
 static size_t fwd_columns_smem(const lss_problem *p, bool zero) {
     const size_t per = (size_t)p->D * p->fH;
-    const size_t col = ((size_t)p->fH * p->C + 4 * per) * 4 + 2 * (per + 1) * 2 + 16;
+    const size_t col = ((size_t)p->fH * p->C + 3 * per) * 4 + (per + 1) * 2 + 16;
     const size_t shr = (size_t)(GCL_THREADS / 32) * (4 * GCL_SHORT_CAP + (size_t)GCL_ROWS * p->C) * 4;
     const size_t lng = ((size_t)GCL_SORT_CAP + (size_t)GCL_NG * p->C) * 4;
     size_t total = col > shr ? col : shr;
@@ -989,7 +1020,9 @@ static int launch_fwd_grid(const lss_problem *p, const lss_runplan_layout *L, vo
     a.prow = (const int32_t *)(w + L->off_prow); a.sub = (const int2 *)(w + L->off_sub); a.sub2 = (const int2 *)(w + L->off_sub2);
     a.head = (const unsigned long long *)(w + L->off_head);
     a.counters = (int32_t *)(w + L->off_counters); a.pool = (uint32_t *)(w + L->off_pool);
-    a.recs = (int4 *)(w + L->off_recs); a.n_rec_cap = (long long)L->n_rec_cap;
+    a.recs = (const int4 *)(w + L->off_recs); a.n_rec_cap = (long long)L->n_rec_cap;
+    a.qcount = (const unsigned long long *)(w + L->off_qcount);
+    a.longs = (int4 *)(w + L->off_longs);
     a.prob_col = prob_col; a.ctx_t = ctx_t; a.bev = bev;
     a.n_cons = 4 * rp_num_sms();                          // one warp per shared voxel, 4 warps per CTA
     const size_t smem = fwd_columns_smem(p, a.n_zero > 0);

@@ -405,14 +405,14 @@ class RunPlan:
 
     @property
     def counters(self):
-        """int32[8]: [0] epoch of the last build, [1..5] scratch (zero between launches), [6] / [7] voxels shared by several
-        sub-runs / voxels with >= 64 points met by the last forward."""
+        """int32[8]: [0] epoch of the last build, [6] / [7] voxels shared by
+        several sub-runs / voxels with >= 64 points summed by the last forward, the rest scratch (zero between launches)."""
         return self._view(self.layout.off_counters, 8, torch.int32)
 
     @property
     def scratch(self):
-        """What a forward uses as scratch (all-zero between launches): counters [1..5], the zero-fill progress counters and
-        the READY flags."""
+        """What a forward uses as scratch (all-zero between launches): counters [1..3] and [8..], the zero-fill progress counters
+        and the READY flags."""
         n = (self.layout.off_head - self.layout.off_zero_done) // 4
         c = self._view(self.layout.off_counters, 64, torch.int32)
         return torch.cat((c[1:6], c[8:], self._view(self.layout.off_zero_done, n, torch.int32)))
