@@ -382,7 +382,7 @@ struct FwdArgs {
     int wait_ready;                  // lss_liftsplat_forward: poll READY instead of waiting for the preceding grid to complete
     size_t seg_bytes;                // bytes of one sample's BEV slab
     int32_t *zero_done, *ready;      // [B][32], [32][32]
-    int n_keys, fWD, n_cons;         // camera columns B*N*fW; fW*D; shared-voxel CTAs at the end of the grid
+    int n_keys, fWD, n_cons, cons_first;   // camera columns B*N*fW; fW*D; shared-voxel CTAs; their place in the grid
     unsigned long long mfH;
     const int32_t *prow; const int2 *sub, *sub2; const unsigned long long *head;
     int32_t *counters; uint32_t *pool;
@@ -407,6 +407,108 @@ __device__ __forceinline__ void mul_add2(float &a0, float &a1, float w, float v0
     a0 = r.x; a1 = r.y;
 }
 
+// A voxel with >= 64 points, summed by a whole CTA.  Scratch (s_dyn): [SORT_CAP] keys, [NG][C] products.  Keys are sorted by the CTA
+// (shared memory up to SORT_CAP points, else in the pool), then NG points per pass: every group fetches one point's context
+// row and writes float32(prob*ctx) to shared memory (all loads in flight together); thread c adds the NG products of channel c
+// in ascending point order -- the same sequence of float32 additions as everywhere else.
+template <int CPL>
+__device__ __forceinline__ void sum_long_voxel(const Dims &d, const FwdArgs &a, const int row, float *s_dyn) {
+    constexpr int C = 8 * CPL;
+    __shared__ int s_len, s_pos;
+    const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
+    const int HWC = d.HW * C;
+    const int b = row / (d.nx * d.ny * d.nz);
+    auto decode = [&](unsigned pidx, int &ro, size_t &wi) {   // context row offset (floats) in the sample and prob_col index of a point
+        const unsigned cam = lss_div20(pidx, d.mDHW);
+        const unsigned rr = pidx - cam * d.DHW;
+        const unsigned dd = lss_div20(rr, d.mHW);
+        const unsigned hw = rr - dd * d.HW;
+        const unsigned h = lss_div20(hw, d.mfW), ww = hw - h * d.fW;
+        const unsigned bnn = (unsigned)b * d.N + cam;
+        ro = (int)(cam * HWC + hw * C);
+        wi = ((size_t)(bnn * d.fW + ww) * d.D + dd) * d.fH + h;
+    };
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn);
+    float *s_prod = s_dyn + GCL_SORT_CAP;
+    const int hd = (int)(unsigned)__ldcg(a.head + row);
+    if (threadIdx.x == 0) {                               // points of the voxel; room in the pool if they do not fit shared memory
+        int c = 0;
+        for (int cur = hd; cur != 0;) { const int2 nd = __ldcg(a.sub + (cur - 1)); c += __popc((unsigned)nd.y); cur = nd.x; }
+        s_len = c;
+        s_pos = c > GCL_SORT_CAP ? atomicAdd(a.counters + RPC_POOL, c) : 0;
+        LSS_DASSERT(c >= GCL_SHORT_CAP && s_pos >= 0 && s_pos + c <= d.n_points);
+        if (a.zero_target) spin_until(a.zero_done + b * RP_FLAG_STRIDE, a.zero_target, 200);
+    }
+    __syncthreads();
+    const int npt = s_len;
+    const bool in_smem = npt <= GCL_SORT_CAP;
+    uint32_t *gk = a.pool + s_pos;
+    if (threadIdx.x == 0) {
+        uint32_t *out = in_smem ? s_keys : gk;
+        int i = 0;
+        for (int cur = hd; cur != 0;) {
+            const int2 nd = __ldcg(a.sub + (cur - 1));
+            i += expand_keys((unsigned)__ldcg(a.sub2 + (cur - 1)).y, (unsigned)nd.y, d.fW, out, i, npt);
+            cur = nd.x;
+        }
+    }
+    __syncthreads();
+    if (in_smem) bitonic_sort_block(s_keys, npt);
+    else bitonic_sort_block((volatile uint32_t *)gk, npt);
+    __syncthreads();
+    const float *ctx_s = a.ctx_t + (size_t)b * d.N * HWC;
+    float accc = 0.f;
+    for (int p0 = 0; p0 < npt; p0 += GCL_NG) {
+        const int cntp = min(GCL_NG, npt - p0);
+        if (g < cntp) {
+            const unsigned pidx = in_smem ? s_keys[p0 + g] : ((volatile uint32_t *)gk)[p0 + g];
+            int ro; size_t wi;
+            decode(pidx, ro, wi);
+            const float w = __ldcg(a.prob_col + wi);
+            const float4 *rowp = reinterpret_cast<const float4 *>(ctx_s + ro + gl * 4);
+            float4 *dst = reinterpret_cast<float4 *>(s_prod + g * C) + gl;
+#pragma unroll
+            for (int q = 0; q < CPL / 4; ++q) {
+                const float4 v = __ldcg(rowp + 8 * q);
+                dst[8 * q] = make_float4(__fmul_rn(w, v.x), __fmul_rn(w, v.y), __fmul_rn(w, v.z), __fmul_rn(w, v.w));
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < C)
+            for (int jj = 0; jj < cntp; ++jj) accc = __fadd_rn(accc, s_prod[jj * C + threadIdx.x]);
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < C) a.bev[(size_t)row * C + threadIdx.x] = accc;
+    __syncthreads();
+}
+
+// End of a column / shared-voxel CTA.  The last CTA of the grid to get here sums the long voxels that did not fit a CTA's own
+// list and leaves the scratch of the forward clean: by then every CTA has seen the flags it waits for.
+template <int CPL>
+__device__ __forceinline__ void forward_cta_done(const Dims &d, const FwdArgs &a, float *s_dyn, int n_done, int n_long_cta) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (n_done) atomicAdd(a.counters + RPC_NSHARED, n_done);
+        if (n_long_cta) atomicAdd(a.counters + RPC_NLONG_CTA, n_long_cta);
+        __threadfence();
+        s_last = atomicAdd(a.counters + RPC_FWD_DONE, 1) == a.n_keys + a.n_cons - 1;
+        if (s_last) __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    const int n_long = __ldcg(a.counters + RPC_NLONG);
+    for (int l = 0; l < n_long; ++l) sum_long_voxel<CPL>(d, a, __ldcg(a.longs + l).x, s_dyn);
+    if (threadIdx.x == 0) {
+        const int n_long_all = n_long + atomicExch(a.counters + RPC_NLONG_CTA, 0);
+        a.counters[RPC_STAT] = atomicExch(a.counters + RPC_NSHARED, 0) + n_long_all;
+        a.counters[RPC_STAT + 1] = n_long_all;
+        a.counters[RPC_NLONG] = 0; a.counters[RPC_POOL] = 0; a.counters[RPC_FWD_DONE] = 0;
+        if (a.wait_ready) for (int i = 0; i < RP_READY_LINES; ++i) a.ready[i * RP_FLAG_STRIDE] = 0;
+        if (a.zero_target) for (int i = 0; i < d.B; ++i) a.zero_done[i * RP_FLAG_STRIDE] = 0;
+    }
+}
+
 // Shared voxels (several sub-runs on the voxel's list, about 5 % of the voxels: neighbouring columns at close range, the
 // overlap of neighbouring cameras), spread evenly over the last `n_cons` CTAs of the forward grid: one warp per voxel, from the
 // queue the index pass made -- every pusher that found a sub-run on the list before it queued {voxel, previous, itself, its row
@@ -423,10 +525,9 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
     constexpr int CH = C / 32;                            // channels per lane
     constexpr int PR = C / 4;                             // 16-byte pieces per context row
     constexpr int NW = GCL_THREADS / 32;
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, gl = lane & 7, g = threadIdx.x >> 3;
-    const int HWC = d.HW * C;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int vps = d.nx * d.ny * d.nz;                   // voxels per sample
-    __shared__ int s_nlong, s_ndone, s_last, s_len, s_pos;
+    __shared__ int s_nlong, s_ndone;
     __shared__ int s_longrow[GCL_LONG_CAP];
     if (threadIdx.x == 0) { s_nlong = 0; s_ndone = 0; }
     __syncthreads();
@@ -531,105 +632,16 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
         }
     }
     tl_stamp(4, true);
-    // ---- long voxels (>= 64 points) met by this CTA's warps, one at a time by the whole CTA.  Scratch: [SORT_CAP] keys, [NG][C]
-    // products.  Keys are sorted by the CTA (shared memory up to SORT_CAP points, else in the pool), then NG points per pass:
-    // every group fetches one point's context row and writes float32(prob*ctx) to shared memory (all loads in flight
-    // together); thread c adds the NG products of channel c in ascending point order -- the same sequence of float32
-    // additions as everywhere else.
-    auto decode = [&](unsigned pidx, int b, int &ro, size_t &wi) {   // context row offset (floats) in the sample and prob_col index of a point
-        const unsigned cam = lss_div20(pidx, d.mDHW);
-        const unsigned rr = pidx - cam * d.DHW;
-        const unsigned dd = lss_div20(rr, d.mHW);
-        const unsigned hw = rr - dd * d.HW;
-        const unsigned h = lss_div20(hw, d.mfW), ww = hw - h * d.fW;
-        const unsigned bnn = (unsigned)b * d.N + cam;
-        ro = (int)(cam * HWC + hw * C);
-        wi = ((size_t)(bnn * d.fW + ww) * d.D + dd) * d.fH + h;
-    };
-    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn);
-    float *s_prod = s_dyn + GCL_SORT_CAP;
-    auto sum_long = [&](const int row) {
-        const int b = row / vps;
-        const int hd = (int)(unsigned)__ldcg(a.head + row);
-        if (threadIdx.x == 0) {                           // points of the voxel; room in the pool if they do not fit shared memory
-            int c = 0;
-            for (int cur = hd; cur != 0;) { const int2 nd = __ldcg(a.sub + (cur - 1)); c += __popc((unsigned)nd.y); cur = nd.x; }
-            s_len = c;
-            s_pos = c > GCL_SORT_CAP ? atomicAdd(a.counters + RPC_POOL, c) : 0;
-            LSS_DASSERT(c >= GCL_SHORT_CAP && s_pos >= 0 && s_pos + c <= d.n_points);
-            if (a.zero_target) spin_until(a.zero_done + b * RP_FLAG_STRIDE, a.zero_target, 200);
-        }
-        __syncthreads();
-        const int npt = s_len;
-        const bool in_smem = npt <= GCL_SORT_CAP;
-        uint32_t *gk = a.pool + s_pos;
-        if (threadIdx.x == 0) {
-            uint32_t *out = in_smem ? s_keys : gk;
-            int i = 0;
-            for (int cur = hd; cur != 0;) {
-                const int2 nd = __ldcg(a.sub + (cur - 1));
-                i += expand_keys((unsigned)__ldcg(a.sub2 + (cur - 1)).y, (unsigned)nd.y, d.fW, out, i, npt);
-                cur = nd.x;
-            }
-        }
-        __syncthreads();
-        if (in_smem) bitonic_sort_block(s_keys, npt);
-        else bitonic_sort_block((volatile uint32_t *)gk, npt);
-        __syncthreads();
-        const float *ctx_s = a.ctx_t + (size_t)b * d.N * HWC;
-        float accc = 0.f;
-        for (int p0 = 0; p0 < npt; p0 += GCL_NG) {
-            const int cntp = min(GCL_NG, npt - p0);
-            if (g < cntp) {
-                const unsigned pidx = in_smem ? s_keys[p0 + g] : ((volatile uint32_t *)gk)[p0 + g];
-                int ro; size_t wi;
-                decode(pidx, b, ro, wi);
-                const float w = __ldcg(a.prob_col + wi);
-                const float4 *rowp = reinterpret_cast<const float4 *>(ctx_s + ro + gl * 4);
-                float4 *dst = reinterpret_cast<float4 *>(s_prod + g * C) + gl;
-#pragma unroll
-                for (int q = 0; q < CPL / 4; ++q) {
-                    const float4 v = __ldcg(rowp + 8 * q);
-                    dst[8 * q] = make_float4(__fmul_rn(w, v.x), __fmul_rn(w, v.y), __fmul_rn(w, v.z), __fmul_rn(w, v.w));
-                }
-            }
-            __syncthreads();
-            if ((int)threadIdx.x < C)
-                for (int jj = 0; jj < cntp; ++jj) accc = __fadd_rn(accc, s_prod[jj * C + threadIdx.x]);
-            __syncthreads();
-        }
-        if ((int)threadIdx.x < C) a.bev[(size_t)row * C + threadIdx.x] = accc;
-        __syncthreads();
-    };
     __syncthreads();
-    const int n_long_cta = min(s_nlong, GCL_LONG_CAP);
-    for (int l = 0; l < n_long_cta; ++l) sum_long(s_longrow[l]);
-    // ---- the last CTA to finish: the long voxels that did not fit a CTA's list, then the scratch of the forward is left clean
-    if (threadIdx.x == 0) {
-        if (s_ndone) atomicAdd(a.counters + RPC_NSHARED, s_ndone);
-        if (n_long_cta) atomicAdd(a.counters + RPC_NLONG_CTA, n_long_cta);
-        __threadfence();
-        s_last = atomicAdd(a.counters + RPC_FWD_DONE, 1) == a.n_cons - 1;
-        if (s_last) __threadfence();
-    }
-    __syncthreads();
-    if (!s_last) return;
-    const int n_long = __ldcg(a.counters + RPC_NLONG);
-    for (int l = 0; l < n_long; ++l) sum_long(__ldcg(a.longs + l).x);
-    if (threadIdx.x == 0) {                               // every progress counter has been seen complete by a column CTA by now
-        const int n_long_all = n_long + atomicExch(a.counters + RPC_NLONG_CTA, 0);
-        a.counters[RPC_STAT] = atomicExch(a.counters + RPC_NSHARED, 0) + n_long_all;
-        a.counters[RPC_STAT + 1] = n_long_all;
-        a.counters[RPC_NLONG] = 0; a.counters[RPC_POOL] = 0; a.counters[RPC_FWD_DONE] = 0;
-        if (a.wait_ready) for (int i = 0; i < RP_READY_LINES; ++i) a.ready[i * RP_FLAG_STRIDE] = 0;
-        if (a.zero_target) for (int i = 0; i < d.B; ++i) a.zero_done[i * RP_FLAG_STRIDE] = 0;
-    }
+    const int n_long_cta = min(s_nlong, GCL_LONG_CAP);    // long voxels met by this CTA's warps: one at a time by the whole CTA
+    for (int l = 0; l < n_long_cta; ++l) sum_long_voxel<CPL>(d, a, s_longrow[l], s_dyn);
+    forward_cta_done<CPL>(d, a, s_dyn, s_ndone, n_long_cta);
 }
 
-// The forward grid.  [0, n_zero): zero CTAs (LSS_ZERO_ORDERED only).  [.., + n_keys): one CTA per camera column (bn, w): stage
-// the column's operands and plan, find the sub-runs that are alone on their voxel's list (EXCLUSIVE), sum them from the staged
-// operands and write their voxel rows.  [.., + n_cons): the shared voxels, from the queue the index pass made (shared_voxels_cta):
-// they depend on nothing the column CTAs do and run next to them.
+// The forward grid.  [0, n_zero): zero CTAs (LSS_ZERO_ORDERED only).  [.., + n_cons): the shared voxels, from the queue the index
+// pass made (shared_voxels_cta): they depend on nothing the column CTAs do, are few and take the longest, so they get their SM
+// slots first.  [.., + n_keys): one CTA per camera column (bn, w): stage the column's operands and plan, find the sub-runs that
+// are alone on their voxel's list (EXCLUSIVE), sum them from the staged operands and write their voxel rows.
 template <int CPL>
 __global__ void __launch_bounds__(GCL_THREADS, 9)        // <= 56 registers: 8 column CTAs per SM next to the two zero CTAs
 k_fwd_columns(Dims d, FwdArgs a) {
@@ -648,11 +660,12 @@ k_fwd_columns(Dims d, FwdArgs a) {
         if (threadIdx.x == 0) s_epoch = __ldcg(a.counters + RPC_EPOCH);
     }
     __syncthreads();
-    if ((int)blockIdx.x >= a.n_zero + a.n_keys) { shared_voxels_cta<CPL>(d, a, (int)blockIdx.x - a.n_zero - a.n_keys, s_epoch, s_dyn); return; }
+    const int rel = (int)blockIdx.x - a.n_zero;
+    if (a.cons_first ? rel < a.n_cons : rel >= a.n_keys) { shared_voxels_cta<CPL>(d, a, a.cons_first ? rel : rel - a.n_keys, s_epoch, s_dyn); return; }
     tl_stamp(3, false);
     const int lane = threadIdx.x & 31, gl = lane & 7, g = threadIdx.x >> 3;
     const int per = d.D * d.fH;
-    const int key = (int)blockIdx.x - a.n_zero;           // camera column (bn, w)
+    const int key = a.cons_first ? rel - a.n_cons : rel;  // camera column (bn, w)
     const int bn = key / d.fW, w0 = key - bn * d.fW;
     const int b = bn / d.N;
     tl_mark(key, 0);
@@ -781,6 +794,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
     }
     tl_mark(key, 3);
     tl_stamp(3, true);
+    forward_cta_done<CPL>(d, a, s_dyn, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -996,8 +1010,15 @@ static size_t fwd_columns_smem(const lss_problem *p, bool zero) {
 }
 
 template <int CPL>
-static int launch_fwd_kernel(const Dims &d, const FwdArgs &a, size_t smem, bool pdl, cudaStream_t s) {
+static int launch_fwd_kernel(const Dims &d, FwdArgs a, size_t smem, bool pdl, cudaStream_t s) {
     if (smem > 48 * 1024 && cudaFuncSetAttribute(k_fwd_columns<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LSS_ERR_CUDA;
+    // Where the shared-voxel CTAs sit in the grid.  If the column CTAs fit the GPU in one wave they come first and the shared-voxel
+    // CTAs fill in as they leave (cfg 2: 53.2 against 54.0 us per step); if the columns need several waves anyway (big frusta:
+    // fewer CTAs per SM), the shared-voxel CTAs -- few, independent of the columns, the longest-running -- go first (cfg 4: 439
+    // against 496 us).
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd_columns<CPL>, GCL_THREADS, smem) != cudaSuccess) return LSS_ERR_CUDA;
+    a.cons_first = a.n_keys > per_sm * rp_num_sms() ? 1 : 0;
     if (lss_launch(k_fwd_columns<CPL>, dim3(a.n_zero + a.n_keys + a.n_cons), dim3(GCL_THREADS), smem, s, pdl, d, a) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
     return LSS_OK;
