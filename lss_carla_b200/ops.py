@@ -126,6 +126,15 @@ class Plan:
         item = torch.empty(0, dtype=dtype).element_size()
         return self.ws[off:off + n * item].view(dtype)
 
+    def scratch_rows(self, name, rows, device):
+        """Row workspace f32[rows, C] of the tile-plan kernels (compact voxel sums / gradient rows), allocated once per plan
+        (the kernels of one plan are stream-ordered: forward and backward never use the same buffer at the same time)."""
+        cache = self.__dict__.setdefault("_rows_cache", {})
+        t = cache.get(name)
+        if t is None or t.shape[0] < rows or t.device != device:
+            t = cache[name] = torch.empty((rows, self.prob.C), dtype=torch.float32, device=device)
+        return t
+
     @property
     def vox(self):
         return self._view(self.layout.off_vox, self.prob.n_points, torch.int32)
@@ -328,7 +337,7 @@ def splat_fwd(prob: Problem, plan: Plan, pr, ct, mode="sorted", channels_last=Fa
         raise RuntimeError("mode='sorted' needs a plan built with sorted=True")
     bev = out if out is not None else _empty_bev(prob, pr.device, channels_last)
     if voxel_sums is None and mode == "sorted" and variant != "warp" and prob.C in (32, 64, 128):
-        voxel_sums = torch.empty((plan.layout.n_rows_cap, prob.C), dtype=torch.float32, device=pr.device)
+        voxel_sums = plan.scratch_rows("voxel_sums", plan.layout.n_rows_cap, pr.device)    # plan-sized: kept with the plan, not per call
     check(lib().lss_splat_fwd(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), _ptr(pr), _ptr(ct),
                               _ptr(_prob_col(pr)), _ptr(voxel_sums), _ptr(bev),
                               SPLAT_MODES[mode], LAYOUT_CHANNELS_LAST if channels_last else LAYOUT_NCHW,
@@ -342,7 +351,7 @@ def splat_bwd(prob: Problem, plan: Plan, grad_bev, pr, ct, grad_rows=None, prob_
               batch_range=(0, 0)):
     g, layout = _bev_layout(_f32c_keep(grad_bev))
     if grad_rows is None and (layout == LAYOUT_NCHW or plan.sorted):
-        grad_rows = torch.empty((max(prob.n_voxels, plan.layout.n_rows_cap), prob.C), dtype=torch.float32, device=g.device)
+        grad_rows = plan.scratch_rows("grad_rows", max(prob.n_voxels, plan.layout.n_rows_cap), g.device)
     if out is None:
         out = torch.empty((prob.B * prob.N, prob.D + prob.C, prob.fH, prob.fW), dtype=torch.float32, device=g.device)
     if prob_col is None:
