@@ -296,7 +296,7 @@ typedef struct lss_runplan_layout {
  * use the tile plan (lss_plan_build + lss_splat_fwd) for such shapes.  Host-only. */
 int lss_runplan_layout_init(const lss_problem *p, lss_runplan_layout *out);
 /* Zero the counters and list heads of a freshly allocated workspace (build epochs keep them consistent afterwards;
- * the epoch is 32 bits wide: reset once more before 2^32 builds into the same workspace). */
+ * the forward tells builds apart by 31 bits of the epoch: reset once more before 2^31 builds into the same workspace). */
 int lss_runplan_reset(const lss_runplan_layout *L, void *workspace, void *stream);
 /* Build the run plan of one batch from calibration (replaces models.py:170-190 + :212-231).  Either the prepared
  * matrices M1 = inverse(post_rots), M2 = rots @ inverse(intrins) are given (bit-exact w.r.t. the reference's host

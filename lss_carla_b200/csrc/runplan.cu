@@ -337,8 +337,10 @@ __device__ __forceinline__ void prologue_cta_done(const PrologueArgs &a, int epo
     __threadfence();                                      // ... and ordered before the count
     if (atomicAdd(a.counters + RPC_PRO_DONE, 1) != a.n_index + a.n_lift - 1) return;
     __threadfence();                                      // the last CTA: everybody's writes are visible to it, and through
-    const int epoch = epoch0 + (a.n_index ? 1 : 0);       // READY (which carries the epoch of the plan to use) to the forward grid
-    if (a.ready) for (int i = 0; i < RP_READY_LINES; ++i) atomicExch(a.ready + i * RP_FLAG_STRIDE, epoch);
+    const int epoch = (int)((unsigned)epoch0 + (a.n_index ? 1u : 0u));   // READY carries the epoch of the plan to use, as (epoch & 0x7fffffff) + 1:
+    // non-zero (raised) for every epoch, an unbuilt plan (epoch 0: all-empty lists, a forward of zeros) included; the forward compares
+    // 31 bits of the epoch with the list heads' 32 -- enough to tell a build from the ones before it
+    if (a.ready) for (int i = 0; i < RP_READY_LINES; ++i) atomicExch(a.ready + i * RP_FLAG_STRIDE, (epoch & 0x7fffffff) + 1);
     a.counters[RPC_PRO_DONE] = 0;
     a.counters[RPC_EPOCH] = epoch;                        // every index CTA has read the old epoch
 }
@@ -534,7 +536,7 @@ __device__ __forceinline__ void shared_voxels_cta(const Dims &d, const FwdArgs &
     tl_stamp(4, false);
     // the sub-queues were filled by the index pass of the build this forward reads: lane s holds the count of shard s
     const unsigned long long q64 = __ldcg(a.qcount + lane * (RP_FLAG_STRIDE / 2));
-    const int q_cnt = (unsigned)(q64 >> 32) == (unsigned)epoch ? (int)(unsigned)q64 : 0;
+    const int q_cnt = ((unsigned)(q64 >> 32) & 0x7fffffffu) == ((unsigned)epoch & 0x7fffffffu) ? (int)(unsigned)q64 : 0;
     const int n_rec = __reduce_max_sync(LSS_FULL_MASK, q_cnt) * RP_QSHARDS;      // slots to look at (the tail of a short shard is skipped)
     {
         // per warp: keys, context-row numbers and weight indices of the voxel's points in list order [3][64], their order
@@ -654,7 +656,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
     }
     __shared__ int s_epoch;
     if (a.wait_ready) {                                   // the zero-fill grid is still streaming: only the plan + lift grid counts
-        if (threadIdx.x == 0) s_epoch = spin_until(a.ready + (blockIdx.x % RP_READY_LINES) * RP_FLAG_STRIDE, 1, 100);   // READY = the plan's epoch
+        if (threadIdx.x == 0) s_epoch = spin_until(a.ready + (blockIdx.x % RP_READY_LINES) * RP_FLAG_STRIDE, 1, 100) - 1;   // READY = the plan's epoch + 1
     } else {
         lss_pdl_wait();                                   // plan and lift operands come from the preceding kernel(s)
         if (threadIdx.x == 0) s_epoch = __ldcg(a.counters + RPC_EPOCH);
@@ -676,7 +678,8 @@ k_fwd_columns(Dims d, FwdArgs a) {
     unsigned short *s_list = reinterpret_cast<unsigned short *>(s_aux + per);      // [per] slots of the EXCLUSIVE leaders
     __shared__ int s_n;
     if (threadIdx.x == 0) s_n = 0;
-    const unsigned long long tag = (unsigned long long)(unsigned)s_epoch << 32;
+    const unsigned long long tag = (unsigned long long)((unsigned)s_epoch & 0x7fffffffu) << 32;      // (31 bits: see prologue_cta_done)
+    const unsigned long long tag_mask = 0x7fffffffffffffffull;
     const size_t base = (size_t)key * per;
     constexpr int SU = 3;                                 // slots per thread and round: their loads are all in flight together
     constexpr int c4 = C >> 2;
@@ -718,10 +721,10 @@ k_fwd_columns(Dims d, FwdArgs a) {
                 s_prob[i] = pw[u];
                 unsigned aux = 0u;
                 if (hd[u] != 0ull) {
-                    LSS_DASSERT((hd[u] >> 32) == (tag >> 32) && (unsigned)hd[u] >= 1u && (unsigned)hd[u] <= (unsigned)d.n_points);
+                    LSS_DASSERT(((hd[u] & tag_mask) >> 32) == (tag >> 32) && (unsigned)hd[u] >= 1u && (unsigned)hd[u] <= (unsigned)d.n_points);
                     // nobody pushed after it: EXCLUSIVE.  (Otherwise the voxel is shared: the index pass has queued it for the
                     // shared-voxel CTAs at the end of this grid.)
-                    if (hd[u] == (tag | (unsigned long long)(base + i + 1))) aux = em = (unsigned)node[u].y;
+                    if ((hd[u] & tag_mask) == (tag | (unsigned long long)(base + i + 1))) aux = em = (unsigned)node[u].y;
                 }
                 s_aux[i] = aux;
             }

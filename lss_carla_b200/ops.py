@@ -525,12 +525,12 @@ def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None
 
 @_nvtx("lss:forward(zero || lift+index || classify+gather)")
 def liftsplat_forward(prob: Problem, plan: RunPlan, depthnet_out, lift_out=None, out=None, frustum=None, trans=None, post_trans=None,
-                      M1=None, M2=None, rots=None, intrins=None, post_rots=None):
+                      M1=None, M2=None, rots=None, intrins=None, post_rots=None, _allow_unbuilt=False):
     """The whole forward of a step (lss_liftsplat_forward): three launches that run side by side -- zero-fill with progress
     counters, lift || plan build, classify + gather polling both.  `frustum` None: the plan in `plan` is kept (static calibration).
     Returns (bev, pr, ct); `bev` is channels_last, the same bits as splat_fwd(mode="sorted")."""
     build, args, res, keep = _prologue_args(prob, depthnet_out, lift_out, plan, frustum, trans, post_trans, M1, M2, rots, intrins, post_rots)
-    if not build and not plan.built:
+    if not build and not plan.built and not _allow_unbuilt:
         raise RuntimeError("liftsplat_forward without calibration needs a built plan")
     bev = out if out is not None else _empty_bev(prob, depthnet_out.device, True)
     if not bev.is_contiguous(memory_format=torch.channels_last):

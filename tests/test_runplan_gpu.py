@@ -357,3 +357,17 @@ def test_api_plan_cache_on_repeating_host_calibration():
     dev_cal = [batches[0][k].to(dev()) for k in ("rots", "trans", "intrins", "post_rots", "post_trans")]
     ls(batches[0]["depthnet_out"].to(dev()), *dev_cal)                                            # device calibration: not hashed, not cached
     assert ls.plan_cache_stats()["misses"] == 5
+
+
+def test_forward_on_an_unbuilt_plan_is_all_zero_and_does_not_hang():
+    """The C entry point cannot see whether the workspace holds a plan: a forward without calibration on a fresh (all-zero) workspace
+    must come back -- READY is raised for epoch 0 too -- with an all-zero BEV (empty lists), not spin until the 2 s trap."""
+    cfg = CONFIGS["tiny"]
+    dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    prob = problem_of(cfg, {"dx": dx, "bx": bx, "nx": nx})
+    rp = ops.RunPlan(prob, dev())
+    dn = make_batch(cfg, 0, "train")["depthnet_out"].to(dev())
+    bev = torch.full(prob.bev_shape, float("nan"), device=dev()).contiguous(memory_format=torch.channels_last)
+    ops.liftsplat_forward(prob, rp, dn, out=bev, _allow_unbuilt=True)
+    torch.cuda.synchronize()
+    assert not bev.any() and not rp.scratch.any()
