@@ -98,12 +98,20 @@ extern "C" int lss_debug_runplan_timeline(int on, unsigned long long *out_host) 
 #define RP_READY_LINES 32  // copies of READY (lss_liftsplat_forward: 1 once the plan and the lift operands of the step are
                            // complete); column CTA i polls copy i % 32, so that a thousand pollers do not queue on one L2 line
 
+// floor(x / divisor) for any 32-bit x, with m = ceil(2^64 / divisor), divisor >= 2: x*e < 2^64 for e = m*divisor - 2^64 < divisor.
+// (The index pass makes four runtime divisions per point; as library calls they were a quarter of its instructions.)
+__device__ __forceinline__ unsigned div_magic(unsigned x, unsigned long long m) { return m ? (unsigned)__umul64hi((unsigned long long)x, m) : x; }
+static inline unsigned long long magic_of(unsigned divisor) {      // 0 stands for divisor 1
+    return divisor < 2 ? 0ull : (unsigned long long)(((unsigned __int128)1 << 64) / divisor) + 1ull;
+}
+
 // thread -> point mapping of the index pass
 struct RunDims {
     int fH, RPW;        // runs per warp = 32 / fH
     int R;              // runs = B*N*fW*D
     int fWD;            // fW*D: runs per camera
     unsigned fmask;     // fH low bits
+    unsigned long long m_fH, m_fWD, m_D, m_N;      // magic_of(fH), (fW*D), (D), (N)
 };
 
 struct RunLane { int r, h, rw; bool valid; unsigned run_mask; };
@@ -111,7 +119,7 @@ struct RunLane { int r, h, rw; bool valid; unsigned run_mask; };
 __device__ __forceinline__ RunLane run_lane(const RunDims &rd, int cta, int u) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RunLane q;
-    q.rw = lane / rd.fH;
+    q.rw = (int)div_magic((unsigned)lane, rd.m_fH);
     q.h = lane - q.rw * rd.fH;
     const int wg = (cta * RP_WARPS + warp) * RP_U + u;
     q.r = wg * rd.RPW + q.rw;
@@ -133,7 +141,7 @@ __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, 
     tl_stamp(1, false);
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
     __shared__ unsigned s_epoch;
-    const int cam0 = (int)(((long long)cta * RP_WARPS * RP_U * rd.RPW) / rd.fWD);
+    const int cam0 = (int)div_magic((unsigned)(cta * RP_WARPS * RP_U * rd.RPW), rd.m_fWD);       // first run of the CTA < R < 2^31
     if (threadIdx.x == 32) s_epoch = (unsigned)__ldcg(counters + RPC_EPOCH) + 1u;     // this build's epoch (published by prologue_cta_done)
     if (RAW) {      // the calibration matrices of the few cameras this CTA touches, made on the fly (no extra launch)
         const int cam = cam0 + (int)threadIdx.x;
@@ -148,14 +156,14 @@ __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, 
         int row = -1;
         const size_t cm = (size_t)q.r * d.fH + q.h;
         if (q.valid) {
-            const int bn = q.r / rd.fWD, rem = q.r - bn * rd.fWD;
-            const int w = rem / d.D, dd = rem - w * d.D;
+            const int bn = (int)div_magic((unsigned)q.r, rd.m_fWD), rem = q.r - bn * rd.fWD;
+            const int w = (int)div_magic((unsigned)rem, rd.m_D), dd = rem - w * d.D;
             const int in_cam = (dd * d.fH + q.h) * d.fW + w;
             float g[3];
             if (RAW) ego_point(c, bn, in_cam, g, s_m[bn - cam0], s_m[bn - cam0] + 9);
             else ego_point(c, bn, in_cam, g);
             long long ii[3];
-            const int b = bn / d.N;
+            const int b = (int)div_magic((unsigned)bn, rd.m_N);
             if (voxel_of_point(d, b, g, ii) >= 0)
                 row = ((b * d.nx + (int)ii[0]) * d.ny + (int)ii[1]) * d.nz + (int)ii[2];
             prow[cm] = row;
@@ -816,6 +824,7 @@ static inline RunDims make_run_dims(const lss_problem *p) {
     rd.R = p->B * p->N * p->fW * p->D;
     rd.fWD = p->fW * p->D;
     rd.fmask = p->fH == 32 ? 0xFFFFFFFFu : ((1u << p->fH) - 1u);
+    rd.m_fH = magic_of((unsigned)p->fH); rd.m_fWD = magic_of((unsigned)rd.fWD); rd.m_D = magic_of((unsigned)p->D); rd.m_N = magic_of((unsigned)p->N);
     return rd;
 }
 
