@@ -194,7 +194,7 @@ def gpu_reference_run(cfg, dev, iters=3):
 # training metric (DDP)
 # ------------------------------------------------------------------------------------------------
 
-def train_measure(cfg, dev, local, rank, world, per_gpu, steps, warm, mode, inverse, channels_last=True, splat="ours"):
+def train_measure(cfg, dev, local, rank, world, per_gpu, steps, warm, mode, inverse, channels_last=True, splat="ours", amp=False):
     """samples/s of the training step (train_simbev.py:231-248: fwd + BCE + bwd + clip 5.0 + Adam) at `per_gpu` samples per
     rank, data-parallel over the ranks (DDP, NCCL all-reduce of the gradients; no collective inside the lift-splat)."""
     import contextlib
@@ -209,7 +209,7 @@ def train_measure(cfg, dev, local, rank, world, per_gpu, steps, warm, mode, inve
             calib = {"rots": rots, "trans": trans, "intrins": intrins, "post_rots": post_rots, "post_trans": post_trans}
             return T.liftsplat_forward(dn, model.frustum, calib, model.dx, model.bx, model.nx, dn.shape[1] - model.D)
     step = TrainStep(cfg, dev, splat_mode=mode, inverse_mode=inverse, splat_override=override, ddp=world > 1, local_rank=local,
-                     channels_last=channels_last)
+                     channels_last=channels_last, amp=amp)
     batches = [make_train_batch(cfg, per_gpu, 10 * rank + i, dev) for i in range(2)]
 
     def barrier():
@@ -233,6 +233,8 @@ def train_measure(cfg, dev, local, rank, world, per_gpu, steps, warm, mode, inve
     elapsed = timed(steps)
     out = {"samples_per_s": round(world * per_gpu * steps / elapsed, 2), "ms_per_step": round(elapsed / steps * 1e3, 3),
            "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "steps": steps, "warmup": warm}
+    if amp:
+        out["autocast"] = "bfloat16"
     if world > 1:
         nosync = timed(steps, step.net.no_sync)     # the same step without the gradient all-reduce
         out["ms_per_step_no_allreduce"] = round(nosync / steps * 1e3, 3)
@@ -583,7 +585,9 @@ def main():
                              "liblss_b200; DDP over the ranks, NCCL gradient all-reduce, no collective inside the lift-splat",
                      "weak": train_measure(tcfg, dev, local, rank, world, 8, args.train_steps, 4, "sorted", "device"),
                      "strong": train_measure(tcfg, dev, local, rank, world, max(1, 64 // world), max(4, args.train_steps // 2), 2,
-                                             "sorted", "device")}
+                                             "sorted", "device"),
+                     # the same step under bfloat16 autocast (AMP); the lift-splat reads the bfloat16 depthnet output
+                     "weak_amp_bf16": train_measure(tcfg, dev, local, rank, world, 8, args.train_steps, 4, "sorted", "device", amp=True)}
         except Exception as e:
             train = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 

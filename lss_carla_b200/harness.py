@@ -34,10 +34,12 @@ class TrainStep:
     """`channels_last`: BEV emitted in channels_last strides and BevEncode converted to that memory format (the faster
     layout end to end on B200, see models.install); `splat_override(model, depthnet_out, *calibration) -> BEV` replaces the
     lift-splat by something else -- the baseline arm passes the reference's stock ATen op chain here (measurement only: the
-    hook lives in this harness, not in the product's model code)."""
+    hook lives in this harness, not in the product's model code); `amp`: the forward and the loss under bfloat16 autocast
+    (the lift-splat then reads the bfloat16 depthnet output directly, `lss_lift_prepare_bf16`, accumulates in float32 and hands
+    BevEncode a float32 BEV; parameters, gradients and Adam stay float32 -- no loss scaling needed with bfloat16)."""
 
     def __init__(self, cfg, device, splat_mode="sorted", inverse_mode="device", splat_override=None, ddp=False,
-                 local_rank=0, seed=0, channels_last=True):
+                 local_rank=0, seed=0, channels_last=True, amp=False):
         torch.manual_seed(seed)                       # same initial weights on every rank (DDP broadcasts anyway)
         self.model = models.LiftSplatShoot(cfg.grid_conf, cfg.data_aug_conf, outC=1, splat_mode=splat_mode,
                                            inverse_mode=inverse_mode, bev_channels_last=channels_last).to(device)
@@ -56,11 +58,13 @@ class TrainStep:
         self.opt = torch.optim.Adam(self.net.parameters(), lr=1e-3, weight_decay=1e-7)
         self.loss_fn = nn.BCEWithLogitsLoss(pos_weight=torch.tensor([2.13], device=device))
         self.net.train()
+        self.amp = bool(amp)
 
     def __call__(self, batch):
         self.opt.zero_grad(set_to_none=True)
-        preds = self.net(batch["imgs"], batch["rots"], batch["trans"], batch["intrins"], batch["post_rots"], batch["post_trans"])
-        loss = self.loss_fn(preds, batch["binimgs"])
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            preds = self.net(batch["imgs"], batch["rots"], batch["trans"], batch["intrins"], batch["post_rots"], batch["post_trans"])
+            loss = self.loss_fn(preds.float(), batch["binimgs"])
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.net.parameters(), 5.0)
         self.opt.step()
