@@ -401,6 +401,16 @@ int lss_pipe_event_synchronize(void *event);
  * `record` (may be NULL).  Returns LSS_OK or LSS_ERR_CUDA. */
 int lss_pipe_stage(void *stream, void *wait_a, void *wait_b, int32_t n_copies, void *const *dst,
                    const void *const *src, const size_t *bytes, void *record);
+/* One whole pipelined step, enqueued with a single call (the host side of api.StepPipeline.run):
+ *   copy_in_stream:  wait ev_compute (the previous run of this step has read its inputs), copy in_bytes from pinned in_host to
+ *                    in_dev, record ev_in;
+ *   compute_stream:  wait ev_in and ev_done (the previous results have left the device), launch `graph_exec` (a cudaGraphExec_t
+ *                    holding the step's kernels, e.g. torch.cuda.CUDAGraph.raw_cuda_graph_exec()), record ev_compute;
+ *   copy_out_stream: wait ev_compute, copy out_bytes from out_dev to pinned out_host, record ev_done.
+ * All three events must have been recorded once before the first call.  Returns LSS_OK, LSS_ERR_BAD_ARG or LSS_ERR_CUDA. */
+int lss_pipe_step(void *copy_in_stream, void *compute_stream, void *copy_out_stream, void *graph_exec,
+                  void *ev_in, void *ev_compute, void *ev_done, void *in_dev, const void *in_host, size_t in_bytes,
+                  void *out_host, const void *out_dev, size_t out_bytes);
 
 #ifdef __cplusplus
 }

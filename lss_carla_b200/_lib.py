@@ -81,6 +81,7 @@ SIGNATURES = {
     "lss_pipe_event_synchronize": (C.c_int, [_P]),
     "lss_pipe_stage": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_size_t), _P]),
+    "lss_pipe_step": (C.c_int, [_P] * 9 + [C.c_size_t, _P, _P, C.c_size_t]),
     "lss_bev_clear": (C.c_int, [_PP, _P, _P]),
     "lss_runplan_layout_init": (C.c_int, [_PP, _PR]),
     "lss_runplan_reset": (C.c_int, [_PR, _P, _P]),

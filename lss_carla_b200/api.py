@@ -323,7 +323,7 @@ class StepPipeline:
     block (input gradient, BEV probe) on the copy-out stream, chained by events.  All instances of a group run their
     kernels on the SAME compute stream -- the kernels of different steps never interleave (co-scheduled steps were
     measured ~20 % slower per step than back-to-back ones) -- while the copies of the neighbouring steps overlap them on
-    the two copy engines.  The host side of a step is four foreign-function calls (lss_pipe_stage) and one graph launch.
+    the two copy engines.  The host side of a step is ONE foreign-function call (lss_pipe_step: event waits, the two copies, the graph launch).
     Every instance owns its device buffers and plan workspace; it may be re-run once its previous results have been
     consumed (`done.synchronize()`).  `host` comes from `pinned_step_buffers`."""
 
@@ -355,11 +355,6 @@ class StepPipeline:
         self._keep = (keep, x, cal)
 
         self.ev_in, self.ev_c, self.done = _Event(), _Event(), _Event()
-        P = C.c_void_p
-        self._in_args = ((P * 1)(self.in_dev.data_ptr()), (P * 1)(host["in_block"].data_ptr()),
-                         (C.c_size_t * 1)(host["in_block"].numel() * 4))
-        self._out_args = ((P * 1)(host["out_block"].data_ptr()), (P * 1)(self.out_dev.data_ptr()),
-                          (C.c_size_t * 1)(host["out_block"].numel() * 4))
         self._s = tuple(C.c_void_p(st.cuda_stream) for st in (streams.next_h2d(), streams.compute, streams.d2h))
         cs = streams.compute
         cs.wait_stream(torch.cuda.current_stream(dev))
@@ -372,23 +367,21 @@ class StepPipeline:
         with torch.cuda.graph(self.graph, stream=cs):
             compute()
         cs.synchronize()
-        for ev in (self.ev_c, self.done):              # "recorded and complete": the first run() must not wait
+        for ev in (self.ev_in, self.ev_c, self.done):  # "recorded and complete": the first run() must not wait
             check(self._lib.lss_pipe_stage(self._s[1], None, None, 0, None, None, None, ev.h), "lss_pipe_stage")
         cs.synchronize()
+        # the whole of run() as ONE foreign call: (copy-in stream, compute stream, copy-out stream, the graph's cudaGraphExec_t,
+        # events, input block, output block)
+        self._step_args = (self._s[0], self._s[1], self._s[2], C.c_void_p(int(self.graph.raw_cuda_graph_exec())),
+                           self.ev_in.h, self.ev_c.h, self.done.h,
+                           C.c_void_p(self.in_dev.data_ptr()), C.c_void_p(host["in_block"].data_ptr()),
+                           C.c_size_t(host["in_block"].numel() * 4),
+                           C.c_void_p(host["out_block"].data_ptr()), C.c_void_p(self.out_dev.data_ptr()),
+                           C.c_size_t(host["out_block"].numel() * 4))
 
     def run(self):
-        L, s = self._lib, self._s
-        # copy-in: after the previous run of this instance has read its inputs
-        st = L.lss_pipe_stage(s[0], self.ev_c.h, None, 1, *self._in_args, self.ev_in.h)
-        # compute: after the inputs have arrived and the previous results have left the device
-        st |= L.lss_pipe_stage(s[1], self.ev_in.h, self.done.h, 0, None, None, None, None)
-        if torch.cuda.current_stream(self.ls.device) == self.streams.compute:
-            self.graph.replay()
-        else:
-            with torch.cuda.stream(self.streams.compute):
-                self.graph.replay()
-        st |= L.lss_pipe_stage(s[1], None, None, 0, None, None, None, self.ev_c.h)
-        # copy-out
-        st |= L.lss_pipe_stage(s[2], self.ev_c.h, None, 1, *self._out_args, self.done.h)
+        # copy-in after the previous run of this instance has read its inputs; the kernels after the inputs have arrived and the
+        # previous results have left the device; copy-out after the kernels (lss_pipe_step, include/lss_b200.h)
+        st = self._lib.lss_pipe_step(*self._step_args)
         if st:
-            self._check(st, "lss_pipe_stage")
+            self._check(st, "lss_pipe_step")

@@ -189,6 +189,23 @@ extern "C" int lss_pipe_stage(void *stream, void *wait_a, void *wait_b, int32_t 
     return LSS_OK;
 }
 
+extern "C" int lss_pipe_step(void *copy_in_stream, void *compute_stream, void *copy_out_stream, void *graph_exec,
+                             void *ev_in, void *ev_compute, void *ev_done, void *in_dev, const void *in_host, size_t in_bytes,
+                             void *out_host, const void *out_dev, size_t out_bytes) {
+    LSS_REQUIRE(graph_exec && ev_in && ev_compute && ev_done && in_dev && in_host && out_host && out_dev, LSS_ERR_BAD_ARG);
+    cudaStream_t ci = (cudaStream_t)copy_in_stream, cs = (cudaStream_t)compute_stream, co = (cudaStream_t)copy_out_stream;
+    cudaEvent_t e_in = (cudaEvent_t)ev_in, e_c = (cudaEvent_t)ev_compute, e_done = (cudaEvent_t)ev_done;
+    bool ok = cudaStreamWaitEvent(ci, e_c, 0) == cudaSuccess
+           && cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, ci) == cudaSuccess
+           && cudaEventRecord(e_in, ci) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent(cs, e_in, 0) == cudaSuccess && cudaStreamWaitEvent(cs, e_done, 0) == cudaSuccess
+            && cudaGraphLaunch((cudaGraphExec_t)graph_exec, cs) == cudaSuccess && cudaEventRecord(e_c, cs) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent(co, e_c, 0) == cudaSuccess
+            && cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, co) == cudaSuccess
+            && cudaEventRecord(e_done, co) == cudaSuccess;
+    return ok ? LSS_OK : LSS_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------------------------------------
 // process-wide options (the only global state of the library)
 // ------------------------------------------------------------------------------------------------
