@@ -377,6 +377,14 @@ class RunPlanPath:
         self.forward_kept_plan(bs)
         self.backward(bs)
 
+    def forward_persistent(self, bs):    # the output tensor is kept between steps: only the rows the previous step wrote are cleared
+        bs.out["bev"], bs.out["pr"], bs.out["ct"] = self.ops.liftsplat_forward(self.prob, bs.plan, bs.dn, bs.lift_out, bs.bev_out,
+                                                                                 persistent=True, **self.plan_args(bs))
+
+    def step_persistent(self, bs):
+        self.forward_persistent(bs)
+        self.backward(bs)
+
 
 class TilePlanPath:
     """Reference memory format (NCHW) or the atomic / red modes: the tile-plan kernels of round 1."""
@@ -625,6 +633,13 @@ def main():
         alone["forward_kept_plan"] = time_kernel(path.forward_kept_plan, sets, kiters, stream)
         alone["one_launch_forward_from_plan(zero+classify+gather)"] = time_kernel(path.gather_with_zero, sets, kiters, stream)
         alone["step_kept_plan"] = time_kernel(path.step_kept_plan, sets, kiters, stream)
+        persist_err = None
+        try:      # opt-in mode, reported next to the headline (which zero-fills the whole tensor every step)
+            alone["forward_persistent_bev"] = time_kernel(path.forward_persistent, sets, kiters, stream)
+            alone["step_persistent_bev"] = time_kernel(path.step_persistent, sets, kiters, stream)
+        except Exception as e:
+            alone.pop("forward_persistent_bev", None)
+            persist_err = f"{type(e).__name__}: {e}"[:200]
 
     IN = 4 * cfg.B * cfg.N * (cfg.D + cfg.C) * fH * fW
     G = 4 * cfg.B * cfg.C * Z * X * Y
@@ -661,6 +676,16 @@ def main():
                                       "loader draws crop_w per SAMPLE (data_simbev.py:119-133, 128 values), so a batch of 8 repeats with "
                                       "probability 128^-8 -- a per-batch plan never hits there, and since the plan build runs next to the lift "
                                       "and the zero-fill it costs only the difference above: the headline `value` is the cold-plan step"}
+    if run and "step_persistent_bev" in alone:
+        ps = alone["step_persistent_bev"]
+        roof["persistent_bev"] = {"step_us": round(ps * 1e6, 2), "forward_us": round(alone["forward_persistent_bev"] * 1e6, 2),
+                                  "mpoints_per_s": round(cfg.points / ps / 1e6, 1), "bytes_cleared": 4 * cfg.C * v_hit,
+                                  "note": "NOT the headline: ops.liftsplat_forward(persistent=True) / lss_liftsplat_forward_persistent keep the "
+                                          "output tensor between steps and zero only the rows the previous step wrote (named by the plan that "
+                                          "is about to be overwritten) instead of the whole tensor -- same bits; for callers that own the "
+                                          "BEV buffer.  `value` above zero-fills all G bytes every step, as torch.zeros in models.py:240 does"}
+    elif run:
+        roof["persistent_bev"] = {"unavailable": persist_err}
     if run:     # the one bandwidth-bound piece: the zero-fill role (G bytes) timed alone
         roof["zero_fill"] = {"bytes": G, "us": round(alone["zero_fill"] * 1e6, 2), "frac": round(G / alone["zero_fill"] / 1e9 / peak, 4)}
 

@@ -347,6 +347,20 @@ int lss_liftsplat_forward(const lss_problem *p, const lss_runplan_layout *L, voi
                           const float *post_trans, const float *M1, const float *M2, const float *trans,
                           const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
                           float *prob, float *ctx_t, float *prob_col, float *bev, void *stream);
+/* The same forward into a PERSISTENT output tensor (no counterpart in the reference, whose voxel_pooling allocates a fresh
+ * torch.zeros tensor per call, models.py:240): `bev` must still hold what the previous lss_liftsplat_forward /
+ * lss_liftsplat_forward_persistent call on this workspace wrote -- or be all zero, with a workspace that has not been built since
+ * lss_runplan_reset.  Only the rows that call wrote can be non-zero, and the workspace still names them: the plan build zeroes
+ * exactly those (10 MB instead of the tensor's 82 MB at the benchmark configuration) before it overwrites the plan; with
+ * frustum == NULL (plan kept) the rows to be written are the rows that were written and nothing is cleared.  There is no
+ * zero-fill grid and nobody waits for zeros: two launches.  The result is bit-identical to lss_liftsplat_forward's.
+ * The caller owns the pairing of workspace and tensor; a tensor that anybody else wrote to must go through
+ * lss_liftsplat_forward (or lss_bev_zero + lss_runplan_reset) once. */
+int lss_liftsplat_forward_persistent(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                                     const float *post_trans, const float *M1, const float *M2, const float *trans,
+                                     const float *rots, const float *intrins, const float *post_rots,
+                                     const float *depthnet_out, float *prob, float *ctx_t, float *prob_col, float *bev,
+                                     void *stream);
 /* Backward to the depthnet output from a channels_last BEV gradient (tools.py:212-219 + autograd of models.py:58-59). */
 int lss_liftsplat_bwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,
                          const float *grad_bev, const float *prob_col, const float *ctx_t, float *grad_depthnet,

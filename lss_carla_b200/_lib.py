@@ -91,6 +91,7 @@ SIGNATURES = {
     "lss_liftsplat_prologue": (C.c_int, [_PP, _PR] + [_P] * 15),
     "lss_liftsplat_fwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, C.c_int, _P]),
     "lss_liftsplat_forward": (C.c_int, [_PP, _PR] + [_P] * 15),
+    "lss_liftsplat_forward_persistent": (C.c_int, [_PP, _PR] + [_P] * 15),
     "lss_liftsplat_bwd_cl": (C.c_int, [_PP, _PR, _P, _P, _P, _P, _P, _P]),
     "lss_splat_fwd": (C.c_int, [_PP, _PL, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "lss_splat_bwd": (C.c_int, [_PP, _PL, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -137,7 +137,7 @@ template <bool RAW>
 __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, const CalibPtrs &c, int32_t *__restrict__ prow,
                                               unsigned long long *__restrict__ head, int2 *__restrict__ sub, int2 *__restrict__ sub2,
                                               int4 *__restrict__ recs, unsigned long long *__restrict__ qcount,
-                                              const int32_t *__restrict__ counters, int cta) {
+                                              const int32_t *__restrict__ counters, int cta, float *__restrict__ clear_bev) {
     tl_stamp(1, false);
     __shared__ float s_m[RAW ? LSS_RAW_CAMS : 1][18];
     __shared__ unsigned s_epoch;
@@ -155,6 +155,14 @@ __device__ __forceinline__ void run_index_cta(const Dims &d, const RunDims &rd, 
         const RunLane q = run_lane(rd, cta, u);
         int row = -1;
         const size_t cm = (size_t)q.r * d.fH + q.h;
+        if (clear_bev != nullptr && q.valid) {            // persistent output: the previous build's sub-run leaders name the rows its
+            const int old_row = __ldcg(prow + cm);        // forward wrote -- zero them (the rest of the tensor is still zero).
+            const int old_mask = __ldcg(&sub[cm].y);      // (Measured: the warp clearing its leaders' rows together, 128 / C rows per
+            if (old_mask != 0 && old_row >= 0) {          // store instruction, is slower -- and slows the regular build by 0.5 us.)
+                float4 *dst = reinterpret_cast<float4 *>(clear_bev + (size_t)old_row * d.C);
+                for (int k = 0; k < (d.C >> 2); ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         if (q.valid) {
             const int bn = (int)div_magic((unsigned)q.r, rd.m_fWD), rem = q.r - bn * rd.fWD;
             const int w = (int)div_magic((unsigned)rem, rd.m_D), dd = rem - w * d.D;
@@ -335,6 +343,7 @@ struct PrologueArgs {
     int32_t *prow, *counters; unsigned long long *head, *qcount; int2 *sub, *sub2; int4 *recs;
     int n_lift; const float *dn; float *prob, *ctx_t, *prob_col;      // lift role (n_lift = 0: off)
     int32_t *ready;                                                   // != null: raise READY when lift + index are complete
+    float *clear_bev;                                                 // != null: the index role zeroes the rows the previous build's forward wrote
 };
 
 // `epoch0` (thread 0): the epoch of the plan in the workspace when this CTA started.
@@ -367,7 +376,7 @@ k_prologue(Dims d, PrologueArgs a) {
         lift_prepare_cta<float>(d, a.dn, a.prob, a.ctx_t, a.prob_col, cta, s_pro);
         tl_stamp(2, true);
     } else {
-        run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.head, a.sub, a.sub2, a.recs, a.qcount, a.counters, cta - a.n_lift);
+        run_index_cta<RAW>(d, a.rd, a.c, a.prow, a.head, a.sub, a.sub2, a.recs, a.qcount, a.counters, cta - a.n_lift, a.clear_bev);
     }
     prologue_cta_done(a, epoch0);
 }
@@ -901,13 +910,15 @@ static ZeroTune zero_tune(size_t seg_bytes, bool own_grid) {
 // `ready`: launched programmatically behind k_zero_flags (no dependence on it); the last lift / index CTA raises READY
 static int launch_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, bool index, const CalibPtrs &c, bool raw,
                            const float *dn, float *prob, float *ctx_t, float *prob_col, float *bev, size_t bev_bytes, bool ready,
-                           cudaStream_t s) {
+                           cudaStream_t s, bool clear_rows = false) {
     const Dims d = make_dims(p);
     PrologueArgs a = {};
     a.rd = make_run_dims(p);
     char *w = (char *)workspace;
     if (w != nullptr) a.counters = (int32_t *)(w + L->off_counters);
-    if (bev != nullptr && bev_bytes > 0) {      // two issuing CTAs per SM (one: 67.5 us per step at cfg 2 against 63)
+    if (clear_rows) {                           // persistent output: no zero role, the index role clears what the last forward wrote
+        a.clear_bev = index ? bev : nullptr;
+    } else if (bev != nullptr && bev_bytes > 0) {      // two issuing CTAs per SM (one: 67.5 us per step at cfg 2 against 63)
         a.bev = bev; a.bev_bytes = bev_bytes;
         a.n_zero = (int)min((size_t)2 * rp_num_sms(), (bev_bytes + ZERO_CHUNK - 1) / ZERO_CHUNK);
     }
@@ -933,7 +944,8 @@ static int launch_prologue(const lss_problem *p, const lss_runplan_layout *L, vo
     if (smem > 227 * 1024) return LSS_ERR_UNSUPPORTED;
     auto kern = raw ? k_prologue<true> : k_prologue<false>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LSS_ERR_CUDA;
-    if (lss_launch(kern, dim3(grid), dim3(RP_THREADS), smem, s, ready, d, a) != cudaSuccess) return LSS_ERR_CUDA;
+    // programmatic launch only behind k_zero_flags of the same call: behind anybody else's kernel the grid keeps stream order
+    if (lss_launch(kern, dim3(grid), dim3(RP_THREADS), smem, s, ready && !clear_rows, d, a) != cudaSuccess) return LSS_ERR_CUDA;
     LSS_CHECK_LAUNCH();
     return LSS_OK;
 }
@@ -972,7 +984,7 @@ static int prologue_validate(const lss_problem *p, const lss_runplan_layout *L, 
 static int prologue_checked(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
                             const float *post_trans, const float *M1, const float *M2, const float *trans,
                             const float *rots, const float *intrins, const float *post_rots, const float *depthnet_out,
-                            float *prob, float *ctx_t, float *prob_col, float *bev, bool ready, void *stream) {
+                            float *prob, float *ctx_t, float *prob_col, float *bev, bool ready, void *stream, bool clear_rows = false) {
     int st = prologue_validate(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,
                                prob_col, bev, ready);
     if (st != LSS_OK) return st;
@@ -981,7 +993,7 @@ static int prologue_checked(const lss_problem *p, const lss_runplan_layout *L, v
     const size_t bytes = (size_t)p->B * p->nz * p->C * p->nx * p->ny * 4;
     const CalibPtrs c{frustum, post_trans, M1, M2, trans, rots, intrins, post_rots};
     return launch_prologue(p, L, (L && workspace) ? workspace : nullptr, index, c, index && raw, depthnet_out, prob, ctx_t, prob_col, bev,
-                           bytes, ready, (cudaStream_t)stream);
+                           bytes, ready, (cudaStream_t)stream, clear_rows);
 }
 
 extern "C" int lss_liftsplat_prologue(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
@@ -1107,6 +1119,25 @@ extern "C" int lss_liftsplat_forward(const lss_problem *p, const lss_runplan_lay
                           prob_col, nullptr, true, stream);
     if (st != LSS_OK) return st;
     return launch_fwd_grid(p, L, workspace, prob_col, ctx_t, bev, t.n_cta, false, true, s);
+}
+
+// The same forward into a PERSISTENT output tensor: `bev` still holds what the previous lss_liftsplat_forward* call on this workspace
+// wrote (or is all zero, with a workspace that has not been built since lss_runplan_reset).  Nothing but the rows that call wrote
+// is non-zero, and the workspace still names them (the leaders of its sub-runs): the index role zeroes exactly those -- 10 MB
+// instead of the tensor's 82 MB at cfg 2 -- before it overwrites the plan; without a rebuild (frustum == NULL) the rows about to
+// be written are the rows that were written, and nothing is cleared at all.  No zero-fill grid, no waiting for zeros.
+extern "C" int lss_liftsplat_forward_persistent(const lss_problem *p, const lss_runplan_layout *L, void *workspace, const float *frustum,
+                                                const float *post_trans, const float *M1, const float *M2, const float *trans,
+                                                const float *rots, const float *intrins, const float *post_rots,
+                                                const float *depthnet_out, float *prob, float *ctx_t, float *prob_col, float *bev,
+                                                void *stream) {
+    int st = fwd_args_ok(p, L, workspace, prob_col, ctx_t, bev);
+    if (st != LSS_OK) return st;
+    LSS_REQUIRE(depthnet_out != nullptr, LSS_ERR_BAD_ARG);
+    st = prologue_checked(p, L, workspace, frustum, post_trans, M1, M2, trans, rots, intrins, post_rots, depthnet_out, prob, ctx_t,
+                          prob_col, bev, true, stream, true);
+    if (st != LSS_OK) return st;
+    return launch_fwd_grid(p, L, workspace, prob_col, ctx_t, bev, 0, false, true, (cudaStream_t)stream);
 }
 
 extern "C" int lss_liftsplat_bwd_cl(const lss_problem *p, const lss_runplan_layout *L, const void *workspace,

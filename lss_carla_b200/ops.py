@@ -389,6 +389,7 @@ class RunPlan:
         self.built = False
         self.busy = False
         self.generation = 0
+        self._bev_ref = self._bev_version = None      # the output tensor liftsplat_forward(persistent=True) is paired with
 
     def _view(self, off, n, dtype):
         item = torch.empty(0, dtype=dtype).element_size()
@@ -452,6 +453,7 @@ class RunPlan:
         return rows, pts, n_shared
 
     def reset(self):
+        self._bev_ref = self._bev_version = None
         check(lib().lss_runplan_reset(C.byref(self.layout), _ptr(self.ws), _stream()), "lss_runplan_reset")
 
 
@@ -473,6 +475,7 @@ def build_runplan(prob: Problem, frustum, trans, post_trans, M1=None, M2=None, r
           "lss_runplan_build")
     plan.built, plan._keepalive = True, (ts, mats)
     plan.generation += 1
+    plan._bev_ref = plan._bev_version = None           # rebuilt without clearing anybody's rows
     return plan
 
 
@@ -520,26 +523,38 @@ def liftsplat_prologue(prob: Problem, depthnet_out=None, lift_out=None, bev=None
     if build:
         plan.built, plan._keepalive = True, keep
         plan.generation += 1
+        plan._bev_ref = plan._bev_version = None
     return res
 
 
 @_nvtx("lss:forward(zero || lift+index || classify+gather)")
 def liftsplat_forward(prob: Problem, plan: RunPlan, depthnet_out, lift_out=None, out=None, frustum=None, trans=None, post_trans=None,
-                      M1=None, M2=None, rots=None, intrins=None, post_rots=None, _allow_unbuilt=False):
+                      M1=None, M2=None, rots=None, intrins=None, post_rots=None, _allow_unbuilt=False, persistent=False):
     """The whole forward of a step (lss_liftsplat_forward): three launches that run side by side -- zero-fill with progress
     counters, lift || plan build, classify + gather polling both.  `frustum` None: the plan in `plan` is kept (static calibration).
-    Returns (bev, pr, ct); `bev` is channels_last, the same bits as splat_fwd(mode="sorted")."""
+    Returns (bev, pr, ct); `bev` is channels_last, the same bits as splat_fwd(mode="sorted").
+
+    `persistent`: the output tensor is kept between calls (`out`, or a tensor the plan owns) and only the rows the previous call
+    wrote are cleared (lss_liftsplat_forward_persistent: no zero-fill of the whole tensor).  The plan remembers the tensor it is
+    paired with and holds a reference to it; the first call with another tensor, or after the plan was rebuilt by anything else,
+    takes the regular path once.  Nobody else may write to the tensor in between (in-place torch ops on it are detected)."""
     build, args, res, keep = _prologue_args(prob, depthnet_out, lift_out, plan, frustum, trans, post_trans, M1, M2, rots, intrins, post_rots)
     if not build and not plan.built and not _allow_unbuilt:
         raise RuntimeError("liftsplat_forward without calibration needs a built plan")
+    if persistent and out is None:
+        out = plan._bev_ref if plan._bev_ref is not None else _empty_bev(prob, depthnet_out.device, True)
     bev = out if out is not None else _empty_bev(prob, depthnet_out.device, True)
     if not bev.is_contiguous(memory_format=torch.channels_last):
         raise RuntimeError("liftsplat_forward writes channels_last tensors only")
-    check(lib().lss_liftsplat_forward(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), *args, _ptr(bev), _stream()),
-          "lss_liftsplat_forward")
+    paired = (persistent and plan._bev_ref is not None and plan._bev_ref.data_ptr() == bev.data_ptr()
+              and plan._bev_ref.shape == bev.shape and plan._bev_version == bev._version)
+    fn, what = (lib().lss_liftsplat_forward_persistent, "lss_liftsplat_forward_persistent") if paired else \
+               (lib().lss_liftsplat_forward, "lss_liftsplat_forward")
+    check(fn(C.byref(prob.c), C.byref(plan.layout), _ptr(plan.ws), *args, _ptr(bev), _stream()), what)
     if build:
         plan.built, plan._keepalive = True, keep
         plan.generation += 1
+    plan._bev_ref, plan._bev_version = (bev, bev._version) if persistent else (None, None)
     return bev, res[0], res[1]
 
 

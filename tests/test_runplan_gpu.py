@@ -371,3 +371,51 @@ def test_forward_on_an_unbuilt_plan_is_all_zero_and_does_not_hang():
     ops.liftsplat_forward(prob, rp, dn, out=bev, _allow_unbuilt=True)
     torch.cuda.synchronize()
     assert not bev.any() and not rp.scratch.any()
+
+
+@pytest.mark.parametrize("cfg_name,B", [("cfg2", 8), ("cfg1", 1), ("tiny", 2), ("cfg4", 1)])
+def test_persistent_output_forward_clears_only_the_previous_rows(cfg_name, B):
+    """lss_liftsplat_forward_persistent: the output tensor is kept between calls and only the rows the previous call wrote are
+    zeroed (by the plan build, from the plan it is about to overwrite).  Over a sequence of different calibrations and depthnet
+    outputs -- rebuilds, kept-plan calls, a tensor nobody has paired with the plan yet, an in-place modification by somebody else,
+    a plan rebuilt behind its back -- every result must be the regular forward's, bit for bit over the whole tensor."""
+    cfg = dataclasses.replace(CONFIGS[cfg_name], B=B)
+    dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    prob = problem_of(cfg, {"dx": dx, "bx": bx, "nx": nx})
+    fr = cu(O.create_frustum(cfg.final_dim, list(cfg.dbound)))
+    rp, ref_rp = ops.RunPlan(prob, dev()), ops.RunPlan(prob, dev())
+    bev = torch.full(prob.bev_shape, float("nan"), device=dev()).contiguous(memory_format=torch.channels_last)
+    calls = []
+
+    def run(seed, mode, rebuild=True):
+        b = make_batch(cfg, seed, mode)
+        args = dict(trans=b["trans"].to(dev()).reshape(-1, 3), post_trans=b["post_trans"].to(dev()).reshape(-1, 3),
+                    rots=b["rots"].to(dev()), intrins=b["intrins"].to(dev()), post_rots=b["post_rots"].to(dev()))
+        dn = b["depthnet_out"].to(dev())
+        paired = rp._bev_ref is not None and rp._bev_ref.data_ptr() == bev.data_ptr() and rp._bev_version == bev._version
+        calls.append(paired)
+        if rebuild:
+            got, _, _ = ops.liftsplat_forward(prob, rp, dn, None, bev, fr, persistent=True, **args)
+            want, _, _ = ops.liftsplat_forward(prob, ref_rp, dn, None, None, fr, **args)
+        else:               # plan kept: only the depthnet output changes
+            got, _, _ = ops.liftsplat_forward(prob, rp, dn, None, bev, persistent=True)
+            want, _, _ = ops.liftsplat_forward(prob, ref_rp, dn, None, None)
+        assert got.data_ptr() == bev.data_ptr()
+        assert torch.equal(got, want), (seed, mode, rebuild)
+        assert not rp.scratch.any()
+
+    run(0, "train")                      # not paired yet: the regular path, zero-fill of the NaN tensor included
+    run(1, "full")                       # paired: rows of call 0 cleared by the build of call 1
+    run(2, "eval")
+    run(3, "train", rebuild=False)       # kept plan: nothing to clear
+    run(4, "full")
+    assert calls == [False, True, True, True, True]
+    bev.add_(1.0)                        # somebody else wrote to the tensor: detected, one regular call
+    run(5, "train")
+    run(6, "full")
+    b9 = make_batch(cfg, 9, "train")       # the plan rebuilt by somebody else: detected, one regular call
+    ops.build_runplan(prob, fr, b9["trans"].to(dev()).reshape(-1, 3), b9["post_trans"].to(dev()).reshape(-1, 3), rots=b9["rots"].to(dev()),
+                      intrins=b9["intrins"].to(dev()), post_rots=b9["post_rots"].to(dev()), plan=rp)
+    run(7, "eval")
+    run(8, "train")
+    assert calls[5:] == [False, True, False, True]
