@@ -777,6 +777,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
         for (int k = 0; k < CPL; ++k) acc[k] = 0.f;
         const float *wp_ = s_prob + s;
         const float *rowp0 = my_ctx + h0 * C;
+#pragma unroll 8
         for (int j = 0; j < d.fH; ++j) {
             if ((m >> j) & 1u) {                          // bit j set => image row h0 + j < fH of the same run
                 const float wj = wp_[j];

@@ -81,6 +81,13 @@ def main():
             return
         _, s.pr, s.ct = ops.liftsplat_forward(prob, s.rp, s.dn, s.lift, s.bev, fr, **cal_args(s))
 
+    def forward_persistent(s):   # output tensor kept between steps: only the rows of the previous step are cleared
+        _, s.pr, s.ct = ops.liftsplat_forward(prob, s.rp, s.dn, s.lift, s.bev, fr, persistent=True, **cal_args(s))
+
+    def step_persistent(s):
+        forward_persistent(s)
+        bwd(s)
+
     def forward_kept(s):
         _, s.pr, s.ct = ops.liftsplat_forward(prob, s.rp, s.dn, s.lift, s.bev)
 
@@ -145,7 +152,7 @@ def main():
     res = {"workload": name}
     for nm, fn in (("plan", plan), ("lift", lift), ("zero", zero), ("prologue(lift+plan)", prologue), ("fwd_precleared", fwd_precleared),
                    ("fwd_ordered", fwd_ordered), ("bwd", bwd), ("forward", forward), ("forward_fork_memset", forward_fork("memset")), ("forward_fork_fill", forward_fork("fill")), ("forward_kept_plan", forward_kept), ("step", step),
-                   ("step_kept_plan", step_kept)):
+                   ("step_kept_plan", step_kept), ("forward_persistent", forward_persistent), ("step_persistent", step_persistent)):
         res[nm + "_us"] = round(timeit(fn), 2)
     res["mpoints_per_s"] = round(cfg.points / res["step_us"], 1)
     res["counters"] = sets[0].rp.counters.cpu().tolist()
@@ -162,7 +169,7 @@ def main():
     for s in sets:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            (fwd_ordered if os.environ.get("QUICK_TL") == "ordered" else step)(s)
+            {"ordered": fwd_ordered, "persistent": step_persistent}.get(os.environ.get("QUICK_TL"), step)(s)
         graphs.append(g)
     for i in range(12):
         graphs[i % 4].replay()
