@@ -729,6 +729,7 @@ k_fwd_columns(Dims d, FwdArgs a) {
                 hd[u] = __ldcg(a.head + row[u]);
             }
         }
+        unsigned hb[SU];                                  // which lanes hold an EXCLUSIVE leader in slot u
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
             const int i = i0 + u * GCL_THREADS + threadIdx.x;
@@ -745,12 +746,19 @@ k_fwd_columns(Dims d, FwdArgs a) {
                 }
                 s_aux[i] = aux;
             }
-            const unsigned hb = __ballot_sync(LSS_FULL_MASK, em != 0u);
-            int wbase = 0;
-            if (lane == 0 && hb) wbase = atomicAdd(&s_n, __popc(hb));
-            wbase = __shfl_sync(LSS_FULL_MASK, wbase, 0);
-            LSS_DASSERT(em == 0u || wbase + __popc(hb) <= per);
-            if (em != 0u) s_list[wbase + __popc(hb & ((1u << lane) - 1u))] = (unsigned short)i;
+            hb[u] = __ballot_sync(LSS_FULL_MASK, em != 0u);
+        }
+        int total = 0;                                    // one reservation in the CTA's list for the warp's leaders of all SU slots
+#pragma unroll
+        for (int u = 0; u < SU; ++u) total += __popc(hb[u]);
+        int wbase = 0;
+        if (lane == 0 && total) wbase = atomicAdd(&s_n, total);
+        wbase = __shfl_sync(LSS_FULL_MASK, wbase, 0);
+        LSS_DASSERT(wbase + total <= per);
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            if ((hb[u] >> lane) & 1u) s_list[wbase + __popc(hb[u] & ((1u << lane) - 1u))] = (unsigned short)(i0 + u * GCL_THREADS + threadIdx.x);
+            wbase += __popc(hb[u]);
         }
     }
 #pragma unroll
